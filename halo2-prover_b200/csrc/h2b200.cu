@@ -1,0 +1,1045 @@
+// h2b200.cu -- context, launch planning and the C ABI of libh2b200.so (see include/h2b200.h).
+//
+// Everything arithmetic runs on the device.  The host side only plans launches,
+// owns the workspace / SRS / twiddle caches and moves bytes.  There is no CPU
+// implementation of the MSM or the NTT in this library and no fallback: a missing
+// or failing GPU surfaces as H2B_ERR_CUDA.
+#include "../../include/h2b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "curve.cuh"
+#include "field.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace h2b;
+
+static_assert(sizeof(Fe) == 32, "Fr/Fq must be 32 bytes (4 x u64)");
+static_assert(sizeof(Affine) == 64, "G1Affine must be 64 bytes");
+static_assert(sizeof(Jacobian) == 96, "G1 must be 96 bytes");
+static_assert(sizeof(XYZZ) == 128, "bucket must be 128 bytes");
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+
+enum BufId {
+    BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_OFFSETS, BUF_CURSOR, BUF_TASKOFF, BUF_SORTED,
+    BUF_BUCKETS, BUF_PARTIALS, BUF_WINDOWS, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
+    BUF_NTT_OUT, BUF_MISC,
+    BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
+};
+
+struct TwKey {
+    uint64_t w[4];
+    uint32_t log_n;
+    bool operator<(const TwKey &o) const {
+        int c = memcmp(w, o.w, sizeof w);
+        if (c) return c < 0;
+        return log_n < o.log_n;
+    }
+};
+struct Srs {
+    Affine *d = nullptr;
+    size_t n = 0;
+};
+
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    void *buf[BUF_COUNT] = {};
+    size_t cap[BUF_COUNT] = {};
+    std::map<uint64_t, Srs> srs;
+    uint64_t next_handle = 1;
+    std::map<TwKey, Fe *> twiddles;
+    size_t twiddle_bytes = 0;
+    std::map<uint64_t, h2b_domain> domains;
+    uint64_t launches = 0;
+    uint32_t msm_window = 0;
+    int timing = 0;
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    std::vector<cudaEvent_t> tev0, tev1;  // timing event pairs
+    uint32_t tev_used = 0;
+    int sm_count = 148;
+};
+Ctx *g = nullptr;
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+    char tmp[512];
+    if (e != cudaSuccess) snprintf(tmp, sizeof tmp, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(tmp, sizeof tmp, "%s", what);
+    g_err = tmp;
+    return code;
+}
+#define CU(call)                                                             \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return fail(H2B_ERR_CUDA, #call, e__);       \
+    } while (0)
+#define LAUNCHED()                                                           \
+    do {                                                                     \
+        g->launches++;                                                       \
+        cudaError_t e__ = cudaGetLastError();                                \
+        if (e__ != cudaSuccess) return fail(H2B_ERR_CUDA, "kernel launch", e__); \
+    } while (0)
+#define TRY(expr)                        \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != H2B_OK) return rc__; \
+    } while (0)
+
+int ensure_ctx() {
+    if (g) return H2B_OK;
+    return fail(H2B_ERR_STATE, "h2b_init has not been called");
+}
+
+int get_buf(BufId id, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (g->cap[id] < bytes) {
+        if (g->buf[id]) {
+            CU(cudaDeviceSynchronize());  // work on any stream may still reference it
+            CU(cudaFree(g->buf[id]));
+            g->buf[id] = nullptr;
+            g->cap[id] = 0;
+        }
+        size_t want = bytes + bytes / 8;  // a little headroom against regrowth
+        cudaError_t e = cudaMalloc(&g->buf[id], want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&g->buf[id], want);
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(H2B_ERR_OOM, "cudaMalloc(workspace)", e);
+        }
+        g->cap[id] = want;
+    }
+    *out = g->buf[id];
+    return H2B_OK;
+}
+
+// The workspace is shared by every call, so work submitted on different streams is chained:
+// a call on stream B waits for the previous call's work on stream A.
+int enter(cudaStream_t s) {
+    if (g->last_stream && g->last_stream != s) CU(cudaStreamWaitEvent(s, g->last_done, 0));
+    return H2B_OK;
+}
+int leave(cudaStream_t s, int rc) {
+    if (cudaEventRecord(g->last_done, s) == cudaSuccess) g->last_stream = s;
+    return rc;
+}
+
+constexpr uint32_t kMaxTimed = 256;
+void time_begin(cudaStream_t s) {
+    if (!g->timing || g->tev_used >= kMaxTimed) return;
+    if (g->tev0.size() <= g->tev_used) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        g->tev0.push_back(a);
+        g->tev1.push_back(b);
+    }
+    cudaEventRecord(g->tev0[g->tev_used], s);
+}
+void time_end(cudaStream_t s) {
+    if (!g->timing || g->tev_used >= kMaxTimed || g->tev0.size() <= g->tev_used) return;
+    cudaEventRecord(g->tev1[g->tev_used], s);
+    g->tev_used++;
+}
+
+// ------------------------------------------------------------------------------ MSM
+uint32_t ceil_log2(size_t n) {
+    uint32_t l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return l;
+}
+
+MsmCfg msm_plan(size_t n) {
+    MsmCfg cfg{};
+    cfg.n = (uint32_t)n;
+    uint32_t lg = ceil_log2(n);
+    uint32_t c = g->msm_window ? g->msm_window : (lg > 4 ? lg - 4 : 0);
+    if (!g->msm_window) {
+        if (c < 4) c = 4;
+        if (c > 16) c = 16;
+    }
+    if (c < 2) c = 2;
+    if (c > 22) c = 22;
+    cfg.c = c;
+    uint32_t W = (254 + c - 1) / c;
+    uint32_t top_bits = 254 - (W - 1) * c;
+    if (top_bits > c - 1) W += 1;  // the (unsigned) top digit plus carry must fit 2^(c-1)
+    cfg.windows = W;
+    cfg.bpw = 1u << (c - 1);
+    cfg.nb = W * cfg.bpw;
+    uint32_t t = 256;
+    while ((size_t)t * t < n) t <<= 1;
+    cfg.task = t;
+    uint32_t lgrp = 0;  // groups of 2^lgrp buckets, at most 256 groups per window
+    while ((cfg.bpw >> lgrp) > 256) lgrp++;
+    cfg.lgrp = lgrp;
+    return cfg;
+}
+
+int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_out, cudaStream_t s) {
+    if (n == 0) {
+        // G1::identity() = (0, R, 0)
+        Jacobian id;
+        memset(&id, 0, sizeof id);
+        const uint32_t one[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                                 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        memcpy(id.y.l, one, sizeof one);
+        CU(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));  // `id` lives on this stack frame
+        return H2B_OK;
+    }
+    if (n > (1u << 30)) return fail(H2B_ERR_ARG, "msm: n > 2^30 not supported");
+    MsmCfg cfg = msm_plan(n);
+    size_t entries = (size_t)n * cfg.windows;
+    size_t max_tasks = (size_t)cfg.nb + entries / cfg.task + 1;
+    uint32_t *counts, *offsets, *cursor, *task_off, *sorted;
+    XYZZ *buckets, *partials, *windows;
+    TRY(get_buf(BUF_COUNTS, (size_t)cfg.nb * 4, (void **)&counts));
+    TRY(get_buf(BUF_OFFSETS, (size_t)cfg.nb * 4, (void **)&offsets));
+    TRY(get_buf(BUF_CURSOR, (size_t)cfg.nb * 4, (void **)&cursor));
+    TRY(get_buf(BUF_TASKOFF, ((size_t)cfg.nb + 1) * 4, (void **)&task_off));
+    TRY(get_buf(BUF_SORTED, entries * 4, (void **)&sorted));
+    TRY(get_buf(BUF_BUCKETS, (size_t)cfg.nb * sizeof(XYZZ), (void **)&buckets));
+    TRY(get_buf(BUF_PARTIALS, max_tasks * sizeof(XYZZ), (void **)&partials));
+    TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
+
+    CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
+    CU(cudaMemsetAsync(buckets, 0, (size_t)cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
+    uint32_t nblk = (uint32_t)((n + 255) / 256);
+    msm_digits_kernel<0><<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, nullptr);
+    LAUNCHED();
+    msm_scan_kernel<<<1, 1024, 0, s>>>(counts, cfg.nb, cfg.task, offsets, cursor, task_off);
+    LAUNCHED();
+    msm_digits_kernel<1><<<nblk, 256, 0, s>>>(d_scalars, cfg, cursor, sorted);
+    LAUNCHED();
+    time_begin(s);
+    msm_accumulate_kernel<<<(uint32_t)((max_tasks + 127) / 128), 128, 0, s>>>(
+        d_bases, sorted, offsets, counts, task_off, cfg, buckets, partials);
+    LAUNCHED();
+    time_end(s);
+    msm_combine_kernel<<<(cfg.nb + 127) / 128, 128, 0, s>>>(counts, task_off, cfg, partials, buckets);
+    LAUNCHED();
+    uint32_t G = cfg.bpw >> cfg.lgrp;
+    msm_reduce_kernel<<<cfg.windows, G, G * sizeof(XYZZ), s>>>(buckets, cfg, windows);
+    LAUNCHED();
+    msm_final_kernel<<<1, 32, 0, s>>>(windows, cfg, d_out);
+    LAUNCHED();
+    return H2B_OK;
+}
+
+// ------------------------------------------------------------------------------ NTT
+int get_twiddles(const uint64_t omega[4], uint32_t log_n, cudaStream_t s, const Fe **out) {
+    TwKey key;
+    memcpy(key.w, omega, 32);
+    key.log_n = log_n;
+    auto it = g->twiddles.find(key);
+    if (it != g->twiddles.end()) {
+        *out = it->second;
+        return H2B_OK;
+    }
+    size_t n = (size_t)1 << log_n;
+    size_t bytes = n * sizeof(Fe);
+    if (g->twiddle_bytes + bytes > ((size_t)24 << 30)) {  // bound the cache
+        CU(cudaDeviceSynchronize());
+        for (auto &kv : g->twiddles) cudaFree(kv.second);
+        g->twiddles.clear();
+        g->twiddle_bytes = 0;
+    }
+    Fe *W = nullptr;
+    cudaError_t e = cudaMalloc(&W, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(H2B_ERR_OOM, "cudaMalloc(twiddles)", e);
+    }
+    uint32_t lo_bits = log_n < 10 ? log_n : 10;
+    uint32_t n_lo = 1u << lo_bits, n_hi = 1u << (log_n - lo_bits);
+    Fe *small;
+    TRY(get_buf(BUF_MISC, ((size_t)n_lo + n_hi) * sizeof(Fe), (void **)&small));
+    Fe w;
+    memcpy(&w, omega, 32);
+    uint32_t mx = n_lo > n_hi ? n_lo : n_hi;
+    ntt_pow_small_kernel<<<(mx + 127) / 128, 128, 0, s>>>(w, lo_bits, n_lo, n_hi, small, small + n_lo);
+    LAUNCHED();
+    ntt_pow_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(small, small + n_lo, lo_bits,
+                                                                     (uint32_t)n, W);
+    LAUNCHED();
+    g->twiddles[key] = W;
+    g->twiddle_bytes += bytes;
+    *out = W;
+    return H2B_OK;
+}
+
+template <int S, int C, int NT>
+int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log_ns, bool last,
+                const NttIo &io, cudaStream_t s) {
+    constexpr int R = 1 << S;
+    size_t smem = ((size_t)2 * R * C + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        CU(cudaFuncSetAttribute(ntt_pass_kernel<S, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+        attr_set = true;
+    }
+    uint32_t M = 1u << (log_n - S);
+    uint32_t blocks = M / C;
+    if (blocks == 0) return fail(H2B_ERR_ARG, "ntt: tile wider than the pass");
+    ntt_pass_kernel<S, C, NT><<<blocks, NT, smem, s>>>(in, out, W, log_n, log_ns, last ? 1u : 0u, io);
+    LAUNCHED();
+    return H2B_OK;
+}
+
+int dispatch_pass(uint32_t S, bool single, const Fe *in, Fe *out, const Fe *W, uint32_t log_n,
+                  uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s) {
+    if (single) {
+        switch (S) {
+            case 1: return launch_pass<1, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 2: return launch_pass<2, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 3: return launch_pass<3, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 4: return launch_pass<4, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 5: return launch_pass<5, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 6: return launch_pass<6, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 1, 64>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 9: return launch_pass<9, 1, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 10: return launch_pass<10, 1, 512>(in, out, W, log_n, log_ns, last, io, s);
+        }
+    } else {
+        switch (S) {
+            case 5: return launch_pass<5, 64, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 6: return launch_pass<6, 32, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 16, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 8, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 9: return launch_pass<9, 4, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 10: return launch_pass<10, 2, 256>(in, out, W, log_n, log_ns, last, io, s);
+        }
+    }
+    return fail(H2B_ERR_ARG, "ntt: unsupported radix");
+}
+
+uint32_t g_ntt_max_radix = 8;
+
+// Transform `src` (n_in valid elements of a 2^log_n domain) into `dst`; `dst` may equal `src`.
+// dst_full: `dst` holds 2^log_n elements and may carry intermediate passes; otherwise (truncated
+// output) intermediates stay in library scratch and only the last pass touches `dst`.
+int ntt_run(const Fe *src, Fe *dst, uint32_t log_n, const uint64_t omega[4], NttIo io, cudaStream_t s,
+            bool dst_full = true) {
+    if (log_n > 28) return fail(H2B_ERR_ARG, "ntt: log_n > 28 (Fr::S)");
+    if (log_n == 0) {
+        // length-1 transform is the identity; only the fused scalings remain (index 0: pro is a no-op)
+        if (io.n_out == 0) return H2B_OK;
+        if (src != dst) CU(cudaMemcpyAsync(dst, src, sizeof(Fe), cudaMemcpyDeviceToDevice, s));
+        if (io.epi) {
+            Fe *c;
+            TRY(get_buf(BUF_MISC, sizeof(Fe), (void **)&c));
+            CU(cudaMemcpyAsync(c, &io.epi_c[0], sizeof(Fe), cudaMemcpyHostToDevice, s));
+            fr_scale_cyclic_kernel<<<1, 32, 0, s>>>(dst, 1, c, 1);
+            LAUNCHED();
+            CU(cudaStreamSynchronize(s));
+        }
+        return H2B_OK;
+    }
+    const Fe *W;
+    TRY(get_twiddles(omega, log_n, s, &W));
+    uint32_t P, radix[4];
+    bool single = log_n <= 10;
+    if (single) {
+        P = 1;
+        radix[0] = log_n;
+    } else {
+        P = (log_n + g_ntt_max_radix - 1) / g_ntt_max_radix;
+        if (P < 2) P = 2;
+        uint32_t base = log_n / P, rem = log_n % P;
+        for (uint32_t i = 0; i < P; i++) radix[i] = base + (i < rem ? 1 : 0);
+    }
+    Fe *tmp = nullptr, *tmp2 = dst;
+    if (P > 1) TRY(get_buf(BUF_NTT_T, ((size_t)1 << log_n) * sizeof(Fe), (void **)&tmp));
+    if (P > 2 && !dst_full) TRY(get_buf(BUF_NTT_T2, ((size_t)1 << log_n) * sizeof(Fe), (void **)&tmp2));
+    time_begin(s);
+    const Fe *cur = src;
+    uint32_t log_ns = 0;
+    for (uint32_t i = 0; i < P; i++) {
+        bool last = (i + 1 == P);
+        Fe *to = last ? dst : ((i & 1) == 0 ? tmp : tmp2);
+        NttIo pio = io;
+        if (i != 0) { pio.pro = 0; pio.n_in = 1u << log_n; }
+        if (!last) { pio.epi = 0; pio.n_out = 1u << log_n; }
+        TRY(dispatch_pass(radix[i], single, cur, to, W, log_n, log_ns, last, pio, s));
+        cur = to;
+        log_ns += radix[i];
+    }
+    time_end(s);
+    return H2B_OK;
+}
+
+NttIo io_plain(uint32_t log_n) {
+    NttIo io;
+    memset(&io, 0, sizeof io);
+    io.n_in = io.n_out = 1u << log_n;
+    return io;
+}
+
+// ------------------------------------------------------------------------------ domain constants
+__device__ const uint32_t kRootOfUnityMont[8] = {0xb639feb8u, 0x9632c7c5u, 0x0d0ff299u, 0x985ce340u,
+                                                 0x01b0ecd8u, 0xb2dd8800u, 0x6d98ce29u, 0x1d69070du};
+__device__ const uint32_t kZetaMont[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu,
+                                          0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};
+
+struct DomainDev {
+    Fe omega, omega_inv, ext_omega, ext_omega_inv, g_coset, g_coset_inv, ifft_div, ext_ifft_div;
+    Fe t_eval[32];
+    Fe ext_coset[3];
+    uint32_t t_count;
+};
+
+// One block of 64 threads: thread 0 derives the forward constants, then 4 + n_t threads invert
+// in parallel (EvaluationDomain::new batches these inversions; the values are the same).
+__global__ void domain_new_kernel(uint32_t k, uint32_t ext_k, DomainDev *out) {
+    __shared__ Fe to_inv[36];
+    __shared__ uint32_t t_count;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        Fe w, zeta;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { w.l[i] = kRootOfUnityMont[i]; zeta.l[i] = kZetaMont[i]; }
+        for (uint32_t i = ext_k; i < 28; i++) w = Fr::sqr(w);
+        Fe ext_w = w;
+        for (uint32_t i = k; i < ext_k; i++) w = Fr::sqr(w);
+        out->omega = w;
+        out->ext_omega = ext_w;
+        out->g_coset = zeta;
+        out->g_coset_inv = Fr::sqr(zeta);
+        uint64_t n = 1ull << k;
+        Fe orig = Fr::pow_u64(zeta, n);
+        Fe step = Fr::pow_u64(ext_w, n);
+        Fe cur = orig;
+        uint32_t cnt = 0;
+        do {
+            if (cnt < 32) to_inv[4 + cnt] = Fr::sub(cur, Fr::one());
+            cnt++;
+            cur = Fr::mul(cur, step);
+        } while (!Fr::eq(cur, orig) && cnt < 64);
+        t_count = cnt;
+        to_inv[0] = w;
+        to_inv[1] = ext_w;
+        Fe two_k = Fr::zero();
+        two_k.l[k >> 5] = 1u << (k & 31);
+        to_inv[2] = Fr::to_mont(two_k);
+        Fe two_e = Fr::zero();
+        two_e.l[ext_k >> 5] = 1u << (ext_k & 31);
+        to_inv[3] = Fr::to_mont(two_e);
+    }
+    __syncthreads();
+    uint32_t cnt = t_count < 32 ? t_count : 32;
+    if (tid < 4 + cnt) {
+        Fe v = Fr::inv(to_inv[tid]);
+        if (tid == 0) out->omega_inv = v;
+        else if (tid == 1) out->ext_omega_inv = v;
+        else if (tid == 2) out->ifft_div = v;
+        else if (tid == 3) {
+            out->ext_ifft_div = v;
+            Fe zeta;
+#pragma unroll
+            for (int i = 0; i < 8; i++) zeta.l[i] = kZetaMont[i];
+            out->ext_coset[0] = v;
+            out->ext_coset[1] = Fr::mul(v, Fr::sqr(zeta));
+            out->ext_coset[2] = Fr::mul(v, zeta);
+        } else out->t_eval[tid - 4] = v;
+    }
+    if (tid == 0) out->t_count = t_count;
+}
+
+int domain_build(uint32_t j, uint32_t k, h2b_domain *out) {
+    if (j < 2) return fail(H2B_ERR_ARG, "domain: j < 2");
+    uint64_t qdeg = j - 1;
+    uint32_t ext_k = k;
+    if (k > 28) return fail(H2B_ERR_ARG, "domain: k > 28");
+    while (((uint64_t)1 << ext_k) < ((uint64_t)1 << k) * qdeg) ext_k++;
+    if (ext_k > 28) return fail(H2B_ERR_ARG, "domain: extended_k > Fr::S");
+    if (ext_k - k > 5) return fail(H2B_ERR_ARG, "domain: extended_k - k > 5 not supported");
+    uint64_t key = ((uint64_t)j << 32) | k;
+    auto it = g->domains.find(key);
+    if (it != g->domains.end()) {
+        *out = it->second;
+        return H2B_OK;
+    }
+    DomainDev *dd;
+    TRY(get_buf(BUF_MISC, sizeof(DomainDev), (void **)&dd));
+    domain_new_kernel<<<1, 64, 0, g->stream>>>(k, ext_k, dd);
+    LAUNCHED();
+    DomainDev h;
+    CU(cudaMemcpyAsync(&h, dd, sizeof h, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (h.t_count != (1u << (ext_k - k)))  // domain.rs:101
+        return fail(H2B_ERR_ARG, "domain: t_evaluations.len() != 1 << (extended_k - k)");
+    h2b_domain d;
+    memset(&d, 0, sizeof d);
+    d.k = k; d.extended_k = ext_k; d.j = j; d.n_t = h.t_count;
+    memcpy(d.omega, &h.omega, 32);
+    memcpy(d.omega_inv, &h.omega_inv, 32);
+    memcpy(d.extended_omega, &h.ext_omega, 32);
+    memcpy(d.extended_omega_inv, &h.ext_omega_inv, 32);
+    memcpy(d.g_coset, &h.g_coset, 32);
+    memcpy(d.g_coset_inv, &h.g_coset_inv, 32);
+    memcpy(d.ifft_divisor, &h.ifft_div, 32);
+    memcpy(d.extended_ifft_divisor, &h.ext_ifft_div, 32);
+    memcpy(d.t_evaluations, h.t_eval, 32 * d.n_t);
+    memcpy(d.extended_ifft_coset, h.ext_coset, 96);
+    g->domains[key] = d;
+    *out = d;
+    return H2B_OK;
+}
+
+int check_domain(const h2b_domain *d) {
+    if (!d) return fail(H2B_ERR_ARG, "domain is null");
+    if (d->k > d->extended_k || d->extended_k > 28 || d->j < 2) return fail(H2B_ERR_ARG, "domain is malformed");
+    return H2B_OK;
+}
+
+int dev_lagrange_to_coeff(const h2b_domain *d, Fe *a, cudaStream_t s) {
+    NttIo io = io_plain(d->k);
+    io.epi = 1;
+    for (int i = 0; i < 3; i++) memcpy(&io.epi_c[i], d->ifft_divisor, 32);
+    return ntt_run(a, a, d->k, d->omega_inv, io, s);
+}
+int dev_coeff_to_extended(const h2b_domain *d, const Fe *in, Fe *out, cudaStream_t s) {
+    NttIo io = io_plain(d->extended_k);
+    io.n_in = 1u << d->k;
+    io.pro = 1;
+    memcpy(&io.pro_c[1], d->g_coset, 32);      // i % 3 == 1 -> zeta
+    memcpy(&io.pro_c[2], d->g_coset_inv, 32);  // i % 3 == 2 -> zeta^2
+    return ntt_run(in, out, d->extended_k, d->extended_omega, io, s);
+}
+int dev_extended_to_coeff(const h2b_domain *d, const Fe *in, Fe *out, cudaStream_t s) {
+    // ifft with extended_omega_inv; the last pass multiplies by 1/2^ext_k * {1, zeta^2, zeta}[i % 3]
+    // and stores only the first n * (j - 1) coefficients (the truncation of domain.rs:~325).
+    size_t en = (size_t)1 << d->extended_k;
+    size_t keep = (size_t)(d->j - 1) << d->k;
+    if (keep > en) return fail(H2B_ERR_ARG, "extended_to_coeff: n*(j-1) > extended length");
+    NttIo io = io_plain(d->extended_k);
+    io.epi = 1;
+    memcpy(io.epi_c, d->extended_ifft_coset, 96);
+    io.n_out = (uint32_t)keep;
+    return ntt_run(in, out, d->extended_k, d->extended_omega_inv, io, s, /*dst_full=*/false);
+}
+
+// ------------------------------------------------------------------------------ test kernels
+template <class F>
+__global__ void test_field_kernel(int op, const Fe *a, const Fe *b, Fe *o, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fe x = load_fe(&a[i]);
+    Fe y = b ? load_fe(&b[i]) : F::zero();
+    Fe r;
+    switch (op) {
+        case 0: r = F::mul(x, y); break;
+        case 1: r = F::add(x, y); break;
+        case 2: r = F::sub(x, y); break;
+        case 3: r = F::mul_portable(x, y); break;
+        case 4: r = F::inv(x); break;
+        default: r = F::from_mont(x); break;
+    }
+    store_fe(&o[i], r);
+}
+__global__ void test_g1_add_kernel(const Affine *a, const Affine *b, Jacobian *o, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine p = load_affine(&a[i]), q = load_affine(&b[i]);
+    XYZZ acc = xyzz_from_affine(p);
+    if (!affine_is_identity(q)) xyzz_madd(acc, q);
+    Jacobian j = xyzz_to_jacobian(acc);
+    store_fe(&o[i].x, j.x);
+    store_fe(&o[i].y, j.y);
+    store_fe(&o[i].z, j.z);
+}
+
+// Integer-pipe microbenchmarks: 8 independent chains per thread, fully unrolled bodies.
+__global__ void imad_bench_kernel(uint32_t *sink, uint32_t iters, uint32_t seed) {
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 9, a5 = a0 * 11,
+             a6 = a0 * 13, a7 = a0 * 15;
+    uint32_t b = seed | 1, c = seed ^ 0x9e3779b9u;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a0) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a1) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a2) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a3) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a4) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a5) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a6) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a7) : "r"(b), "r"(c));
+        }
+    }
+    uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x12345678u) sink[0] = r;
+}
+__global__ void imad_wide_bench_kernel(uint64_t *sink, uint32_t iters, uint32_t seed) {
+    uint64_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 9, a5 = a0 * 11,
+             a6 = a0 * 13, a7 = a0 * 15;
+    uint32_t b = seed | 1;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"((uint32_t)a0), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"((uint32_t)a1), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"((uint32_t)a2), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"((uint32_t)a3), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"((uint32_t)a4), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"((uint32_t)a5), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"((uint32_t)a6), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"((uint32_t)a7), "r"(b));
+        }
+    }
+    uint64_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x12345678u) sink[0] = r;
+}
+
+// host staging helpers
+int stage_in(BufId id, const void *host, size_t bytes, void **dev) {
+    TRY(enter(g->stream));
+    TRY(get_buf(id, bytes, dev));
+    CU(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, g->stream));
+    return H2B_OK;
+}
+
+}  // namespace
+
+// ============================================================================== C ABI
+extern "C" {
+
+uint32_t h2b_abi_version(void) { return 1; }
+const char *h2b_last_error(void) { return g_err.c_str(); }
+
+int h2b_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g && g->device == device) return H2B_OK;
+    if (g) return fail(H2B_ERR_STATE, "h2b_init: already initialised on another device");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(H2B_ERR_CUDA, "h2b_init: no CUDA device (this library has no CPU fallback)", e);
+    }
+    if (device < 0 || device >= count) return fail(H2B_ERR_ARG, "h2b_init: bad device index");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(H2B_ERR_CUDA, "h2b_init: kernels are built for sm_100a only");
+    Ctx *c = new Ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return fail(H2B_ERR_CUDA, "h2b_init: stream/event creation failed", cudaGetLastError());
+    }
+    const char *mr = getenv("H2B_NTT_MAX_RADIX");
+    if (mr) {
+        int v = atoi(mr);
+        if (v >= 5 && v <= 10) g_ntt_max_radix = (uint32_t)v;
+    }
+    g = c;
+    return H2B_OK;
+}
+
+void h2b_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < BUF_COUNT; i++)
+        if (g->buf[i]) cudaFree(g->buf[i]);
+    for (auto &kv : g->srs) cudaFree(kv.second.d);
+    for (auto &kv : g->twiddles) cudaFree(kv.second);
+    for (auto e : g->tev0) cudaEventDestroy(e);
+    for (auto e : g->tev1) cudaEventDestroy(e);
+    cudaEventDestroy(g->last_done);
+    cudaStreamDestroy(g->stream);
+    delete g;
+    g = nullptr;
+}
+
+int h2b_set_msm_window(uint32_t c) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (c != 0 && (c < 2 || c > 22)) return fail(H2B_ERR_ARG, "msm window must be 0 or in [2, 22]");
+    g->msm_window = c;
+    return H2B_OK;
+}
+uint64_t h2b_kernel_launches(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g ? g->launches : 0;
+}
+int h2b_set_kernel_timing(int enabled) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    g->timing = enabled;
+    g->tev_used = 0;
+    return H2B_OK;
+}
+int h2b_kernel_time_collect(double *total_ms, uint32_t *calls) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    CU(cudaSetDevice(g->device));
+    double sum = 0;
+    for (uint32_t i = 0; i < g->tev_used; i++) {
+        CU(cudaEventSynchronize(g->tev1[i]));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, g->tev0[i], g->tev1[i]));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (calls) *calls = g->tev_used;
+    g->tev_used = 0;
+    return H2B_OK;
+}
+
+// ---- MSM
+int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!d_out || (n && (!d_coeffs || !d_bases))) return fail(H2B_ERR_ARG, "msm: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, msm_run((const Fe *)d_coeffs, (const Affine *)d_bases, n, (Jacobian *)d_out, s));
+}
+
+int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out[12]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!out || (n && (!coeffs || !bases))) return fail(H2B_ERR_ARG, "best_multiexp: null pointer");
+    CU(cudaSetDevice(g->device));
+    void *ds = nullptr, *db = nullptr, *dout;
+    if (n) {
+        TRY(stage_in(BUF_SCALARS, coeffs, n * 32, &ds));
+        TRY(stage_in(BUF_BASES, bases, n * 64, &db));
+    }
+    TRY(get_buf(BUF_OUT, 96, &dout));
+    TRY(msm_run((const Fe *)ds, (const Affine *)db, n, (Jacobian *)dout, g->stream));
+    CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+
+int h2b_srs_register(const uint64_t *bases, size_t n, uint64_t *handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!bases || !handle || n == 0) return fail(H2B_ERR_ARG, "srs_register: bad argument");
+    CU(cudaSetDevice(g->device));
+    Srs s;
+    cudaError_t e = cudaMalloc(&s.d, n * sizeof(Affine));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(H2B_ERR_OOM, "cudaMalloc(srs)", e);
+    }
+    s.n = n;
+    e = cudaMemcpy(s.d, bases, n * sizeof(Affine), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(s.d);
+        return fail(H2B_ERR_CUDA, "cudaMemcpy(srs)", e);
+    }
+    *handle = g->next_handle++;
+    g->srs[*handle] = s;
+    return H2B_OK;
+}
+int h2b_srs_release(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    auto it = g->srs.find(handle);
+    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "srs_release: unknown handle");
+    CU(cudaSetDevice(g->device));
+    CU(cudaStreamSynchronize(g->stream));
+    cudaFree(it->second.d);
+    g->srs.erase(it);
+    return H2B_OK;
+}
+int h2b_srs_device_ptr(uint64_t srs, void **d_bases, size_t *n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    auto it = g->srs.find(srs);
+    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "srs_device_ptr: unknown handle");
+    if (d_bases) *d_bases = it->second.d;
+    if (n) *n = it->second.n;
+    return H2B_OK;
+}
+int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    auto it = g->srs.find(srs);
+    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit: unknown SRS handle");
+    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit: bases.len() < size");  // commitment.rs:319/:363
+    if (!out || (n && !scalars)) return fail(H2B_ERR_ARG, "commit: null pointer");
+    CU(cudaSetDevice(g->device));
+    void *ds = nullptr, *dout;
+    if (n) TRY(stage_in(BUF_SCALARS, scalars, n * 32, &ds));
+    TRY(get_buf(BUF_OUT, 96, &dout));
+    TRY(msm_run((const Fe *)ds, it->second.d, n, (Jacobian *)dout, g->stream));
+    CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+
+int h2b_dev_g1_fold(const void *d_points, size_t count, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!d_out || (count && !d_points)) return fail(H2B_ERR_ARG, "g1_fold: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    g1_fold_kernel<<<1, 32, 0, s>>>((const Jacobian *)d_points, (uint32_t)count, (Jacobian *)d_out);
+    LAUNCHED();
+    return leave(s, H2B_OK);
+}
+int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[8], void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!base || (n && (!d_scalars || !d_out))) return fail(H2B_ERR_ARG, "fixed_base_mul: null pointer");
+    if (n > (1u << 30)) return fail(H2B_ERR_ARG, "fixed_base_mul: n > 2^30");
+    if (n == 0) return H2B_OK;
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    Affine b;
+    memcpy(&b, base, 64);
+    g1_fixed_base_mul_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>((const Fe *)d_scalars, (uint32_t)n, b,
+                                                                         (Affine *)d_out);
+    LAUNCHED();
+    return leave(s, H2B_OK);
+}
+int h2b_g1_fold(const uint64_t *points, size_t count, uint64_t out[12]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!out || (count && !points)) return fail(H2B_ERR_ARG, "g1_fold: null pointer");
+    CU(cudaSetDevice(g->device));
+    void *dp = nullptr, *dout;
+    TRY(stage_in(BUF_TEST_A, points, count * 96, &dp));
+    TRY(get_buf(BUF_OUT, 96, &dout));
+    g1_fold_kernel<<<1, 32, 0, g->stream>>>((const Jacobian *)dp, (uint32_t)count, (Jacobian *)dout);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+
+// ---- NTT
+int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!d_a || !omega) return fail(H2B_ERR_ARG, "best_fft: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, ntt_run((const Fe *)d_a, (Fe *)d_a, log_n, omega, io_plain(log_n), s));
+}
+int h2b_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!a || !omega) return fail(H2B_ERR_ARG, "best_fft: null pointer");
+    if (log_n > 28) return fail(H2B_ERR_ARG, "best_fft: log_n > 28");
+    CU(cudaSetDevice(g->device));
+    size_t bytes = ((size_t)1 << log_n) * 32;
+    void *da;
+    TRY(stage_in(BUF_NTT_A, a, bytes, &da));
+    TRY(ntt_run((const Fe *)da, (Fe *)da, log_n, omega, io_plain(log_n), g->stream));
+    CU(cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+
+int h2b_domain_new(uint32_t j, uint32_t k, h2b_domain *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!out) return fail(H2B_ERR_ARG, "domain_new: null pointer");
+    CU(cudaSetDevice(g->device));
+    return domain_build(j, k, out);
+}
+
+int h2b_dev_lagrange_to_coeff(const h2b_domain *d, void *d_a, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!d_a) return fail(H2B_ERR_ARG, "lagrange_to_coeff: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, dev_lagrange_to_coeff(d, (Fe *)d_a, s));
+}
+int h2b_lagrange_to_coeff(const h2b_domain *d, uint64_t *a) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!a) return fail(H2B_ERR_ARG, "lagrange_to_coeff: null pointer");
+    CU(cudaSetDevice(g->device));
+    size_t bytes = ((size_t)1 << d->k) * 32;
+    void *da;
+    TRY(stage_in(BUF_NTT_A, a, bytes, &da));
+    TRY(dev_lagrange_to_coeff(d, (Fe *)da, g->stream));
+    CU(cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+int h2b_dev_coeff_to_extended(const h2b_domain *d, const void *d_in, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!d_in || !d_out) return fail(H2B_ERR_ARG, "coeff_to_extended: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, dev_coeff_to_extended(d, (const Fe *)d_in, (Fe *)d_out, s));
+}
+int h2b_coeff_to_extended(const h2b_domain *d, const uint64_t *in, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!in || !out) return fail(H2B_ERR_ARG, "coeff_to_extended: null pointer");
+    CU(cudaSetDevice(g->device));
+    size_t in_bytes = ((size_t)1 << d->k) * 32, out_bytes = ((size_t)1 << d->extended_k) * 32;
+    void *din, *dout;
+    TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din));
+    TRY(get_buf(BUF_NTT_A, out_bytes, &dout));
+    TRY(dev_coeff_to_extended(d, (const Fe *)din, (Fe *)dout, g->stream));
+    CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+int h2b_dev_extended_to_coeff(const h2b_domain *d, const void *d_in, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!d_in || !d_out) return fail(H2B_ERR_ARG, "extended_to_coeff: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, dev_extended_to_coeff(d, (const Fe *)d_in, (Fe *)d_out, s));
+}
+int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!in || !out) return fail(H2B_ERR_ARG, "extended_to_coeff: null pointer");
+    CU(cudaSetDevice(g->device));
+    size_t in_bytes = ((size_t)1 << d->extended_k) * 32;
+    size_t out_bytes = ((size_t)(d->j - 1) << d->k) * 32;
+    void *din, *dout;
+    TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din));
+    TRY(get_buf(BUF_NTT_OUT, out_bytes, &dout));
+    TRY(dev_extended_to_coeff(d, (const Fe *)din, (Fe *)dout, g->stream));
+    CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!a) return fail(H2B_ERR_ARG, "divide_by_vanishing_poly: null pointer");
+    CU(cudaSetDevice(g->device));
+    size_t n = (size_t)1 << d->extended_k;
+    void *da, *dt;
+    TRY(stage_in(BUF_NTT_A, a, n * 32, &da));
+    TRY(stage_in(BUF_MISC, d->t_evaluations, (size_t)d->n_t * 32, &dt));
+    fr_scale_cyclic_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, g->stream>>>((Fe *)da, (uint32_t)n,
+                                                                               (const Fe *)dt, d->n_t);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+
+// ---- test hooks
+int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!a || !out || n == 0) return fail(H2B_ERR_ARG, "test_field_op: bad argument");
+    CU(cudaSetDevice(g->device));
+    void *da, *db = nullptr, *dout;
+    TRY(stage_in(BUF_TEST_A, a, n * 32, &da));
+    if (b) TRY(stage_in(BUF_TEST_B, b, n * 32, &db));
+    TRY(get_buf(BUF_TEST_O, n * 32, &dout));
+    uint32_t blocks = (uint32_t)((n + 127) / 128);
+    if (field == 0)
+        test_field_kernel<Fr><<<blocks, 128, 0, g->stream>>>(op, (Fe *)da, (Fe *)db, (Fe *)dout, (uint32_t)n);
+    else
+        test_field_kernel<Fq><<<blocks, 128, 0, g->stream>>>(op, (Fe *)da, (Fe *)db, (Fe *)dout, (uint32_t)n);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!a || !b || !out || n == 0) return fail(H2B_ERR_ARG, "test_g1_add_affine: bad argument");
+    CU(cudaSetDevice(g->device));
+    void *da, *db, *dout;
+    TRY(stage_in(BUF_TEST_A, a, n * 64, &da));
+    TRY(stage_in(BUF_TEST_B, b, n * 64, &db));
+    TRY(get_buf(BUF_TEST_O, n * 96, &dout));
+    test_g1_add_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>((Affine *)da, (Affine *)db,
+                                                                           (Jacobian *)dout, (uint32_t)n);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(out, dout, n * 96, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return leave(g->stream, H2B_OK);
+}
+
+int h2b_imad_peak(double *imad_gops, double *imad_wide_gops, double *sm_mhz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    CU(cudaSetDevice(g->device));
+    void *sink;
+    TRY(get_buf(BUF_MISC, 64, &sink));
+    const uint32_t iters = 2000, threads = 512;
+    const uint32_t blocks = (uint32_t)g->sm_count * 4;
+    const double ops = (double)blocks * threads * iters * 16.0 * 8.0;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best[2] = {1e30f, 1e30f};
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, g->stream));
+        imad_bench_kernel<<<blocks, threads, 0, g->stream>>>((uint32_t *)sink, iters, 12345u + rep);
+        LAUNCHED();
+        CU(cudaEventRecord(e1, g->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best[0]) best[0] = ms;
+        CU(cudaEventRecord(e0, g->stream));
+        imad_wide_bench_kernel<<<blocks, threads, 0, g->stream>>>((uint64_t *)sink, iters, 12345u + rep);
+        LAUNCHED();
+        CU(cudaEventRecord(e1, g->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best[1]) best[1] = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (imad_gops) *imad_gops = ops / (best[0] * 1e-3) / 1e9;
+    if (imad_wide_gops) *imad_wide_gops = ops / (best[1] * 1e-3) / 1e9;
+    if (sm_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g->device);
+        *sm_mhz = khz / 1000.0;
+    }
+    return H2B_OK;
+}
+
+}  // extern "C"

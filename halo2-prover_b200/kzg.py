@@ -1,0 +1,59 @@
+"""Host mirror of the caller-side boundary: ParamsKZG::{commit, commit_lagrange}
+(halo2_proofs @6b43b6b src/poly/kzg/commitment.rs:319, :363).
+
+Upstream copies the polynomial into a Vec and calls
+``best_multiexp(&scalars, &self.g[0..n])`` (resp. ``g_lagrange``); the blind is ignored
+for KZG.  Here the two base arrays are registered once (device-resident SRS) and each
+commit moves only the 32*n bytes of scalars.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+class ParamsKZG:
+    def __init__(self, k: int, g: np.ndarray, g_lagrange: np.ndarray | None = None):
+        """``g`` / ``g_lagrange``: (2^k, 8) uint64 G1Affine arrays (the body of ParamsKZG::write)."""
+        self.k = k
+        self.n = 1 << k
+        _ffi.init()
+        self._handles = {}
+        for name, arr in (("g", g), ("g_lagrange", g_lagrange)):
+            if arr is None:
+                continue
+            arr = _ffi.as_u64(arr, 8)
+            assert arr.shape[0] >= self.n
+            h = C.c_uint64(0)
+            _ffi.check(_ffi.lib().h2b_srs_register(_ffi.u64p(arr), C.c_size_t(arr.shape[0]), C.byref(h)))
+            self._handles[name] = h.value
+
+    def _commit(self, which: str, poly: np.ndarray) -> np.ndarray:
+        poly = _ffi.as_u64(poly, 4)
+        size = poly.shape[0]
+        assert self.n >= size, "assert!(bases.len() >= size)"  # commitment.rs:319 / :363
+        out = np.zeros(12, dtype=np.uint64)
+        _ffi.check(_ffi.lib().h2b_commit(C.c_uint64(self._handles[which]), _ffi.u64p(poly), C.c_size_t(size),
+                                         _ffi.u64p(out)))
+        return out
+
+    def commit(self, poly: np.ndarray, _blind=None) -> np.ndarray:
+        return self._commit("g", poly)
+
+    def commit_lagrange(self, poly: np.ndarray, _blind=None) -> np.ndarray:
+        return self._commit("g_lagrange", poly)
+
+    def device_bases(self, which: str = "g"):
+        """(device pointer, length) of a registered base array."""
+        p = C.c_void_p()
+        n = C.c_size_t()
+        _ffi.check(_ffi.lib().h2b_srs_device_ptr(C.c_uint64(self._handles[which]), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def release(self) -> None:
+        for h in self._handles.values():
+            _ffi.lib().h2b_srs_release(C.c_uint64(h))
+        self._handles = {}

@@ -1,0 +1,52 @@
+"""Point-range sharded MSM across ranks (one process per GPU).
+
+The reference already splits an MSM into contiguous chunks and folds the partial sums
+(halo2_proofs @6b43b6b src/arithmetic.rs:152-176); here a chunk is a GPU.  Rank g of G
+owns points [g*n/G, (g+1)*n/G): its slice of the SRS stays resident, its slice of the
+scalars arrives over its own PCIe link, it runs the single-GPU MSM and emits one
+Jacobian point.  The only exchange is an all-gather of G x 96 bytes (group addition is
+not an NCCL reduction op), after which every rank folds the G partials on its GPU.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) owned by ``rank``; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_partials(partial, group=None):
+    """all_gather of one (12,) int64 partial per rank -> (world, 12) tensor on the same device."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    out = torch.empty((world, 12), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out.view(-1), partial.contiguous().view(-1), group=group)
+    return out
+
+
+def sharded_multiexp(coeffs_local, bases_local, group=None, stream=None):
+    """MSM over the union of all ranks' (coeffs_local, bases_local) slices.
+
+    Inputs are cuda int64 tensors ((m,4) and (m,8)) already resident on this rank's GPU.
+    Returns a (12,) int64 cuda tensor holding the folded Jacobian sum (same on every rank).
+    """
+    import torch
+    import torch.distributed as dist
+
+    from .arithmetic import dev_g1_fold, dev_msm
+
+    dev = coeffs_local.device
+    partial = torch.empty(12, dtype=torch.int64, device=dev)
+    dev_msm(coeffs_local, bases_local, partial, stream=stream)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return partial
+    parts = gather_partials(partial, group)
+    out = torch.empty(12, dtype=torch.int64, device=dev)
+    dev_g1_fold(parts, out, stream=stream)
+    return out

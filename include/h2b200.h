@@ -1,0 +1,148 @@
+/*
+ * h2b200.h -- C ABI of libh2b200.so: BN254 MSM + NTT proving hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary for the leaf functions the reference reaches through
+ * halo2_proofs::plonk::create_proof (/root/reference/circuits/src/utils.rs:83-91,
+ * :105-120; keygen at :67-68).  The leaves live in the Cargo.lock-pinned,
+ * un-vendored dependency halo2_proofs 0.2.0 @6b43b6b (circuits/Cargo.lock:836-838)
+ * with field/curve types from halo2curves 0.3.2 @9f5c508 (:854-856); each entry
+ * point below names the upstream item it replaces.  INTEGRATION.md shows the Rust
+ * `-sys` binding and the patch that rewires the call sites.
+ *
+ * Data layout (identical to the Rust types, so buffers cross the FFI untouched):
+ *   Fr, Fq      4 x uint64_t little-endian limbs, Montgomery form (R = 2^256), < modulus
+ *   G1Affine    {x: Fq, y: Fq}       64 bytes, identity = (0, 0)
+ *   G1          {x, y, z: Fq}        96 bytes, Jacobian, identity z = 0
+ * All pointers are plain host pointers unless the function name contains `_dev`,
+ * in which case they are CUDA device pointers on the library's device and `stream`
+ * is a cudaStream_t passed as void* (NULL = the library's own stream).
+ *
+ * Errors: upstream panics (assert_eq!) on bad lengths; a C ABI cannot unwind, so
+ * every function returns H2B_OK (0) or a negative code and never throws.  The
+ * binding asserts on non-zero to keep the reference's behaviour.  There is no CPU
+ * fallback: without a usable GPU every compute call returns H2B_ERR_CUDA.
+ *
+ * Threading: calls may come from any thread; the library serialises them on one
+ * internal mutex (create_proof issues them sequentially from one thread anyway).
+ */
+#ifndef H2B200_H
+#define H2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2B_OK 0
+#define H2B_ERR_ARG (-1)    /* bad length / null pointer / unsupported size (upstream: assert panic) */
+#define H2B_ERR_CUDA (-2)   /* CUDA runtime error, no device */
+#define H2B_ERR_OOM (-3)    /* device allocation failed */
+#define H2B_ERR_STATE (-4)  /* unknown handle / not initialised */
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+/* Select the CUDA device and create the library context (stream, workspace pool).
+ * Idempotent for the same device. */
+int h2b_init(int device);
+void h2b_shutdown(void);
+/* Human-readable description of the last error on the calling thread's last call. */
+const char *h2b_last_error(void);
+/* ABI version of this header. */
+uint32_t h2b_abi_version(void);
+
+/* ---- MSM ------------------------------------------------------------------------- */
+/* best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1
+ * replaces halo2_proofs src/arithmetic.rs:147-180 (and multiexp_serial :28-140).
+ * coeffs: n x 4 u64, bases: n x 8 u64, out: 12 u64 (Jacobian; any representative of the sum). */
+int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out[12]);
+
+/* SRS residency.  ParamsKZG keeps two static base arrays (g, g_lagrange); register each
+ * once (copied to device memory; the host copy is not referenced after return).
+ * replaces the `&self.g[0..n]` / `&self.g_lagrange[0..n]` arguments of
+ * src/poly/kzg/commitment.rs:319 (commit_lagrange) and :363 (commit). */
+int h2b_srs_register(const uint64_t *bases, size_t n, uint64_t *handle);
+int h2b_srs_release(uint64_t handle);
+/* ParamsKZG::commit / commit_lagrange: best_multiexp(scalars, &bases[0..n]) against a
+ * registered SRS (n <= registered length; upstream asserts bases.len() >= size). */
+int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]);
+
+/* Sum of `count` Jacobian points (fold of per-GPU partial MSM results;
+ * arithmetic.rs:~176 `results.iter().fold(identity, |a, b| a + b)`). */
+int h2b_g1_fold(const uint64_t *points /* count x 12 */, size_t count, uint64_t out[12]);
+
+/* ---- NTT ------------------------------------------------------------------------- */
+/* best_fft(a: &mut [Fr], omega: Fr, log_n: u32)   replaces src/arithmetic.rs:185-290.
+ * In place, natural order in and out, a has 2^log_n elements, log_n <= 28. */
+int h2b_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n);
+
+/* EvaluationDomain<Fr> constants, replaces EvaluationDomain::new(j, k)
+ * (src/poly/domain.rs:~40-140; the assert at :101 is checked). */
+typedef struct h2b_domain {
+    uint32_t k;
+    uint32_t extended_k;
+    uint32_t j;                 /* cs degree; quotient_poly_degree = j - 1 */
+    uint32_t n_t;               /* 2^(extended_k - k) = t_evaluations.len() */
+    uint64_t omega[4];
+    uint64_t omega_inv[4];
+    uint64_t extended_omega[4];
+    uint64_t extended_omega_inv[4];
+    uint64_t g_coset[4];        /* ZETA */
+    uint64_t g_coset_inv[4];    /* ZETA^2 */
+    uint64_t ifft_divisor[4];          /* 1 / 2^k */
+    uint64_t extended_ifft_divisor[4]; /* 1 / 2^extended_k */
+    uint64_t t_evaluations[32 * 4];    /* 1 / ((zeta * extended_omega^i)^n - 1), i < n_t <= 32 */
+    /* derived, filled by h2b_domain_new: extended_ifft_divisor * {1, zeta^2, zeta}, the fused
+     * store-side scaling of extended_to_coeff (ifft divisor, then distribute_powers_zeta(false)) */
+    uint64_t extended_ifft_coset[3 * 4];
+} h2b_domain;
+int h2b_domain_new(uint32_t j, uint32_t k, h2b_domain *out);
+
+/* EvaluationDomain::lagrange_to_coeff (domain.rs:227): a has 2^k elements, in place. */
+int h2b_lagrange_to_coeff(const h2b_domain *d, uint64_t *a);
+/* EvaluationDomain::coeff_to_extended (domain.rs:244): in 2^k elements -> out 2^extended_k. */
+int h2b_coeff_to_extended(const h2b_domain *d, const uint64_t *in, uint64_t *out);
+/* EvaluationDomain::extended_to_coeff (domain.rs:311): in 2^extended_k -> out 2^k * (j-1). */
+int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out);
+/* EvaluationDomain::divide_by_vanishing_poly: a[i] *= t_evaluations[i % n_t], 2^extended_k, in place. */
+int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a);
+
+/* ---- device-resident variants (inputs/outputs already in HBM) ---------------------- */
+int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out /* 96 B */, void *stream);
+/* Device address of a registered SRS (n x 64 bytes). */
+int h2b_srs_device_ptr(uint64_t srs, void **d_bases, size_t *n);
+int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *stream);
+int h2b_dev_lagrange_to_coeff(const h2b_domain *d, void *d_a, void *stream);
+int h2b_dev_coeff_to_extended(const h2b_domain *d, const void *d_in, void *d_out, void *stream);
+int h2b_dev_extended_to_coeff(const h2b_domain *d, const void *d_in, void *d_out, void *stream);
+int h2b_dev_g1_fold(const void *d_points, size_t count, void *d_out, void *stream);
+/* out[i] = [scalars[i]] * base as G1Affine (n x 64 B): the per-element fixed-base multiplication of
+ * ParamsKZG::setup (src/poly/kzg/commitment.rs:68-114); builds synthetic SRS / benchmark bases in HBM. */
+int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[8], void *d_out, void *stream);
+
+/* ---- tuning / introspection ------------------------------------------------------- */
+/* Override the MSM window (0 = automatic). */
+int h2b_set_msm_window(uint32_t c);
+/* Number of kernel launches issued by the library since h2b_init (for bench accounting). */
+uint64_t h2b_kernel_launches(void);
+/* Dominant-kernel timing (MSM: the bucket-accumulation kernel; NTT: all passes of one transform).
+ * While enabled every call brackets that kernel with a CUDA event pair on the launching stream
+ * (no synchronisation is added).  h2b_kernel_time_collect waits for the recorded pairs, returns
+ * the summed milliseconds and the number of calls, and clears them (at most 256 are kept). */
+int h2b_set_kernel_timing(int enabled);
+int h2b_kernel_time_collect(double *total_ms, uint32_t *calls);
+
+/* ---- test hooks (element-wise device arithmetic, used by tests/ only) ---------------- */
+/* op: 0 mul, 1 add, 2 sub, 3 mul (portable 64-bit path), 4 inverse of a, 5 from_mont(a)
+ * field: 0 Fr, 1 Fq.  a, b, out: n x 4 u64 host buffers. */
+int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* out[i] = a[i] + b[i] on affine inputs (n x 8 u64) through the XYZZ mixed-add path -> n x 12 u64. */
+int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* Integer-pipe microbenchmark: returns measured 32-bit IMAD (mad.lo.u32) and IMAD.WIDE
+ * (mad.wide.u32) throughput in G instr/s on the current device. */
+int h2b_imad_peak(double *imad_gops, double *imad_wide_gops, double *sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2B200_H */

@@ -1,0 +1,173 @@
+"""GPU parity for best_multiexp / ParamsKZG::commit (compared after affine normalisation,
+SURVEY.md section 8b: the Jacobian representative is free)."""
+import numpy as np
+import pytest
+
+from util import load_golden, unhx
+
+pytestmark = pytest.mark.gpu
+
+
+def _affine(href, jac):
+    return href.g1_to_affine(np.ascontiguousarray(jac))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 32, 33, 255, 256, 257, 1000, 4096, (1 << 14) - 1, 1 << 16])
+def test_msm_vs_oracle(h2b, href, n):
+    sc, pts = href.random_fr(n, 5000 + n), href.random_g1(n, 6000 + n)
+    want = _affine(href, href.best_multiexp(sc, pts))
+    got = _affine(href, h2b.best_multiexp(sc, pts))
+    assert (got == want).all()
+
+
+def test_msm_empty_is_identity(h2b, spec):
+    out = h2b.best_multiexp(np.zeros((0, 4), dtype=np.uint64), np.zeros((0, 8), dtype=np.uint64))
+    assert (out[:4] == 0).all() and (out[8:] == 0).all()
+    assert (out[4:8] == spec.ints_to_array([1], spec.Q_MOD)[0]).all()  # (0, R, 0)
+
+
+def test_msm_length_mismatch_asserts(h2b):
+    with pytest.raises(AssertionError):
+        h2b.best_multiexp(np.zeros((2, 4), dtype=np.uint64), np.zeros((3, 8), dtype=np.uint64))
+
+
+def test_msm_edge_scalars(h2b, spec, href):
+    n = 777
+    pts = href.random_g1(n, 42)
+    for name, vals in (("zeros", [0] * n), ("ones", [1] * n), ("r-1", [spec.R_MOD - 1] * n),
+                       ("mixed", [0, 1, spec.R_MOD - 1, 2, (1 << 253), (1 << 128) - 1, 1 << 16, (1 << 16) - 1] * 97 + [5])):
+        sc = spec.fr_array(vals[:n])
+        want = _affine(href, href.best_multiexp(sc, pts))
+        got = _affine(href, h2b.best_multiexp(sc, pts))
+        assert (got == want).all(), name
+    # unit scalars = plain point sum
+    acc = None
+    for p in spec.array_to_affine(pts[:50]):
+        acc = spec.g1_add(acc, p)
+    got = spec.jacobian_array_to_affine(h2b.best_multiexp(spec.fr_array([1] * 50), pts[:50].copy()))
+    assert got == acc
+
+
+def test_msm_degenerate_bases(h2b, spec, href):
+    n = 600
+    sc = href.random_fr(n, 9)
+    pts = href.random_g1(n, 10)
+    pts[::7] = 0                      # identity bases (0,0)
+    pts[1::7] = pts[1]                # one point repeated many times (same bucket doubling chains)
+    neg = spec.affine_to_array([spec.g1_neg(p) for p in spec.array_to_affine(pts[2:3])])
+    pts[2::7] = neg[0]                # -P next to P with equal scalars below
+    sc[2::7] = sc[1]
+    sc[1::7] = sc[1]
+    want = _affine(href, href.best_multiexp(sc, pts))
+    got = _affine(href, h2b.best_multiexp(sc, pts))
+    assert (got == want).all()
+    # everything cancels: sum s*P + s*(-P) = O
+    half = href.random_g1(64, 3)
+    negs = spec.affine_to_array([spec.g1_neg(p) for p in spec.array_to_affine(half)])
+    s = href.random_fr(64, 4)
+    out = h2b.best_multiexp(np.concatenate([s, s]), np.concatenate([half, negs]))
+    assert spec.jacobian_array_to_affine(out) is None
+
+
+def test_msm_witness_like_sparse(h2b, spec, href):
+    """~5% non-zero small values plus a few random tail rows, like an advice column."""
+    n = 1 << 14
+    rng = np.random.default_rng(7)
+    vals = [0] * n
+    for i in rng.choice(n - 8, size=n // 20, replace=False):
+        vals[int(i)] = int(rng.integers(1, 1 << 16))
+    tail = spec.random_fr(6, 99)
+    for t, v in enumerate(tail):
+        vals[n - 6 + t] = v
+    sc = spec.fr_array(vals)
+    pts = href.random_g1(n, 12)
+    want = _affine(href, href.best_multiexp(sc, pts))
+    assert (_affine(href, h2b.best_multiexp(sc, pts)) == want).all()
+    # heavy skew: every scalar equal (one bucket per window takes all points)
+    sc = spec.fr_array([0xDEADBEEFCAFE] * n)
+    want = _affine(href, href.best_multiexp(sc, pts))
+    assert (_affine(href, h2b.best_multiexp(sc, pts)) == want).all()
+
+
+@pytest.mark.parametrize("c", [4, 7, 10, 13, 16, 18])
+def test_msm_every_window_size(h2b, href, c):
+    from halo2_prover_b200 import _ffi
+    n = 3000
+    sc, pts = href.random_fr(n, 77), href.random_g1(n, 78)
+    want = _affine(href, href.best_multiexp(sc, pts))
+    _ffi.check(_ffi.lib().h2b_set_msm_window(c))
+    try:
+        got = _affine(href, h2b.best_multiexp(sc, pts))
+    finally:
+        _ffi.check(_ffi.lib().h2b_set_msm_window(0))
+    assert (got == want).all()
+
+
+def test_commit_against_registered_srs(h2b, spec, href):
+    k = 10
+    n = 1 << k
+    g, gl = href.random_g1(n, 1), href.random_g1(n, 2)
+    params = h2b.ParamsKZG(k, g, gl)
+    poly = href.random_fr(n, 3)
+    assert (_affine(href, params.commit(poly)) == _affine(href, href.best_multiexp(poly, g))).all()
+    assert (_affine(href, params.commit_lagrange(poly)) == _affine(href, href.best_multiexp(poly, gl))).all()
+    short = poly[:100].copy()  # commit of a shorter polynomial uses bases[0..size]
+    assert (_affine(href, params.commit(short)) == _affine(href, href.best_multiexp(short, g[:100].copy()))).all()
+    with pytest.raises(AssertionError):
+        params.commit(href.random_fr(n + 1, 4))
+    params.release()
+
+
+def test_commit_is_p_of_s_times_g(h2b, spec, href):
+    """Synthetic SRS with known s: commit(p) == [p(s)] G."""
+    k, s = 6, 0x1234567
+    n = 1 << k
+    G = spec.affine_to_array([spec.G1_GENERATOR])[0]
+    srs = np.zeros((n, 8), dtype=np.uint64)
+    for i in range(n):
+        srs[i] = href.g1_to_affine(href.g1_scalar_mul(G, spec.fr_array([pow(s, i, spec.R_MOD)])[0]))
+    coeffs = spec.random_fr(n, 8)
+    params = h2b.ParamsKZG(k, srs)
+    p_s = sum(c * pow(s, i, spec.R_MOD) for i, c in enumerate(coeffs)) % spec.R_MOD
+    want = href.g1_to_affine(href.g1_scalar_mul(G, spec.fr_array([p_s])[0]))
+    assert (_affine(href, params.commit(spec.fr_array(coeffs))) == want).all()
+    params.release()
+
+
+def test_golden_vectors(h2b, href):
+    for v in load_golden("spec_vectors.json")["msm"]:
+        jac = h2b.best_multiexp(unhx(v["scalars"], 4), unhx(v["bases"], 8))
+        assert (_affine(href, jac) == unhx(v["affine"], 8)[0]).all(), v["n"]
+
+
+def test_g1_fold(h2b, spec, href):
+    pts = href.random_g1(5, 31)
+    jac = np.zeros((6, 12), dtype=np.uint64)
+    one = spec.ints_to_array([1], spec.Q_MOD)[0]
+    for i in range(5):
+        jac[i, :8] = pts[i]
+        jac[i, 8:] = one
+    jac[5, 4:8] = one  # identity (0, R, 0)
+    acc = None
+    for p in spec.array_to_affine(pts):
+        acc = spec.g1_add(acc, p)
+    assert spec.jacobian_array_to_affine(h2b.g1_fold(jac)) == acc
+
+
+def test_large_msm_linearity(h2b, spec, href):
+    """2^20 points: MSM(a, P) + MSM(b, P) == MSM(a + b, P), and range-split partials fold to the whole."""
+    n = 1 << 20
+    pts = np.tile(href.random_g1(1 << 12, 50), (n >> 12, 1))
+    a, b = np.tile(href.random_fr(1 << 14, 51), (n >> 14, 1)), href.random_fr(n, 52)
+    ra, rb = h2b.best_multiexp(a, pts), h2b.best_multiexp(b, pts)
+    # a + b elementwise via the device test hook
+    import ctypes as C
+    from halo2_prover_b200 import _ffi
+    s = np.zeros_like(a)
+    _ffi.check(_ffi.lib().h2b_test_field_op(0, 1, _ffi.u64p(a), _ffi.u64p(b), _ffi.u64p(s), C.c_size_t(n)))
+    rs = h2b.best_multiexp(s, pts)
+    lhs = href.g1_to_affine(href.g1_add(ra, rb))
+    assert (lhs == href.g1_to_affine(rs)).all()
+    lo = h2b.best_multiexp(b[: n // 2].copy(), pts[: n // 2].copy())
+    hi = h2b.best_multiexp(b[n // 2:].copy(), pts[n // 2:].copy())
+    assert (href.g1_to_affine(h2b.g1_fold(np.stack([lo, hi]))) == href.g1_to_affine(rb)).all()
