@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MSM / NTT hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework on N B200s
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm on host cores
+
+A step is one BN254 G1 multi-scalar multiplication of 2^24 points per GPU (uniform random
+scalars, distinct random bases) -- the configuration the metric "MSM points/s (2^24)" is quoted
+on.  At N > 1 the MSM is sharded by point range (weak scaling: every rank owns 2^24 points of an
+N * 2^24-point MSM), each rank reduces its own buckets and the N partial sums (96 B each) are
+all-gathered over NCCL and folded on every GPU inside the step.  The second headline quantity,
+NTT elements/s at k = 20 (plus the coset extended-domain transform), is measured on rank 0 and
+reported under "ntt" in the same JSON line.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM),
+`e2e` is the same metric through the reference-facing call (ParamsKZG::commit ->
+h2b_commit) with pinned HOST scalars: the host->device copy of the step's scalars and the
+device->host read of the result are inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+MODMUL_IMAD = 272           # one 254-bit Montgomery product on 8x32-bit limbs
+MSM_MODMUL_PER_POINT = 160  # 16 signed 16-bit windows x 10-modmul XYZZ mixed add
+MSM_BYTES_PER_POINT = 96
+
+
+def rand_fr_np(n: int, seed: int) -> np.ndarray:
+    """n uniform values below 2^252 (< r), usable directly as Montgomery-form Fr limbs."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, np.iinfo(np.uint64).max, size=(n, 4), dtype=np.uint64, endpoint=True)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    return a
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks() -> dict:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import h2ref
+    threads = os.cpu_count() or 1
+    lg = args.ref_log_n
+    n = 1 << lg
+    scalars = h2ref.to_mont(rand_fr_np(n, 1))  # any value < r is a valid element; keep the oracle's convention
+    bases = h2ref.random_g1(1 << 12, 2)
+    bases = np.ascontiguousarray(np.tile(bases, (n >> 12, 1)))
+    for _ in range(args.warmup):
+        h2ref.best_multiexp(scalars, bases, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h2ref.best_multiexp(scalars, bases, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "msm_points_per_s", "value": val, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 Montgomery (int)", "data": "synthetic",
+        "config": {"workload": f"BN254 G1 MSM, bounded sample of 2^{lg} points per step (full config: 2^24)",
+                   "parallelism": f"{threads} host threads, contiguous chunks (best_multiexp)"},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": f"C restatement of halo2_proofs@6b43b6b best_multiexp (not the Rust binary), 2^{lg} points"},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------- this framework
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import halo2_prover_b200 as h2b  # raises if the CUDA library is missing: no fallback
+    from halo2_prover_b200 import _ffi, arithmetic, multi_gpu
+    import bn254
+
+    _ffi.init(local)
+    L = _ffi.lib()
+    n = 1 << args.log_n
+    stream = torch.cuda.Stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    # ---- inputs: pinned host scalars, device scalars, device bases (distinct random points)
+    host_scalars = torch.from_numpy(rand_fr_np(n, 1000 + rank).view(np.int64)).pin_memory()
+    gen = bn254.affine_to_array([bn254.G1_GENERATOR])[0]
+    with torch.cuda.stream(stream):
+        d_scalars = host_scalars.cuda(non_blocking=True)
+        seeds = torch.from_numpy(rand_fr_np(n, 2000 + rank).view(np.int64)).cuda()
+        d_bases = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        _ffi.check(L.h2b_dev_fixed_base_mul(C.c_void_p(seeds.data_ptr()), C.c_size_t(n), _ffi.u64p(gen),
+                                            C.c_void_p(d_bases.data_ptr()), sp))
+        stream.synchronize()
+        del seeds
+        out = torch.empty(12, dtype=torch.int64, device="cuda")
+
+        def step():
+            if world == 1:
+                arithmetic.dev_msm(d_scalars, d_bases, out, n=n, stream=stream)
+            else:
+                res = multi_gpu.sharded_multiexp(d_scalars, d_bases, stream=stream)
+                out.copy_(res)
+
+        imad, imad_w, _mhz = C.c_double(), C.c_double(), C.c_double()
+        _ffi.check(L.h2b_imad_peak(C.byref(imad), C.byref(imad_w), C.byref(_mhz)))
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        _ffi.check(L.h2b_set_kernel_timing(1))
+        launches0 = L.h2b_kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = L.h2b_kernel_launches() - launches0
+        ktot, kcalls = C.c_double(), C.c_uint32()
+        _ffi.check(L.h2b_kernel_time_collect(C.byref(ktot), C.byref(kcalls)))
+        _ffi.check(L.h2b_set_kernel_timing(0))
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / args.steps
+        value = world * n / (ms_step * 1e-3)
+
+    # ---- end to end through the reference-facing call: ParamsKZG::commit with pinned host scalars
+    bases_host = d_bases.cpu().numpy().view(np.uint64)
+    handle = C.c_uint64(0)
+    _ffi.check(L.h2b_srs_register(_ffi.u64p(bases_host), C.c_size_t(n), C.byref(handle)))
+    del bases_host
+    res_host = np.zeros(12, dtype=np.uint64)
+    hs_ptr = C.cast(C.c_void_p(host_scalars.data_ptr()), C.POINTER(C.c_uint64))
+
+    def e2e_step():
+        _ffi.check(L.h2b_commit(handle, hs_ptr, C.c_size_t(n), _ffi.u64p(res_host)))
+        if world > 1:
+            part = torch.from_numpy(res_host.view(np.int64)).cuda()
+            parts = multi_gpu.gather_partials(part)
+            folded = torch.empty(12, dtype=torch.int64, device="cuda")
+            arithmetic.dev_g1_fold(parts, folded, stream=torch.cuda.current_stream())
+            folded.cpu()
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(t.item())
+    # the device-resident and the end-to-end paths must agree on the result (rank-local shard)
+    if world == 1:
+        import h2ref
+        assert (h2ref.g1_to_affine(out.cpu().numpy().view(np.uint64)) == h2ref.g1_to_affine(res_host)).all()
+    _ffi.check(L.h2b_srs_release(handle))
+
+    # ---- NTT k = 20 (rank 0): forward best_fft and the coset extended-domain transform
+    ntt = None
+    if rank == 0 and not args.no_ntt:
+        ntt = bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, float(imad.value))
+
+    # ---- CPU baseline beside it (rank 0, N = 1): bounded sample on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import h2ref
+        threads = os.cpu_count() or 1
+        m = 1 << args.ref_log_n
+        sc = np.ascontiguousarray(host_scalars.numpy().view(np.uint64)[:m])
+        bs = np.ascontiguousarray(d_bases[:m].cpu().numpy().view(np.uint64))
+        t0 = time.perf_counter()
+        cpu_res = h2ref.best_multiexp(sc, bs, threads)
+        dt = time.perf_counter() - t0
+        check = np.zeros(12, dtype=np.uint64)
+        _ffi.check(L.h2b_best_multiexp(_ffi.u64p(sc), _ffi.u64p(bs), C.c_size_t(m), _ffi.u64p(check)))
+        assert (h2ref.g1_to_affine(cpu_res) == h2ref.g1_to_affine(check)).all(), "GPU and CPU baseline disagree"
+        cpu = {"value": m / dt, "unit": "points/s", "cores": threads, "kind": "port",
+               "sample": f"first 2^{args.ref_log_n} points of the workload; C restatement of halo2_proofs@6b43b6b "
+                         "best_multiexp (not the Rust binary); result equal to the GPU's on the same sample"}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        acc_ms = ktot.value / max(kcalls.value, 1)
+        imad_per_launch = float(n) * MSM_MODMUL_PER_POINT * MODMUL_IMAD
+        achieved = imad_per_launch / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+        peak = imad.value / 1e3
+        hbm_peak = peaks.get("hbm_gbs")
+        line = {
+            "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32x8 Montgomery (int)", "data": "synthetic",
+            "config": {"workload": f"BN254 G1 MSM, 2^{args.log_n} points per GPU, uniform scalars, distinct random bases",
+                       "global_points": world * n, "parallelism": f"point-range shards x{world}, all-gather of 96 B partials",
+                       "l2": "inputs (1.5 GiB per step) exceed L2; no flush needed",
+                       "ntt_workload": "best_fft k=20 and coeff_to_extended 18->20, 8 rotating buffers (256 MiB > L2)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
+                    "api": "ParamsKZG.commit -> h2b_commit, pinned host scalars, SRS resident"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "TIMAD/s", "frac": (achieved / peak) if achieved and peak else None,
+                         "traffic": None, "launch_ms": acc_ms,
+                         "algorithmic": "43,520 IMAD-class/point (160 modmul x 272) x 2^%d points per launch" % args.log_n,
+                         "peak_source": "measured live: mad.lo.u32 microbenchmark (h2b_imad_peak); "
+                                        "IMAD.WIDE rate %.1f G/s" % imad_w.value,
+                         "hbm": {"achieved_gbs": n * MSM_BYTES_PER_POINT / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
+                                 "peak_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if hbm_peak else "absent"}},
+            "cpu_baseline": cpu,
+            "ntt": ntt,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, imad_gops) -> dict:
+    import bn254 as o
+    k = args.ntt_k
+    n = 1 << k
+    nbuf = 8
+    omega = o.fr_array([pow(o.ROOT_OF_UNITY, 1 << (o.FR_S - k), o.R_MOD)])[0]
+    host = torch.from_numpy(rand_fr_np(n, 77).view(np.int64)).pin_memory()
+    with torch.cuda.stream(stream):
+        bufs = [host.cuda(non_blocking=True).clone() for _ in range(nbuf)]
+        for b in bufs[:3]:
+            arithmetic.dev_best_fft(b, omega, k, stream=stream)
+        stream.synchronize()
+        _ffi.check(L.h2b_set_kernel_timing(1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 4 * nbuf
+        e0.record(stream)
+        for i in range(reps):
+            arithmetic.dev_best_fft(bufs[i % nbuf], omega, k, stream=stream)
+        e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        ktot, kcalls = C.c_double(), C.c_uint32()
+        _ffi.check(L.h2b_kernel_time_collect(C.byref(ktot), C.byref(kcalls)))
+        _ffi.check(L.h2b_set_kernel_timing(0))
+        kms = ktot.value / max(kcalls.value, 1)
+        # coset extended-domain transform 2^(k-2) -> 2^k
+        d = h2b.EvaluationDomain(4, k - 2)
+        ins = [b[: n // 4] for b in bufs]
+        outs = [torch.empty((n, 4), dtype=torch.int64, device="cuda") for _ in range(nbuf)]
+        for i in range(3):
+            d.dev_coeff_to_extended(ins[i], outs[i], stream=stream)
+        stream.synchronize()
+        e0.record(stream)
+        for i in range(reps):
+            d.dev_coeff_to_extended(ins[i % nbuf], outs[i % nbuf], stream=stream)
+        e1.record(stream)
+        stream.synchronize()
+        ms_ext = e0.elapsed_time(e1) / reps
+    # end to end through the host API (best_fft in place on a pinned host buffer)
+    a = host.numpy().view(np.uint64).copy()
+    ha = torch.from_numpy(a.view(np.int64)).pin_memory()
+    pa = C.cast(C.c_void_p(ha.data_ptr()), C.POINTER(C.c_uint64))
+    for _ in range(2):
+        _ffi.check(L.h2b_best_fft(pa, _ffi.u64p(omega), C.c_uint32(k)))
+    t0 = time.perf_counter()
+    for _ in range(5):
+        _ffi.check(L.h2b_best_fft(pa, _ffi.u64p(omega), C.c_uint32(k)))
+    e2e_ms = (time.perf_counter() - t0) / 5 * 1e3
+    peaks = measured_peaks()
+    modmul = n // 2 * k
+    imad_achieved = modmul * MODMUL_IMAD / (kms * 1e-3) / 1e12 if kms > 0 else None
+    hbm_achieved = 64.0 * n / (kms * 1e-3) / 1e9 if kms > 0 else None
+    out = {
+        "k": k, "elems_per_s": n / (ms * 1e-3), "ms": ms, "kernels_ms": kms,
+        "coeff_to_extended": {"from_k": k - 2, "to_k": k, "ms": ms_ext, "out_elems_per_s": n / (ms_ext * 1e-3)},
+        "e2e": {"ms": e2e_ms, "elems_per_s": n / (e2e_ms * 1e-3), "h2d_bytes": n * 32, "d2h_bytes": n * 32,
+                "api": "best_fft -> h2b_best_fft, pinned host buffer, in place"},
+        "roofline": {"bound": "imad", "achieved": imad_achieved, "peak": imad_gops / 1e3, "unit": "TIMAD/s",
+                     "frac": imad_achieved / (imad_gops / 1e3) if imad_achieved else None,
+                     "algorithmic": "(n/2)*k modmul x 272 IMAD; 64*n compulsory bytes",
+                     "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": peaks.get("hbm_gbs"),
+                             "frac": hbm_achieved / peaks["hbm_gbs"] if hbm_achieved and peaks.get("hbm_gbs") else None}},
+    }
+    if not args.no_cpu:
+        import h2ref
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        h2ref.best_fft(a, omega, k, threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / dt, "unit": "elems/s", "cores": threads, "kind": "port",
+                               "sample": f"one best_fft of 2^{k} (C restatement of halo2_proofs@6b43b6b)"}
+    return out
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=24, help="log2 points per GPU")
+    ap.add_argument("--ntt-k", type=int, default=20)
+    ap.add_argument("--ref-log-n", type=int, default=18, help="log2 points of the bounded CPU sample")
+    ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
