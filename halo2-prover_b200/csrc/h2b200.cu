@@ -34,7 +34,7 @@ std::mutex g_mu;
 
 enum BufId {
     BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_OFFSETS, BUF_CURSOR, BUF_TASKOFF, BUF_SORTED,
-    BUF_BUCKETS, BUF_PARTIALS, BUF_WINDOWS, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
+    BUF_BUCKETS, BUF_PARTIALS, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
     BUF_NTT_OUT, BUF_MISC,
     BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
 };
@@ -185,8 +185,9 @@ MsmCfg msm_plan(size_t n) {
     uint32_t t = 256;
     while ((size_t)t * t < n) t <<= 1;
     cfg.task = t;
-    uint32_t lgrp = 0;  // groups of 2^lgrp buckets, at most 256 groups per window
-    while ((cfg.bpw >> lgrp) > 256) lgrp++;
+    // reduction groups of 2^lgrp buckets: 16 per group once a window has >= 4096 buckets
+    uint32_t lgrp = 0;
+    while (lgrp < 4 && (cfg.bpw >> lgrp) > 256) lgrp++;
     cfg.lgrp = lgrp;
     return cfg;
 }
@@ -209,6 +210,7 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_ou
     size_t max_tasks = (size_t)cfg.nb + entries / cfg.task + 1;
     uint32_t *counts, *offsets, *cursor, *task_off, *sorted;
     XYZZ *buckets, *partials, *windows;
+    uint2 *block_sums;
     TRY(get_buf(BUF_COUNTS, (size_t)cfg.nb * 4, (void **)&counts));
     TRY(get_buf(BUF_OFFSETS, (size_t)cfg.nb * 4, (void **)&offsets));
     TRY(get_buf(BUF_CURSOR, (size_t)cfg.nb * 4, (void **)&cursor));
@@ -217,13 +219,21 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_ou
     TRY(get_buf(BUF_BUCKETS, (size_t)cfg.nb * sizeof(XYZZ), (void **)&buckets));
     TRY(get_buf(BUF_PARTIALS, max_tasks * sizeof(XYZZ), (void **)&partials));
     TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
+    TRY(get_buf(BUF_BLOCKSUMS, 1024 * sizeof(uint2), (void **)&block_sums));
 
     CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
     CU(cudaMemsetAsync(buckets, 0, (size_t)cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
     uint32_t nblk = (uint32_t)((n + 255) / 256);
     msm_digits_kernel<0><<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, nullptr);
     LAUNCHED();
-    msm_scan_kernel<<<1, 1024, 0, s>>>(counts, cfg.nb, cfg.task, offsets, cursor, task_off);
+    uint32_t ipt = (cfg.nb + 1024 * 1024 - 1) / (1024 * 1024);
+    uint32_t sblocks = (cfg.nb + 1024 * ipt - 1) / (1024 * ipt);
+    msm_scan_sums_kernel<<<sblocks, 1024, 0, s>>>(counts, cfg.nb, cfg.task, ipt, block_sums);
+    LAUNCHED();
+    msm_scan_blocks_kernel<<<1, 1024, 0, s>>>(block_sums, sblocks, cfg.nb, task_off);
+    LAUNCHED();
+    msm_scan_apply_kernel<<<sblocks, 1024, 0, s>>>(counts, cfg.nb, cfg.task, ipt, block_sums, offsets, cursor,
+                                                  task_off);
     LAUNCHED();
     msm_digits_kernel<1><<<nblk, 256, 0, s>>>(d_scalars, cfg, cursor, sorted);
     LAUNCHED();
@@ -234,8 +244,14 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_ou
     time_end(s);
     msm_combine_kernel<<<(cfg.nb + 127) / 128, 128, 0, s>>>(counts, task_off, cfg, partials, buckets);
     LAUNCHED();
-    uint32_t G = cfg.bpw >> cfg.lgrp;
-    msm_reduce_kernel<<<cfg.windows, G, G * sizeof(XYZZ), s>>>(buckets, cfg, windows);
+    uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
+    uint32_t rthreads = G < 256 ? G : 256;      // power of two
+    uint32_t per_window = G / rthreads;         // blocks (= partials) per window
+    XYZZ *wpart;
+    TRY(get_buf(BUF_WPART, (size_t)cfg.windows * per_window * sizeof(XYZZ), (void **)&wpart));
+    msm_reduce_kernel<<<dim3(per_window, cfg.windows), rthreads, rthreads * sizeof(XYZZ), s>>>(buckets, cfg, wpart);
+    LAUNCHED();
+    msm_window_fold_kernel<<<cfg.windows, 32, 0, s>>>(wpart, per_window, windows);
     LAUNCHED();
     msm_final_kernel<<<1, 32, 0, s>>>(windows, cfg, d_out);
     LAUNCHED();
@@ -303,8 +319,29 @@ int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log
     return H2B_OK;
 }
 
+uint32_t g_ntt_tile_log = 9;  // log2 elements per multi-pass tile (9, 10 or 11); 9 measured best on B200
+
 int dispatch_pass(uint32_t S, bool single, const Fe *in, Fe *out, const Fe *W, uint32_t log_n,
                   uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s) {
+    if (!single && g_ntt_tile_log == 10) {
+        switch (S) {
+            case 5: return launch_pass<5, 32, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 6: return launch_pass<6, 16, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 8, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 4, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 9: return launch_pass<9, 2, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 10: return launch_pass<10, 1, 256>(in, out, W, log_n, log_ns, last, io, s);
+        }
+    }
+    if (!single && g_ntt_tile_log == 9) {
+        switch (S) {
+            case 5: return launch_pass<5, 16, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 6: return launch_pass<6, 8, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 4, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 2, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 9: return launch_pass<9, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
+        }
+    }
     if (single) {
         switch (S) {
             case 1: return launch_pass<1, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
@@ -653,6 +690,12 @@ int h2b_init(int device) {
         int v = atoi(mr);
         if (v >= 5 && v <= 10) g_ntt_max_radix = (uint32_t)v;
     }
+    const char *tl = getenv("H2B_NTT_TILE_LOG");
+    if (tl) {
+        int v = atoi(tl);
+        if (v >= 9 && v <= 11) g_ntt_tile_log = (uint32_t)v;
+    }
+    if (g_ntt_tile_log == 9 && g_ntt_max_radix > 9) g_ntt_max_radix = 9;
     g = c;
     return H2B_OK;
 }

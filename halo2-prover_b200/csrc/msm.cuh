@@ -78,22 +78,78 @@ __global__ void msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg,
     }
 }
 
-// Single-block exclusive scans over the nb buckets:
+// Exclusive scans over the nb buckets in three small launches (block sums, scan of block sums,
+// rescan with offsets):
 //   offsets[b] / cursor[b] = sum_{b' < b} counts[b']
 //   task_off[b]            = sum_{b' < b} ceil(counts[b'] / T);  task_off[nb] = total
+// Blocks of 1024 threads, `ipt` consecutive buckets per thread, at most 1024 blocks.
 __global__ void __launch_bounds__(1024)
-msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t T,
-                uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
-                uint32_t *__restrict__ task_off) {
+msm_scan_sums_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t T, uint32_t ipt,
+                     uint2 *__restrict__ block_sums) {
+    __shared__ uint32_t wa[32], wb[32];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lo = (blockIdx.x * 1024 + tid) * ipt;
+    uint32_t sa = 0, sb = 0;
+    for (uint32_t k = 0; k < ipt; k++) {
+        uint32_t b = lo + k;
+        if (b < nb) {
+            uint32_t cnt = counts[b];
+            sa += cnt;
+            sb += (cnt + T - 1) / T;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        sa += __shfl_down_sync(0xffffffffu, sa, d);
+        sb += __shfl_down_sync(0xffffffffu, sb, d);
+    }
+    if ((tid & 31) == 0) { wa[tid >> 5] = sa; wb[tid >> 5] = sb; }
+    __syncthreads();
+    if (tid < 32) {
+        sa = wa[tid];
+        sb = wb[tid];
+        for (int d = 16; d > 0; d >>= 1) {
+            sa += __shfl_down_sync(0xffffffffu, sa, d);
+            sb += __shfl_down_sync(0xffffffffu, sb, d);
+        }
+        if (tid == 0) block_sums[blockIdx.x] = make_uint2(sa, sb);
+    }
+}
+// One block: exclusive scan of the (<= 1024) block sums in place; totals to task_off[nb].
+__global__ void __launch_bounds__(1024)
+msm_scan_blocks_kernel(uint2 *__restrict__ block_sums, uint32_t nblocks, uint32_t nb,
+                       uint32_t *__restrict__ task_off) {
     __shared__ uint32_t sh_a[1024], sh_b[1024];
     const uint32_t tid = threadIdx.x;
-    const uint32_t per = (nb + 1023) / 1024;
-    const uint32_t lo = tid * per, hi = min(lo + per, nb);
+    uint2 v = tid < nblocks ? block_sums[tid] : make_uint2(0, 0);
+    sh_a[tid] = v.x;
+    sh_b[tid] = v.y;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint32_t va = 0, vb = 0;
+        if (tid >= d) { va = sh_a[tid - d]; vb = sh_b[tid - d]; }
+        __syncthreads();
+        sh_a[tid] += va;
+        sh_b[tid] += vb;
+        __syncthreads();
+    }
+    if (tid < nblocks) block_sums[tid] = make_uint2(sh_a[tid] - v.x, sh_b[tid] - v.y);
+    if (tid == 1023) task_off[nb] = sh_b[1023];
+}
+__global__ void __launch_bounds__(1024)
+msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t T, uint32_t ipt,
+                      const uint2 *__restrict__ block_sums, uint32_t *__restrict__ offsets,
+                      uint32_t *__restrict__ cursor, uint32_t *__restrict__ task_off) {
+    __shared__ uint32_t sh_a[1024], sh_b[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lo = (blockIdx.x * 1024 + tid) * ipt;
     uint32_t sa = 0, sb = 0;
-    for (uint32_t b = lo; b < hi; b++) {
-        uint32_t cnt = counts[b];
-        sa += cnt;
-        sb += (cnt + T - 1) / T;
+    for (uint32_t k = 0; k < ipt; k++) {
+        uint32_t b = lo + k;
+        if (b < nb) {
+            uint32_t cnt = counts[b];
+            sa += cnt;
+            sb += (cnt + T - 1) / T;
+        }
     }
     sh_a[tid] = sa;
     sh_b[tid] = sb;
@@ -106,16 +162,19 @@ msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t T,
         sh_b[tid] += vb;
         __syncthreads();
     }
-    uint32_t ra = sh_a[tid] - sa, rb = sh_b[tid] - sb;  // exclusive prefix of this thread's range
-    for (uint32_t b = lo; b < hi; b++) {
-        uint32_t cnt = counts[b];
-        offsets[b] = ra;
-        cursor[b] = ra;
-        task_off[b] = rb;
-        ra += cnt;
-        rb += (cnt + T - 1) / T;
+    const uint2 base = block_sums[blockIdx.x];
+    uint32_t ra = base.x + sh_a[tid] - sa, rb = base.y + sh_b[tid] - sb;
+    for (uint32_t k = 0; k < ipt; k++) {
+        uint32_t b = lo + k;
+        if (b < nb) {
+            uint32_t cnt = counts[b];
+            offsets[b] = ra;
+            cursor[b] = ra;
+            task_off[b] = rb;
+            ra += cnt;
+            rb += (cnt + T - 1) / T;
+        }
     }
-    if (tid == 1023) task_off[nb] = sh_b[1023];
 }
 
 // One thread per task.  task_off is non-decreasing; the owning bucket is the last b with
@@ -185,13 +244,16 @@ msm_combine_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restri
     store_xyzz(&bucket_sums[b], acc);
 }
 
-// Per window: sum_{k=1..bpw} k * B_k.  Block = one window, thread g owns buckets
-// k in (g*L, (g+1)*L]; blockDim.x = bpw / L (power of two, <= 256).
+// Per window: sum_{k=1..bpw} k * B_k.  Grid = (blocks per window, windows); thread g of a window
+// owns the L = 2^lgrp buckets k in (g*L, (g+1)*L]: running sums give sum (k - g*L) * B_k, the group
+// offset (g*L) * sum B_k is added by a short double-and-add, a shared-memory tree folds the block,
+// and each block writes one partial (window_partials[w * gridDim.x + blockIdx.x]).
 __global__ void __launch_bounds__(256)
-msm_reduce_kernel(const XYZZ *__restrict__ bucket_sums, MsmCfg cfg, XYZZ *__restrict__ window_sums) {
+msm_reduce_kernel(const XYZZ *__restrict__ bucket_sums, MsmCfg cfg, XYZZ *__restrict__ window_partials) {
     extern __shared__ uint4 red_smem[];
     XYZZ *sh = reinterpret_cast<XYZZ *>(red_smem);
-    const uint32_t w = blockIdx.x, g = threadIdx.x, G = blockDim.x;
+    const uint32_t w = blockIdx.y, tid = threadIdx.x, G = blockDim.x;
+    const uint32_t g = blockIdx.x * G + tid;  // group index inside the window
     const uint32_t L = 1u << cfg.lgrp;
     const XYZZ *bk = bucket_sums + (size_t)w * cfg.bpw + (size_t)g * L;
     XYZZ running = xyzz_identity(), acc = xyzz_identity();
@@ -201,7 +263,7 @@ msm_reduce_kernel(const XYZZ *__restrict__ bucket_sums, MsmCfg cfg, XYZZ *__rest
         xyzz_add(acc, running);
     }
     // acc = sum (k - g*L) * B_k ; add (g*L) * running = 2^lgrp * (g * running)
-    if (g != 0) {
+    if (g != 0 && !xyzz_is_identity(running)) {
         XYZZ t = xyzz_identity();
         for (int bit = 31 - __clz(g); bit >= 0; bit--) {
             t = xyzz_dbl_ni(t);
@@ -210,18 +272,44 @@ msm_reduce_kernel(const XYZZ *__restrict__ bucket_sums, MsmCfg cfg, XYZZ *__rest
         for (uint32_t d = 0; d < cfg.lgrp; d++) t = xyzz_dbl_ni(t);
         xyzz_add(acc, t);
     }
-    store_xyzz(&sh[g], acc);
+    store_xyzz(&sh[tid], acc);
     __syncthreads();
     for (uint32_t stride = G >> 1; stride > 0; stride >>= 1) {
-        if (g < stride) {
-            XYZZ a = load_xyzz(&sh[g]);
-            XYZZ b2 = load_xyzz(&sh[g + stride]);
+        if (tid < stride) {
+            XYZZ a = load_xyzz(&sh[tid]);
+            XYZZ b2 = load_xyzz(&sh[tid + stride]);
             xyzz_add(a, b2);
-            store_xyzz(&sh[g], a);
+            store_xyzz(&sh[tid], a);
         }
         __syncthreads();
     }
-    if (g == 0) store_xyzz(&window_sums[w], load_xyzz(&sh[0]));
+    if (tid == 0) store_xyzz(&window_partials[(size_t)w * gridDim.x + blockIdx.x], load_xyzz(&sh[0]));
+}
+
+// Fold the per-block partials of each window: one warp-sized block per window.
+__global__ void __launch_bounds__(32)
+msm_window_fold_kernel(const XYZZ *__restrict__ window_partials, uint32_t per_window,
+                       XYZZ *__restrict__ window_sums) {
+    __shared__ uint4 fold_smem[32 * 8];
+    XYZZ *sh = reinterpret_cast<XYZZ *>(fold_smem);
+    const uint32_t w = blockIdx.x, lane = threadIdx.x;
+    XYZZ acc = xyzz_identity();
+    for (uint32_t i = lane; i < per_window; i += 32) {
+        XYZZ p = load_xyzz(&window_partials[(size_t)w * per_window + i]);
+        xyzz_add(acc, p);
+    }
+    store_xyzz(&sh[lane], acc);
+    __syncwarp();
+    for (uint32_t stride = 16; stride > 0; stride >>= 1) {
+        if (lane < stride) {
+            XYZZ a = load_xyzz(&sh[lane]);
+            XYZZ b2 = load_xyzz(&sh[lane + stride]);
+            xyzz_add(a, b2);
+            store_xyzz(&sh[lane], a);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) store_xyzz(&window_sums[w], load_xyzz(&sh[0]));
 }
 
 // Horner over windows, high to low; result as a Jacobian point (96 B).

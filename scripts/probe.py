@@ -30,12 +30,12 @@ def main():
     res["imad_gops"], res["imad_wide_gops"], res["sm_mhz_attr"] = a.value, b.value, c.value
     print("IMAD peak G/s", a.value, "IMAD.WIDE G/s", b.value, flush=True)
     s = torch.cuda.Stream()
-    sizes = [int(x) for x in os.environ.get("PROBE_MSM", "16,20,22,24").split(",")]
+    sizes = [int(x) for x in os.environ.get("PROBE_MSM", "16,20,22,24").split(",") if x not in ("", "none")]
     gen = np.array([1, 0, 0, 0, 2, 0, 0, 0], dtype=np.uint64)
     import bn254
     gen = bn254.affine_to_array([bn254.G1_GENERATOR])[0]
     with torch.cuda.stream(s):
-        nmax = 1 << max(sizes)
+        nmax = 1 << max(sizes + [4])
         sc_all = torch.from_numpy(rand_fr_np(nmax, 1).view(np.int64)).cuda()
         seeds = torch.from_numpy(rand_fr_np(nmax, 2).view(np.int64)).cuda()
         bases = torch.empty((nmax, 8), dtype=torch.int64, device="cuda")
@@ -70,7 +70,7 @@ def main():
         _ffi.check(L.h2b_set_msm_window(0))
         del bases, seeds, sc_all
         import bn254 as o
-        for k in [int(x) for x in os.environ.get("PROBE_NTT", "10,14,16,18,20,22,24").split(",")]:
+        for k in [int(x) for x in os.environ.get("PROBE_NTT", "10,14,16,18,20,22,24").split(",") if x not in ("", "none")]:
             n = 1 << k
             om = o.fr_array([pow(o.ROOT_OF_UNITY, 1 << (28 - k), o.R_MOD)])[0]
             a_t = torch.from_numpy(rand_fr_np(n, 3).view(np.int64)).cuda()
