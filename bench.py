@@ -41,10 +41,18 @@ MSM_BYTES_PER_POINT = 96
 
 
 def rand_fr_np(n: int, seed: int) -> np.ndarray:
-    """n uniform values below 2^252 (< r), usable directly as Montgomery-form Fr limbs."""
+    """n values uniform in [0, r) (rejection on the top limb), usable directly as Montgomery-form Fr
+    limbs: every value below r is the Montgomery representative of exactly one field element."""
     rng = np.random.default_rng(seed)
+    r3 = np.uint64(0x30644E72E131A029)  # top limb of r
     a = rng.integers(0, np.iinfo(np.uint64).max, size=(n, 4), dtype=np.uint64, endpoint=True)
-    a[:, 3] &= np.uint64((1 << 60) - 1)
+    a[:, 3] &= np.uint64((1 << 62) - 1)
+    bad = a[:, 3] >= r3
+    while bad.any():
+        m = int(bad.sum())
+        a[bad] = rng.integers(0, np.iinfo(np.uint64).max, size=(m, 4), dtype=np.uint64, endpoint=True)
+        a[:, 3] &= np.uint64((1 << 62) - 1)
+        bad = a[:, 3] >= r3
     return a
 
 

@@ -34,7 +34,7 @@ std::mutex g_mu;
 
 enum BufId {
     BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_OFFSETS, BUF_CURSOR, BUF_TASKOFF, BUF_SORTED,
-    BUF_BUCKETS, BUF_PARTIALS, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
+    BUF_BUCKETS, BUF_PARTIALS, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
     BUF_NTT_OUT, BUF_MISC,
     BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
 };
@@ -168,10 +168,12 @@ MsmCfg msm_plan(size_t n) {
     MsmCfg cfg{};
     cfg.n = (uint32_t)n;
     uint32_t lg = ceil_log2(n);
-    uint32_t c = g->msm_window ? g->msm_window : (lg > 4 ? lg - 4 : 0);
+    // window: measured optimum on B200 is lg(n) - 5 for n >= 2^19 (17 at 2^22..2^24; beyond that the
+    // shrinking bucket load costs more in lane divergence than the saved window gains)
+    uint32_t c = g->msm_window ? g->msm_window : (lg >= 19 ? lg - 5 : (lg > 4 ? lg - 4 : 0));
     if (!g->msm_window) {
         if (c < 4) c = 4;
-        if (c > 16) c = 16;
+        if (c > 17) c = 17;
     }
     if (c < 2) c = 2;
     if (c > 22) c = 22;
@@ -182,8 +184,11 @@ MsmCfg msm_plan(size_t n) {
     cfg.windows = W;
     cfg.bpw = 1u << (c - 1);
     cfg.nb = W * cfg.bpw;
-    uint32_t t = 256;
-    while ((size_t)t * t < n) t <<= 1;
+    // task = at most T consecutive entries of one bucket; T = 2x the mean bucket load (rounded up to a
+    // power of two, >= 64) so that ordinary buckets are one task and heavy ones split evenly
+    uint64_t mean2 = 2 * ((uint64_t)n / cfg.bpw + 1);
+    uint32_t t = 64;
+    while (t < mean2) t <<= 1;
     cfg.task = t;
     // reduction groups of 2^lgrp buckets: 16 per group once a window has >= 4096 buckets
     uint32_t lgrp = 0;
@@ -211,6 +216,7 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_ou
     uint32_t *counts, *offsets, *cursor, *task_off, *sorted;
     XYZZ *buckets, *partials, *windows;
     uint2 *block_sums;
+    uint32_t *heavy;
     TRY(get_buf(BUF_COUNTS, (size_t)cfg.nb * 4, (void **)&counts));
     TRY(get_buf(BUF_OFFSETS, (size_t)cfg.nb * 4, (void **)&offsets));
     TRY(get_buf(BUF_CURSOR, (size_t)cfg.nb * 4, (void **)&cursor));
@@ -220,8 +226,10 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_ou
     TRY(get_buf(BUF_PARTIALS, max_tasks * sizeof(XYZZ), (void **)&partials));
     TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
     TRY(get_buf(BUF_BLOCKSUMS, 1024 * sizeof(uint2), (void **)&block_sums));
+    TRY(get_buf(BUF_HEAVY, (entries / cfg.task + 2) * 4, (void **)&heavy));
 
     CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
+    CU(cudaMemsetAsync(heavy, 0, 4, s));
     CU(cudaMemsetAsync(buckets, 0, (size_t)cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
     uint32_t nblk = (uint32_t)((n + 255) / 256);
     msm_digits_kernel<0><<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, nullptr);
@@ -233,7 +241,7 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_ou
     msm_scan_blocks_kernel<<<1, 1024, 0, s>>>(block_sums, sblocks, cfg.nb, task_off);
     LAUNCHED();
     msm_scan_apply_kernel<<<sblocks, 1024, 0, s>>>(counts, cfg.nb, cfg.task, ipt, block_sums, offsets, cursor,
-                                                  task_off);
+                                                  task_off, heavy);
     LAUNCHED();
     msm_digits_kernel<1><<<nblk, 256, 0, s>>>(d_scalars, cfg, cursor, sorted);
     LAUNCHED();
@@ -242,7 +250,7 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_ou
         d_bases, sorted, offsets, counts, task_off, cfg, buckets, partials);
     LAUNCHED();
     time_end(s);
-    msm_combine_kernel<<<(cfg.nb + 127) / 128, 128, 0, s>>>(counts, task_off, cfg, partials, buckets);
+    msm_combine_kernel<<<g->sm_count * 4, 128, 0, s>>>(counts, task_off, heavy, cfg, partials, buckets);
     LAUNCHED();
     uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
     uint32_t rthreads = G < 256 ? G : 256;      // power of two

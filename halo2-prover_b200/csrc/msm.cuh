@@ -138,7 +138,8 @@ msm_scan_blocks_kernel(uint2 *__restrict__ block_sums, uint32_t nblocks, uint32_
 __global__ void __launch_bounds__(1024)
 msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t T, uint32_t ipt,
                       const uint2 *__restrict__ block_sums, uint32_t *__restrict__ offsets,
-                      uint32_t *__restrict__ cursor, uint32_t *__restrict__ task_off) {
+                      uint32_t *__restrict__ cursor, uint32_t *__restrict__ task_off,
+                      uint32_t *__restrict__ heavy /* [0] = count, [1..] = bucket ids */) {
     __shared__ uint32_t sh_a[1024], sh_b[1024];
     const uint32_t tid = threadIdx.x;
     const uint32_t lo = (blockIdx.x * 1024 + tid) * ipt;
@@ -173,6 +174,7 @@ msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t
             task_off[b] = rb;
             ra += cnt;
             rb += (cnt + T - 1) / T;
+            if (cnt > T) heavy[1 + atomicAdd(&heavy[0], 1u)] = b;  // split into several tasks
         }
     }
 }
@@ -226,22 +228,39 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
     else store_xyzz(&partials[t], acc);
 }
 
-// Buckets split into several tasks: fold their partial sums.
+// Buckets that were split into several tasks ("heavy": skewed scalars, or the short top window):
+// one block per heavy bucket folds its partial sums -- threads stride over the partials, then a
+// shared-memory tree.  The grid is persistent and walks the heavy list built by the scan.
 __global__ void __launch_bounds__(128)
 msm_combine_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ task_off,
-                   MsmCfg cfg, const XYZZ *__restrict__ partials, XYZZ *__restrict__ bucket_sums) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= cfg.nb) return;
-    uint32_t cnt = counts[b];
-    uint32_t ntasks = (cnt + cfg.task - 1) / cfg.task;
-    if (ntasks <= 1) return;
-    uint32_t t0 = task_off[b];
-    XYZZ acc = load_xyzz(&partials[t0]);
-    for (uint32_t k = 1; k < ntasks; k++) {
-        XYZZ q = load_xyzz(&partials[t0 + k]);
-        xyzz_add(acc, q);
+                   const uint32_t *__restrict__ heavy, MsmCfg cfg, const XYZZ *__restrict__ partials,
+                   XYZZ *__restrict__ bucket_sums) {
+    __shared__ uint4 comb_smem[128 * 8];
+    XYZZ *sh = reinterpret_cast<XYZZ *>(comb_smem);
+    const uint32_t nheavy = heavy[0], tid = threadIdx.x;
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const uint32_t b = heavy[1 + h];
+        const uint32_t ntasks = (counts[b] + cfg.task - 1) / cfg.task;
+        const uint32_t t0 = task_off[b];
+        XYZZ acc = xyzz_identity();
+        for (uint32_t k = tid; k < ntasks; k += 128) {
+            XYZZ q = load_xyzz(&partials[t0 + k]);
+            xyzz_add(acc, q);
+        }
+        store_xyzz(&sh[tid], acc);
+        __syncthreads();
+        for (uint32_t stride = 64; stride > 0; stride >>= 1) {
+            if (tid < stride && tid + stride < ntasks) {
+                XYZZ a = load_xyzz(&sh[tid]);
+                XYZZ b2 = load_xyzz(&sh[tid + stride]);
+                xyzz_add(a, b2);
+                store_xyzz(&sh[tid], a);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) store_xyzz(&bucket_sums[b], load_xyzz(&sh[0]));
+        __syncthreads();
     }
-    store_xyzz(&bucket_sums[b], acc);
 }
 
 // Per window: sum_{k=1..bpw} k * B_k.  Grid = (blocks per window, windows); thread g of a window

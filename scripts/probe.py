@@ -16,8 +16,15 @@ from halo2_prover_b200 import _ffi, arithmetic  # noqa: E402
 
 def rand_fr_np(n, seed):
     rng = np.random.default_rng(seed)
-    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
-    a[:, 3] &= np.uint64((1 << 60) - 1)  # < 2^252 < r: valid Montgomery representatives
+    r3 = np.uint64(0x30644E72E131A029)
+    a = rng.integers(0, np.iinfo(np.uint64).max, size=(n, 4), dtype=np.uint64, endpoint=True)
+    a[:, 3] &= np.uint64((1 << 62) - 1)
+    bad = a[:, 3] >= r3
+    while bad.any():
+        m = int(bad.sum())
+        a[bad] = rng.integers(0, np.iinfo(np.uint64).max, size=(m, 4), dtype=np.uint64, endpoint=True)
+        a[:, 3] &= np.uint64((1 << 62) - 1)
+        bad = a[:, 3] >= r3
     return a
 
 
