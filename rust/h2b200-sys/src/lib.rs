@@ -1,0 +1,140 @@
+//! Raw + safe bindings of `include/h2b200.h`.
+//!
+//! NOTE: this crate is shipped as source.  The build image of this repository has no Rust
+//! toolchain (no cargo/rustc, no network), so it has not been compiled here; the C ABI it binds
+//! is exercised through the identical ctypes binding in `halo2-prover_b200/_ffi.py`.
+//!
+//! Layout contract (checked by the static asserts below): `Fr`/`Fq` = `[u64; 4]` Montgomery limbs,
+//! `G1Affine` = 64 bytes `{x, y}`, `G1` = 96 bytes `{x, y, z}` -- what halo2curves 0.3.2 stores.
+#![cfg(not(target_family = "wasm"))]
+
+use core::ffi::{c_char, c_int, c_void};
+use halo2curves::bn256::{Fr, G1Affine, G1};
+
+const _: () = assert!(core::mem::size_of::<Fr>() == 32 && core::mem::align_of::<Fr>() == 8);
+const _: () = assert!(core::mem::size_of::<G1Affine>() == 64);
+const _: () = assert!(core::mem::size_of::<G1>() == 96);
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct H2bDomain {
+    pub k: u32,
+    pub extended_k: u32,
+    pub j: u32,
+    pub n_t: u32,
+    pub omega: [u64; 4],
+    pub omega_inv: [u64; 4],
+    pub extended_omega: [u64; 4],
+    pub extended_omega_inv: [u64; 4],
+    pub g_coset: [u64; 4],
+    pub g_coset_inv: [u64; 4],
+    pub ifft_divisor: [u64; 4],
+    pub extended_ifft_divisor: [u64; 4],
+    pub t_evaluations: [u64; 128],
+    pub extended_ifft_coset: [u64; 12],
+}
+
+extern "C" {
+    pub fn h2b_init(device: c_int) -> c_int;
+    pub fn h2b_shutdown();
+    pub fn h2b_last_error() -> *const c_char;
+    pub fn h2b_abi_version() -> u32;
+    pub fn h2b_best_multiexp(coeffs: *const u64, bases: *const u64, n: usize, out: *mut u64) -> c_int;
+    pub fn h2b_srs_register(bases: *const u64, n: usize, handle: *mut u64) -> c_int;
+    pub fn h2b_srs_release(handle: u64) -> c_int;
+    pub fn h2b_commit(srs: u64, scalars: *const u64, n: usize, out: *mut u64) -> c_int;
+    pub fn h2b_g1_fold(points: *const u64, count: usize, out: *mut u64) -> c_int;
+    pub fn h2b_best_fft(a: *mut u64, omega: *const u64, log_n: u32) -> c_int;
+    pub fn h2b_domain_new(j: u32, k: u32, out: *mut H2bDomain) -> c_int;
+    pub fn h2b_lagrange_to_coeff(d: *const H2bDomain, a: *mut u64) -> c_int;
+    pub fn h2b_coeff_to_extended(d: *const H2bDomain, input: *const u64, out: *mut u64) -> c_int;
+    pub fn h2b_extended_to_coeff(d: *const H2bDomain, input: *const u64, out: *mut u64) -> c_int;
+    pub fn h2b_divide_by_vanishing_poly(d: *const H2bDomain, a: *mut u64) -> c_int;
+    pub fn h2b_dev_msm(c: *const c_void, b: *const c_void, n: usize, out: *mut c_void, stream: *mut c_void) -> c_int;
+}
+
+fn check(rc: c_int, what: &str) {
+    // upstream semantics are panics (assert_eq! at arithmetic.rs:148, :199; domain.rs:227, :244, :311)
+    if rc != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(h2b_last_error()) }.to_string_lossy().into_owned();
+        panic!("{what}: h2b200 error {rc}: {msg}");
+    }
+}
+
+fn ensure_init() {
+    static ONCE: std::sync::Once = std::sync::Once::new();
+    ONCE.call_once(|| {
+        let dev = std::env::var("H2B200_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
+        check(unsafe { h2b_init(dev) }, "h2b_init");
+    });
+}
+
+/// Drop-in for `halo2_proofs::arithmetic::best_multiexp::<G1Affine>` (arithmetic.rs:147-180).
+pub fn best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1 {
+    assert_eq!(coeffs.len(), bases.len());
+    ensure_init();
+    let mut out = core::mem::MaybeUninit::<G1>::uninit();
+    check(
+        unsafe {
+            h2b_best_multiexp(coeffs.as_ptr() as *const u64, bases.as_ptr() as *const u64, coeffs.len(), out.as_mut_ptr() as *mut u64)
+        },
+        "best_multiexp",
+    );
+    unsafe { out.assume_init() }
+}
+
+/// Drop-in for `halo2_proofs::arithmetic::best_fft::<Fr, Fr>` (arithmetic.rs:185-250).
+pub fn best_fft(a: &mut [Fr], omega: Fr, log_n: u32) {
+    assert_eq!(a.len(), 1 << log_n);
+    ensure_init();
+    check(unsafe { h2b_best_fft(a.as_mut_ptr() as *mut u64, &omega as *const Fr as *const u64, log_n) }, "best_fft");
+}
+
+/// Device-resident SRS for `ParamsKZG::{commit, commit_lagrange}` (kzg/commitment.rs:319, :363).
+pub struct Srs(u64);
+impl Srs {
+    pub fn register(bases: &[G1Affine]) -> Self {
+        ensure_init();
+        let mut h = 0u64;
+        check(unsafe { h2b_srs_register(bases.as_ptr() as *const u64, bases.len(), &mut h) }, "srs_register");
+        Srs(h)
+    }
+    pub fn commit(&self, scalars: &[Fr]) -> G1 {
+        let mut out = core::mem::MaybeUninit::<G1>::uninit();
+        check(unsafe { h2b_commit(self.0, scalars.as_ptr() as *const u64, scalars.len(), out.as_mut_ptr() as *mut u64) }, "commit");
+        unsafe { out.assume_init() }
+    }
+}
+impl Drop for Srs {
+    fn drop(&mut self) {
+        unsafe { h2b_srs_release(self.0) };
+    }
+}
+
+/// Fused EvaluationDomain transforms (domain.rs:227, :244, :311).
+pub struct Domain(H2bDomain);
+impl Domain {
+    pub fn new(j: u32, k: u32) -> Self {
+        ensure_init();
+        let mut d = core::mem::MaybeUninit::<H2bDomain>::uninit();
+        check(unsafe { h2b_domain_new(j, k, d.as_mut_ptr()) }, "domain_new");
+        Domain(unsafe { d.assume_init() })
+    }
+    pub fn raw(&self) -> &H2bDomain { &self.0 }
+    pub fn lagrange_to_coeff(&self, a: &mut [Fr]) {
+        assert_eq!(a.len(), 1 << self.0.k);
+        check(unsafe { h2b_lagrange_to_coeff(&self.0, a.as_mut_ptr() as *mut u64) }, "lagrange_to_coeff");
+    }
+    pub fn coeff_to_extended(&self, a: &[Fr]) -> Vec<Fr> {
+        assert_eq!(a.len(), 1 << self.0.k);
+        let mut out = vec![Fr::zero(); 1 << self.0.extended_k];
+        check(unsafe { h2b_coeff_to_extended(&self.0, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) }, "coeff_to_extended");
+        out
+    }
+    pub fn extended_to_coeff(&self, a: &[Fr]) -> Vec<Fr> {
+        assert_eq!(a.len(), 1 << self.0.extended_k);
+        let mut out = vec![Fr::zero(); ((self.0.j - 1) as usize) << self.0.k];
+        check(unsafe { h2b_extended_to_coeff(&self.0, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) }, "extended_to_coeff");
+        out
+    }
+}
