@@ -13,7 +13,7 @@ in ``include/h2b200.h`` (``csrc/libh2b200.so``):
 * ``multi_gpu.sharded_multiexp`` -- point-range sharding across ranks, 96-byte gather.
 
 Arrays are numpy ``uint64`` in the FFI layout (Fr/Fq: 4 limbs LE Montgomery;
-G1Affine: 8 limbs; G1: 12 limbs Jacobian).  There is no CPU fallback: importing
+G1Affine: 8 limbs; G1: 12 limbs homogeneous projective).  There is no CPU fallback: importing
 works anywhere, computing requires the CUDA library and a GPU and raises otherwise.
 """
 from . import _ffi  # noqa: F401

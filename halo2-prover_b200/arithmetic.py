@@ -15,7 +15,7 @@ from . import _ffi
 
 
 def best_multiexp(coeffs: np.ndarray, bases: np.ndarray) -> np.ndarray:
-    """sum_i coeffs[i] * bases[i] -> G1 (12 x u64 Jacobian).  coeffs (n,4), bases (n,8)."""
+    """sum_i coeffs[i] * bases[i] -> G1 (12 x u64, homogeneous projective x = X/Z, y = Y/Z).  coeffs (n,4), bases (n,8)."""
     coeffs = _ffi.as_u64(coeffs, 4)
     bases = _ffi.as_u64(bases, 8)
     assert coeffs.shape[0] == bases.shape[0], "assert_eq!(coeffs.len(), bases.len())"  # arithmetic.rs:148
@@ -37,7 +37,7 @@ def best_fft(a: np.ndarray, omega: np.ndarray, log_n: int) -> None:
 
 
 def g1_fold(points: np.ndarray) -> np.ndarray:
-    """Sum of Jacobian points ((m,12) uint64) -- the fold of per-chunk partial results."""
+    """Sum of projective points ((m,12) uint64) -- the fold of per-chunk partial results."""
     points = _ffi.as_u64(points, 12)
     _ffi.init()
     out = np.zeros(12, dtype=np.uint64)

@@ -3,7 +3,10 @@
 // Memory formats are the reference's (halo2curves 0.3.2 @9f5c508 src/bn256/curve.rs,
 // pinned by /root/reference/circuits/Cargo.lock:854-856):
 //   G1Affine {x, y}     64 B, Montgomery, identity = (0, 0)
-//   G1       {x, y, z}  96 B, Jacobian, Montgomery, identity z = 0 ((0, R, 0) from G1::identity())
+//   G1       {x, y, z}  96 B, HOMOGENEOUS projective (x = X/Z, y = Y/Z), Montgomery, identity z = 0
+//                       ((0, R, 0) from G1::identity()).  Established by executing the reference's
+//                       own compiled prover: its best_multiexp results are on the
+//                       curve only under the homogeneous reading, not the Jacobian one.
 // Internally buckets are kept in extended Jacobian "XYZZ" coordinates (x = X/ZZ,
 // y = Y/ZZZ, ZZ^3 = ZZZ^2; identity ZZ = 0): a mixed addition is 8M + 2S, the figure
 // SURVEY.md section 8d uses for the MSM work model.
@@ -18,7 +21,7 @@ struct __align__(16) Affine {
 struct __align__(16) XYZZ {
     Fe x, y, zz, zzz;
 };
-struct __align__(16) Jacobian {
+struct __align__(16) Projective {
     Fe x, y, z;
 };
 
@@ -149,29 +152,29 @@ static __device__ __noinline__ void xyzz_add(XYZZ &acc, const XYZZ &q) {
 
 static __device__ __noinline__ XYZZ xyzz_dbl_ni(const XYZZ &p) { return xyzz_dbl(p); }
 
-// XYZZ -> a Jacobian representative with Z = ZZ * ZZZ (no inversion); identity -> (0, R, 0).
-H2B_DI Jacobian xyzz_to_jacobian(const XYZZ &p) {
-    Jacobian r;
+// XYZZ -> a homogeneous projective representative with Z = ZZ * ZZZ (no inversion);
+// identity -> (0, R, 0).
+H2B_DI Projective xyzz_to_projective(const XYZZ &p) {
+    Projective r;
     if (xyzz_is_identity(p)) {
         r.x = Fq::zero();
         r.y = Fq::one();
         r.z = Fq::zero();
         return r;
     }
-    Fe z2 = Fq::sqr(p.zzz);                 // ZZZ^2
-    r.x = Fq::mul(Fq::mul(p.x, p.zz), z2);  // X * ZZ * ZZZ^2
-    Fe zz3 = Fq::mul(Fq::sqr(p.zz), p.zz);  // ZZ^3
-    r.y = Fq::mul(Fq::mul(p.y, zz3), z2);   // Y * ZZ^3 * ZZZ^2
+    r.x = Fq::mul(p.x, p.zzz);  // X/ZZ = X*ZZZ / (ZZ*ZZZ)
+    r.y = Fq::mul(p.y, p.zz);   // Y/ZZZ = Y*ZZ / (ZZ*ZZZ)
     r.z = Fq::mul(p.zz, p.zzz);
     return r;
 }
-H2B_DI XYZZ jacobian_to_xyzz(const Jacobian &p) {
+// homogeneous (X:Y:Z) -> XYZZ (X*Z, Y*Z^2, Z^2, Z^3)
+H2B_DI XYZZ projective_to_xyzz(const Projective &p) {
     XYZZ r;
     if (Fq::is_zero(p.z)) return xyzz_identity();
-    r.x = p.x;
-    r.y = p.y;
     r.zz = Fq::sqr(p.z);
     r.zzz = Fq::mul(r.zz, p.z);
+    r.x = Fq::mul(p.x, p.z);
+    r.y = Fq::mul(p.y, r.zz);
     return r;
 }
 

@@ -24,7 +24,7 @@ using namespace h2b;
 
 static_assert(sizeof(Fe) == 32, "Fr/Fq must be 32 bytes (4 x u64)");
 static_assert(sizeof(Affine) == 64, "G1Affine must be 64 bytes");
-static_assert(sizeof(Jacobian) == 96, "G1 must be 96 bytes");
+static_assert(sizeof(Projective) == 96, "G1 must be 96 bytes");
 static_assert(sizeof(XYZZ) == 128, "bucket must be 128 bytes");
 
 namespace {
@@ -197,10 +197,10 @@ MsmCfg msm_plan(size_t n) {
     return cfg;
 }
 
-int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Jacobian *d_out, cudaStream_t s) {
+int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_out, cudaStream_t s) {
     if (n == 0) {
         // G1::identity() = (0, R, 0)
-        Jacobian id;
+        Projective id;
         memset(&id, 0, sizeof id);
         const uint32_t one[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
                                  0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
@@ -600,13 +600,13 @@ __global__ void test_field_kernel(int op, const Fe *a, const Fe *b, Fe *o, uint3
     }
     store_fe(&o[i], r);
 }
-__global__ void test_g1_add_kernel(const Affine *a, const Affine *b, Jacobian *o, uint32_t n) {
+__global__ void test_g1_add_kernel(const Affine *a, const Affine *b, Projective *o, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Affine p = load_affine(&a[i]), q = load_affine(&b[i]);
     XYZZ acc = xyzz_from_affine(p);
     if (!affine_is_identity(q)) xyzz_madd(acc, q);
-    Jacobian j = xyzz_to_jacobian(acc);
+    Projective j = xyzz_to_projective(acc);
     store_fe(&o[i].x, j.x);
     store_fe(&o[i].y, j.y);
     store_fe(&o[i].z, j.z);
@@ -768,7 +768,7 @@ int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     TRY(enter(s));
-    return leave(s, msm_run((const Fe *)d_coeffs, (const Affine *)d_bases, n, (Jacobian *)d_out, s));
+    return leave(s, msm_run((const Fe *)d_coeffs, (const Affine *)d_bases, n, (Projective *)d_out, s));
 }
 
 int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out[12]) {
@@ -782,7 +782,7 @@ int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
         TRY(stage_in(BUF_BASES, bases, n * 64, &db));
     }
     TRY(get_buf(BUF_OUT, 96, &dout));
-    TRY(msm_run((const Fe *)ds, (const Affine *)db, n, (Jacobian *)dout, g->stream));
+    TRY(msm_run((const Fe *)ds, (const Affine *)db, n, (Projective *)dout, g->stream));
     CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return leave(g->stream, H2B_OK);
@@ -840,7 +840,7 @@ int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]
     void *ds = nullptr, *dout;
     if (n) TRY(stage_in(BUF_SCALARS, scalars, n * 32, &ds));
     TRY(get_buf(BUF_OUT, 96, &dout));
-    TRY(msm_run((const Fe *)ds, it->second.d, n, (Jacobian *)dout, g->stream));
+    TRY(msm_run((const Fe *)ds, it->second.d, n, (Projective *)dout, g->stream));
     CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return leave(g->stream, H2B_OK);
@@ -853,7 +853,7 @@ int h2b_dev_g1_fold(const void *d_points, size_t count, void *d_out, void *strea
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     TRY(enter(s));
-    g1_fold_kernel<<<1, 32, 0, s>>>((const Jacobian *)d_points, (uint32_t)count, (Jacobian *)d_out);
+    g1_fold_kernel<<<1, 32, 0, s>>>((const Projective *)d_points, (uint32_t)count, (Projective *)d_out);
     LAUNCHED();
     return leave(s, H2B_OK);
 }
@@ -881,7 +881,7 @@ int h2b_g1_fold(const uint64_t *points, size_t count, uint64_t out[12]) {
     void *dp = nullptr, *dout;
     TRY(stage_in(BUF_TEST_A, points, count * 96, &dp));
     TRY(get_buf(BUF_OUT, 96, &dout));
-    g1_fold_kernel<<<1, 32, 0, g->stream>>>((const Jacobian *)dp, (uint32_t)count, (Jacobian *)dout);
+    g1_fold_kernel<<<1, 32, 0, g->stream>>>((const Projective *)dp, (uint32_t)count, (Projective *)dout);
     LAUNCHED();
     CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
@@ -1044,7 +1044,7 @@ int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, 
     TRY(stage_in(BUF_TEST_B, b, n * 64, &db));
     TRY(get_buf(BUF_TEST_O, n * 96, &dout));
     test_g1_add_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>((Affine *)da, (Affine *)db,
-                                                                           (Jacobian *)dout, (uint32_t)n);
+                                                                           (Projective *)dout, (uint32_t)n);
     LAUNCHED();
     CU(cudaMemcpyAsync(out, dout, n * 96, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));

@@ -6,7 +6,7 @@
 // create_proof (/root/reference/circuits/src/utils.rs:83-91, :105-120).
 //
 // Contract kept: sum_i coeffs[i] * bases[i] as a group element (callers normalise
-// to affine before the transcript, so the Jacobian representative is free);
+// to affine before the transcript, so the Projective representative is free);
 // Montgomery-form inputs; (0,0) bases and zero scalars contribute nothing.
 // The algorithm is NOT the reference's per-thread unsigned-window loop:
 //   1. digits   : scalar -> canonical -> signed c-bit digits; per-(window,|digit|)
@@ -18,7 +18,7 @@
 //   5. combine  : buckets that were split into several tasks are folded
 //   6. reduce   : per window, sum_k k * B_k by running sums over bucket groups and
 //                 a shared-memory tree across groups
-//   7. final    : Horner over windows (c doublings per window) -> Jacobian
+//   7. final    : Horner over windows (c doublings per window) -> projective
 #pragma once
 #include "curve.cuh"
 
@@ -331,8 +331,8 @@ msm_window_fold_kernel(const XYZZ *__restrict__ window_partials, uint32_t per_wi
     if (lane == 0) store_xyzz(&window_sums[w], load_xyzz(&sh[0]));
 }
 
-// Horner over windows, high to low; result as a Jacobian point (96 B).
-__global__ void msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Jacobian *out) {
+// Horner over windows, high to low; result as a homogeneous projective point (96 B).
+__global__ void msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     XYZZ acc = xyzz_identity();
     for (int w = (int)cfg.windows - 1; w >= 0; w--) {
@@ -340,7 +340,7 @@ __global__ void msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cf
         XYZZ s = load_xyzz(&window_sums[w]);
         xyzz_add(acc, s);
     }
-    Jacobian j = xyzz_to_jacobian(acc);
+    Projective j = xyzz_to_projective(acc);
     store_fe(&out->x, j.x);
     store_fe(&out->y, j.y);
     store_fe(&out->z, j.z);
@@ -380,19 +380,19 @@ g1_fixed_base_mul_kernel(const Fe *__restrict__ scalars, uint32_t n, Affine base
     store_fe(&out[i].y, r.y);
 }
 
-// out = sum of `count` Jacobian points (multi-GPU fold of partial MSM results).
-__global__ void g1_fold_kernel(const Jacobian *__restrict__ pts, uint32_t count, Jacobian *out) {
+// out = sum of `count` projective points (multi-GPU fold of partial MSM results).
+__global__ void g1_fold_kernel(const Projective *__restrict__ pts, uint32_t count, Projective *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     XYZZ acc = xyzz_identity();
     for (uint32_t i = 0; i < count; i++) {
-        Jacobian p;
+        Projective p;
         p.x = load_fe(&pts[i].x);
         p.y = load_fe(&pts[i].y);
         p.z = load_fe(&pts[i].z);
-        XYZZ q = jacobian_to_xyzz(p);
+        XYZZ q = projective_to_xyzz(p);
         xyzz_add(acc, q);
     }
-    Jacobian j = xyzz_to_jacobian(acc);
+    Projective j = xyzz_to_projective(acc);
     store_fe(&out->x, j.x);
     store_fe(&out->y, j.y);
     store_fe(&out->z, j.z);

@@ -4,7 +4,7 @@ The reference already splits an MSM into contiguous chunks and folds the partial
 (halo2_proofs @6b43b6b src/arithmetic.rs:152-176); here a chunk is a GPU.  Rank g of G
 owns points [g*n/G, (g+1)*n/G): its slice of the SRS stays resident, its slice of the
 scalars arrives over its own PCIe link, it runs the single-GPU MSM and emits one
-Jacobian point.  The only exchange is an all-gather of G x 96 bytes (group addition is
+projective point.  The only exchange is an all-gather of G x 96 bytes (group addition is
 not an NCCL reduction op), after which every rank folds the G partials on its GPU.
 """
 from __future__ import annotations
@@ -34,7 +34,7 @@ def sharded_multiexp(coeffs_local, bases_local, group=None, stream=None):
     """MSM over the union of all ranks' (coeffs_local, bases_local) slices.
 
     Inputs are cuda int64 tensors ((m,4) and (m,8)) already resident on this rank's GPU.
-    Returns a (12,) int64 cuda tensor holding the folded Jacobian sum (same on every rank).
+    Returns a (12,) int64 cuda tensor holding the folded projective sum (same on every rank).
     """
     import torch
     import torch.distributed as dist

@@ -12,7 +12,8 @@
  * Data layout (identical to the Rust types, so buffers cross the FFI untouched):
  *   Fr, Fq      4 x uint64_t little-endian limbs, Montgomery form (R = 2^256), < modulus
  *   G1Affine    {x: Fq, y: Fq}       64 bytes, identity = (0, 0)
- *   G1          {x, y, z: Fq}        96 bytes, Jacobian, identity z = 0
+ *   G1          {x, y, z: Fq}        96 bytes, homogeneous projective (x = X/Z, y = Y/Z), identity z = 0
+ *                                    (what halo2curves 0.3.2 stores; verified by running the reference binary)
  * All pointers are plain host pointers unless the function name contains `_dev`,
  * in which case they are CUDA device pointers on the library's device and `stream`
  * is a cudaStream_t passed as void* (NULL = the library's own stream).
@@ -54,7 +55,7 @@ uint32_t h2b_abi_version(void);
 /* ---- MSM ------------------------------------------------------------------------- */
 /* best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1
  * replaces halo2_proofs src/arithmetic.rs:147-180 (and multiexp_serial :28-140).
- * coeffs: n x 4 u64, bases: n x 8 u64, out: 12 u64 (Jacobian; any representative of the sum). */
+ * coeffs: n x 4 u64, bases: n x 8 u64, out: 12 u64 (projective; any representative of the sum). */
 int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out[12]);
 
 /* SRS residency.  ParamsKZG keeps two static base arrays (g, g_lagrange); register each
@@ -67,7 +68,7 @@ int h2b_srs_release(uint64_t handle);
  * registered SRS (n <= registered length; upstream asserts bases.len() >= size). */
 int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]);
 
-/* Sum of `count` Jacobian points (fold of per-GPU partial MSM results;
+/* Sum of `count` projective points (fold of per-GPU partial MSM results;
  * arithmetic.rs:~176 `results.iter().fold(identity, |a, b| a + b)`). */
 int h2b_g1_fold(const uint64_t *points /* count x 12 */, size_t count, uint64_t out[12]);
 

@@ -287,13 +287,17 @@ def array_to_affine(arr: np.ndarray) -> List[Affine]:
     return out
 
 
-def jacobian_array_to_affine(arr: np.ndarray) -> Affine:
-    """12 x u64 (x,y,z Montgomery Jacobian, identity z=0) -> affine ints."""
+def projective_array_to_affine(arr: np.ndarray) -> Affine:
+    """12 x u64 (x,y,z Montgomery, HOMOGENEOUS projective x = X/Z, y = Y/Z -- the reference's G1,
+    established by executing its compiled prover; identity z=0) -> affine ints."""
     arr = np.asarray(arr, dtype=np.uint64).reshape(12)
     X = from_mont(limbs_to_int(arr[0:4]), Q_MOD)
     Y = from_mont(limbs_to_int(arr[4:8]), Q_MOD)
     Z = from_mont(limbs_to_int(arr[8:12]), Q_MOD)
-    return _from_jac((X, Y, Z))
+    if Z == 0:
+        return None
+    zi = pow(Z, -1, Q_MOD)
+    return (X * zi % Q_MOD, Y * zi % Q_MOD)
 
 
 # --- NTT -----------------------------------------------------------------------------------------

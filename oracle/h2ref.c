@@ -265,6 +265,34 @@ static void g1j_add(g1j *r, const g1j *p, const g1j *q) {
     r->x = x3; r->y = y3; r->z = z3;
 }
 
+/* The reference's G1 {x,y,z} is HOMOGENEOUS projective (x = X/Z, y = Y/Z): established by executing
+ * its compiled prover (oracle/wasm).  This file computes in Jacobian coordinates internally (the
+ * group element is what matters) and converts at the API boundary so that buffers have the
+ * reference's meaning. */
+static void jac_to_hom(uint64_t out[12], const g1j *p) {
+    g1j r;
+    if (fe_is_zero(&p->z)) { g1j_identity(&r); }
+    else {
+        fe z2;
+        f_sqr(&FQ, &z2, &p->z);
+        f_mul(&FQ, &r.x, &p->x, &p->z);  /* X/Z^2 = X*Z / Z^3 */
+        r.y = p->y;                      /* Y/Z^3 */
+        f_mul(&FQ, &r.z, &z2, &p->z);
+    }
+    memcpy(out, &r, sizeof r);
+}
+static void hom_to_jac(g1j *r, const uint64_t in[12]) {
+    g1j p;
+    memcpy(&p, in, sizeof p);
+    if (fe_is_zero(&p.z)) { g1j_identity(r); return; }
+    /* (X:Y:Z) -> Jacobian (X*Z, Y*Z^2, Z) */
+    fe z2;
+    f_sqr(&FQ, &z2, &p.z);
+    f_mul(&FQ, &r->x, &p.x, &p.z);
+    f_mul(&FQ, &r->y, &p.y, &z2);
+    r->z = p.z;
+}
+
 /* ---------------------------------------------------------------- multiexp_serial (arithmetic.rs:28-140) */
 enum { B_NONE = 0, B_AFFINE = 1, B_PROJ = 2 };
 typedef struct { int tag; g1j p; } bucket; /* Affine uses p.x,p.y */
@@ -343,7 +371,7 @@ static void *msm_worker(void *arg) {
     return NULL;
 }
 
-/* best_multiexp (arithmetic.rs:147-180). out = Jacobian, Montgomery, 12 x u64. */
+/* best_multiexp (arithmetic.rs:147-180). out = homogeneous projective, Montgomery, 12 x u64. */
 void h2ref_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, int num_threads, uint64_t out[12]) {
     g1j acc;
     g1j_identity(&acc);
@@ -369,21 +397,19 @@ void h2ref_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n
     } else {
         multiexp_serial((const fe *)coeffs, (const g1a *)bases, n, &acc);
     }
-    memcpy(out, &acc, sizeof acc);
+    jac_to_hom(out, &acc);
 }
 
-/* Jacobian (12 x u64) -> affine (8 x u64), identity -> (0,0); what callers do before the transcript. */
+/* projective (12 x u64) -> affine (8 x u64), identity -> (0,0); what callers do before the transcript. */
 void h2ref_g1_to_affine(const uint64_t in[12], uint64_t out[8]) {
     const g1j *p = (const g1j *)in;
     g1a r;
     if (fe_is_zero(&p->z)) { memset(&r, 0, sizeof r); }
     else {
-        fe zi, zi2, zi3;
+        fe zi;
         f_inv(&FQ, &zi, &p->z);
-        f_sqr(&FQ, &zi2, &zi);
-        f_mul(&FQ, &zi3, &zi2, &zi);
-        f_mul(&FQ, &r.x, &p->x, &zi2);
-        f_mul(&FQ, &r.y, &p->y, &zi3);
+        f_mul(&FQ, &r.x, &p->x, &zi);
+        f_mul(&FQ, &r.y, &p->y, &zi);
     }
     memcpy(out, &r, sizeof r);
 }
@@ -701,10 +727,12 @@ void h2ref_g1_scalar_mul(const uint64_t p_[8], const uint64_t k_mont[4], uint64_
         g1j_double(&acc, &acc);
         if ((k.l[i / 64] >> (i % 64)) & 1) g1j_add_mixed(&acc, &acc, p);
     }
-    memcpy(out, &acc, sizeof acc);
+    jac_to_hom(out, &acc);
 }
 void h2ref_g1_add(const uint64_t a[12], const uint64_t b[12], uint64_t out[12]) {
-    g1j r;
-    g1j_add(&r, (const g1j *)a, (const g1j *)b);
-    memcpy(out, &r, sizeof r);
+    g1j r, x, y;
+    hom_to_jac(&x, a);
+    hom_to_jac(&y, b);
+    g1j_add(&r, &x, &y);
+    jac_to_hom(out, &r);
 }

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY -- see the header of oracle/h2ref.c.  Arrays are numpy
 uint64 in the FFI layout: Fr/Fq = 4 limbs little-endian Montgomery; G1Affine = 8
-limbs (x,y), identity (0,0); G1 Jacobian = 12 limbs, identity z = 0.
+limbs (x,y), identity (0,0); G1 = 12 limbs homogeneous projective (x = X/Z, y = Y/Z), identity z = 0.
 """
 from __future__ import annotations
 

@@ -1,0 +1,790 @@
+// wasmrun.cpp -- a small WebAssembly (MVP + sign-extension) interpreter that executes the
+// reference's own shipped prover, /root/reference/src/lib/wasm/halo2_prover_bg.wasm, and records
+// the inputs and outputs of its best_multiexp (wasm func 347) and best_fft (wasm func 80).
+//
+// TEST INFRASTRUCTURE ONLY (oracle/).  It never ships, is never linked by the product and only
+// runs in the build container (the GPU box has no /root/reference); its output is committed as
+// fixtures under tests/golden/ by oracle/wasm/make_wasm_golden.py.
+//
+// The module imports 35 wasm-bindgen functions (module "wbg", see
+// /root/reference/src/lib/wasm/halo2_prover.js:231-376).  They are shimmed below with a tiny
+// JS-like object heap: console.log, the getrandom detection chain (self/crypto/getRandomValues),
+// Uint8Array new/set/length/subarray, memory/buffer, string_new, throw and the panic hook.
+// crypto.getRandomValues is fed from a seeded splitmix64 stream, which makes every proof
+// deterministic.
+//
+// usage: wasmrun <module.wasm> <out.bin> <k> <circuit> <input-json> <seed> [msm_func fft_func]
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+typedef int64_t i64;
+
+struct Trap : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ------------------------------------------------------------------------------ module structures
+struct FuncType { std::vector<u8> params, results; };
+struct Instr { uint16_t op; u32 a, b; u64 imm; };
+struct Func {
+    u32 type = 0;
+    bool imported = false;
+    std::string import_name;
+    std::vector<u8> locals;  // types of declared locals (params excluded)
+    std::vector<Instr> code;
+    u32 max_depth = 0;
+};
+struct Export { std::string name; u8 kind; u32 index; };
+
+struct Reader {
+    const u8 *p, *end;
+    u8 byte() { if (p >= end) throw Trap("eof"); return *p++; }
+    u64 uleb() { u64 r = 0; int s = 0; for (;;) { u8 b = byte(); r |= (u64)(b & 0x7f) << s; if (!(b & 0x80)) break; s += 7; } return r; }
+    i64 sleb(int bits) {
+        i64 r = 0; int s = 0; u8 b;
+        do { b = byte(); r |= (i64)(b & 0x7f) << s; s += 7; } while (b & 0x80);
+        if (s < bits && (b & 0x40)) r |= -((i64)1 << s);
+        return r;
+    }
+    std::string name() { u32 n = (u32)uleb(); std::string s((const char *)p, n); p += n; return s; }
+};
+
+struct Module {
+    std::vector<FuncType> types;
+    std::vector<Func> funcs;
+    std::vector<Export> exports;
+    std::vector<u32> table;
+    std::vector<u64> globals;
+    std::vector<std::vector<u32>> br_tables;
+    u32 mem_pages = 0;
+    std::vector<u8> mem;
+};
+
+// ------------------------------------------------------------------------------ JS object shim
+struct JsVal {
+    enum Kind { UNDEF, NUL, BOOL, GLOBAL, CRYPTO, MEMORY, BUFFER, U8ARR, STRING, ERR, OTHER, FREE } kind = UNDEF;
+    bool b = false;
+    std::shared_ptr<std::vector<u8>> buf;  // null for views on wasm memory
+    u32 off = 0, len = 0;
+    std::string s;
+    u32 next = 0;  // free-list link when kind == FREE
+};
+
+struct Recorder {
+    FILE *f = nullptr;
+    void put32(u32 v) { fwrite(&v, 4, 1, f); }
+    void bytes(const void *p, size_t n) { fwrite(p, 1, n, f); }
+};
+
+struct VM {
+    Module m;
+    std::vector<u64> stack;
+    size_t sp = 0;
+    std::vector<JsVal> heap;
+    u32 heap_next = 132;
+    u64 rng;
+    u32 msm_func = 347, fft_func = 80;
+    Recorder rec;
+    u64 n_msm = 0, n_fft = 0, n_instr = 0;
+    bool verbose = false;
+
+    // ---- JS heap (mirrors halo2_prover.js:3-46)
+    void heap_init() {
+        heap.assign(132, JsVal());
+        heap[129].kind = JsVal::NUL;
+        heap[130].kind = JsVal::BOOL; heap[130].b = true;
+        heap[131].kind = JsVal::BOOL; heap[131].b = false;
+        heap_next = 132;
+    }
+    u32 add_obj(const JsVal &v) {
+        if (heap_next == heap.size()) { JsVal f; f.kind = JsVal::FREE; f.next = (u32)heap.size() + 1; heap.push_back(f); }
+        u32 idx = heap_next;
+        heap_next = heap[idx].next;
+        heap[idx] = v;
+        return idx;
+    }
+    JsVal &get_obj(u32 idx) { if (idx >= heap.size()) throw Trap("bad heap index"); return heap[idx]; }
+    void drop_obj(u32 idx) {
+        if (idx < 132) return;
+        JsVal f; f.kind = JsVal::FREE; f.next = heap_next;
+        heap[idx] = f;
+        heap_next = idx;
+    }
+    JsVal take_obj(u32 idx) { JsVal v = get_obj(idx); drop_obj(idx); return v; }
+    u8 *arr_ptr(JsVal &v) { return v.buf ? v.buf->data() + v.off : m.mem.data() + v.off; }
+
+    u64 next_rand() {
+        u64 z = (rng += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    std::string mem_str(u32 p, u32 n) {
+        if ((u64)p + n > m.mem.size()) throw Trap("string out of bounds");
+        return std::string((const char *)m.mem.data() + p, n);
+    }
+
+    // ---- host imports, dispatched on the wasm-bindgen import name
+    void host_call(Func &f) {
+        const FuncType &t = m.types[f.type];
+        size_t np = t.params.size();
+        u64 *a = &stack[sp - np];
+        const std::string &n = f.import_name;
+        u64 ret = 0;
+        auto has = [&](const char *s) { return n.find(s) != std::string::npos; };
+        if (has("__wbg_log_")) {
+            if (verbose) fprintf(stderr, "[wasm log] %s\n", mem_str((u32)a[0], (u32)a[1]).c_str());
+        } else if (has("__wbg_new_abda")) { JsVal v; v.kind = JsVal::ERR; ret = add_obj(v);
+        } else if (has("__wbg_stack_")) {
+            // write an empty string (ptr = 1 dangling-but-aligned is what Rust uses for empty; use malloc-free 0 len)
+            u32 out = (u32)a[0];
+            store32(out + 4, 0); store32(out, 1);
+        } else if (has("__wbg_error_")) {
+            fprintf(stderr, "[wasm panic] %s\n", mem_str((u32)a[0], (u32)a[1]).c_str());
+            throw Trap("wasm panic hook invoked");
+        } else if (has("__wbindgen_object_drop_ref")) { take_obj((u32)a[0]);
+        } else if (has("__wbg_getRandomValues_")) {
+            JsVal &arr = get_obj((u32)a[1]);
+            if (arr.kind != JsVal::U8ARR) throw Trap("getRandomValues: not a Uint8Array");
+            u8 *p = arr_ptr(arr);
+            for (u32 i = 0; i < arr.len; i += 8) {
+                u64 r = next_rand();
+                for (u32 j = 0; j < 8 && i + j < arr.len; j++) p[i + j] = (u8)(r >> (8 * j));
+            }
+        } else if (has("__wbg_randomFillSync_")) { throw Trap("randomFillSync: node path not shimmed");
+        } else if (has("__wbg_crypto_")) { JsVal v; v.kind = get_obj((u32)a[0]).kind == JsVal::GLOBAL ? JsVal::CRYPTO : JsVal::UNDEF; ret = add_obj(v);
+        } else if (has("__wbindgen_is_object")) { JsVal::Kind k = get_obj((u32)a[0]).kind; ret = (k != JsVal::UNDEF && k != JsVal::NUL && k != JsVal::BOOL && k != JsVal::STRING && k != JsVal::FREE);
+        } else if (has("__wbg_process_") || has("__wbg_versions_") || has("__wbg_node_") || has("__wbg_msCrypto_")) { ret = add_obj(JsVal());
+        } else if (has("__wbindgen_is_string")) { ret = get_obj((u32)a[0]).kind == JsVal::STRING;
+        } else if (has("__wbg_require_")) { ret = add_obj(JsVal());
+        } else if (has("__wbindgen_is_function")) { ret = 0;
+        } else if (has("__wbindgen_string_new")) { JsVal v; v.kind = JsVal::STRING; v.s = mem_str((u32)a[0], (u32)a[1]); ret = add_obj(v);
+        } else if (has("__wbg_newnoargs_")) { JsVal v; v.kind = JsVal::OTHER; ret = add_obj(v);
+        } else if (has("__wbg_call_")) { JsVal v; v.kind = JsVal::GLOBAL; ret = add_obj(v);
+        } else if (has("__wbindgen_object_clone_ref")) { JsVal v = get_obj((u32)a[0]); ret = add_obj(v);
+        } else if (has("__wbg_self_") || has("__wbg_window_") || has("__wbg_globalThis_") || has("__wbg_global_")) { JsVal v; v.kind = JsVal::GLOBAL; ret = add_obj(v);
+        } else if (has("__wbindgen_is_undefined")) { ret = get_obj((u32)a[0]).kind == JsVal::UNDEF;
+        } else if (has("__wbg_buffer_")) { JsVal v; v.kind = JsVal::BUFFER; ret = add_obj(v);
+        } else if (has("__wbg_newwithbyteoffsetandlength_")) {
+            JsVal v; v.kind = JsVal::U8ARR; v.off = (u32)a[1]; v.len = (u32)a[2];
+            if ((u64)v.off + v.len > m.mem.size()) throw Trap("Uint8Array view out of bounds");
+            ret = add_obj(v);
+        } else if (has("__wbg_new_8125")) {  // new Uint8Array(obj): copy
+            JsVal &src = get_obj((u32)a[0]);
+            JsVal v; v.kind = JsVal::U8ARR;
+            if (src.kind == JsVal::BUFFER) { v.off = 0; v.len = (u32)m.mem.size(); }  // view over the whole wasm memory
+            else { v.len = src.len; v.buf = std::make_shared<std::vector<u8>>(arr_ptr(src), arr_ptr(src) + src.len); }
+            ret = add_obj(v);
+        } else if (has("__wbg_set_")) {
+            JsVal &dst = get_obj((u32)a[0]); JsVal &src = get_obj((u32)a[1]); u32 off = (u32)a[2];
+            if (dst.kind != JsVal::U8ARR || src.kind != JsVal::U8ARR || (u64)off + src.len > dst.len)
+                throw Trap("Uint8Array.set out of range: dst kind " + std::to_string(dst.kind) + " len " + std::to_string(dst.len) +
+                           " src kind " + std::to_string(src.kind) + " len " + std::to_string(src.len) + " off " + std::to_string(off));
+            memmove(arr_ptr(dst) + off, arr_ptr(src), src.len);
+        } else if (has("__wbg_length_")) { ret = get_obj((u32)a[0]).len;
+        } else if (has("__wbg_newwithlength_")) {
+            JsVal v; v.kind = JsVal::U8ARR; v.len = (u32)a[0]; v.buf = std::make_shared<std::vector<u8>>(v.len, 0);
+            ret = add_obj(v);
+        } else if (has("__wbg_subarray_")) {
+            JsVal src = get_obj((u32)a[0]);
+            u32 b = (u32)a[1], e = (u32)a[2];
+            if (e > src.len) e = src.len;
+            if (b > e) b = e;
+            JsVal v = src; v.off = src.off + b; v.len = e - b;
+            ret = add_obj(v);
+        } else if (has("__wbindgen_throw")) { throw Trap("wasm threw: " + mem_str((u32)a[0], (u32)a[1]));
+        } else if (has("__wbindgen_memory")) { JsVal v; v.kind = JsVal::MEMORY; ret = add_obj(v);
+        } else {
+            throw Trap("unhandled import " + n);
+        }
+        sp -= np;
+        if (!t.results.empty()) stack[sp++] = ret;
+    }
+
+    // ---- memory helpers
+    inline void chk(u64 addr, u32 n) { if (addr + n > m.mem.size()) throw Trap("memory access out of bounds"); }
+    u32 load32(u32 a) { chk(a, 4); u32 v; memcpy(&v, &m.mem[a], 4); return v; }
+    void store32(u32 a, u32 v) { chk(a, 4); memcpy(&m.mem[a], &v, 4); }
+
+    // ---- hooks around the two hot leaves
+    void call(u32 fidx) {
+        if (fidx == msm_func) {
+            // (out*, coeffs*, n, bases*, n)
+            u32 out = (u32)stack[sp - 5], co = (u32)stack[sp - 4], n = (u32)stack[sp - 3], ba = (u32)stack[sp - 2];
+            chk(co, n * 32); chk(ba, n * 64);
+            std::vector<u8> sc(m.mem.begin() + co, m.mem.begin() + co + (size_t)n * 32);
+            std::vector<u8> bs(m.mem.begin() + ba, m.mem.begin() + ba + (size_t)n * 64);
+            invoke(fidx);
+            chk(out, 96);
+            rec.put32(1); rec.put32(n);
+            rec.bytes(sc.data(), sc.size()); rec.bytes(bs.data(), bs.size()); rec.bytes(&m.mem[out], 96);
+            n_msm++;
+            return;
+        }
+        if (fidx == fft_func) {
+            // (a*, len, omega*, log_n)
+            u32 a = (u32)stack[sp - 4], len = (u32)stack[sp - 3], om = (u32)stack[sp - 2], logn = (u32)stack[sp - 1];
+            chk(a, len * 32); chk(om, 32);
+            std::vector<u8> in(m.mem.begin() + a, m.mem.begin() + a + (size_t)len * 32);
+            u8 omega[32]; memcpy(omega, &m.mem[om], 32);
+            invoke(fidx);
+            rec.put32(2); rec.put32(logn);
+            rec.bytes(omega, 32); rec.bytes(in.data(), in.size()); rec.bytes(&m.mem[a], (size_t)len * 32);
+            n_fft++;
+            return;
+        }
+        invoke(fidx);
+    }
+
+    struct Label { u32 cont; u32 height; u32 arity; };
+    std::vector<Label> lstack = std::vector<Label>(1u << 20);
+    size_t lsp = 0;
+
+    void invoke(u32 fidx) {
+        Func &f = m.funcs[fidx];
+        if (f.imported) { host_call(f); return; }
+        const FuncType &ft = m.types[f.type];
+        const size_t np = ft.params.size(), nl = f.locals.size();
+        if (sp + nl + 4096 > stack.size()) throw Trap("value stack overflow");
+        const size_t fp = sp - np;
+        for (size_t i = 0; i < nl; i++) stack[sp++] = 0;
+        u64 *loc = &stack[fp];
+        if (lsp + f.max_depth + 2 > lstack.size()) throw Trap("label stack overflow");
+        Label *labels = &lstack[lsp];
+        const size_t lsp_saved = lsp;
+        lsp += f.max_depth + 2;
+        u32 nlab = 0;
+        labels[nlab++] = Label{(u32)f.code.size(), (u32)sp, (u32)ft.results.size()};
+        const Instr *code = f.code.data();
+        u32 pc = 0;
+        u8 *mem = m.mem.data();
+        size_t msz = m.mem.size();
+        u64 *S = stack.data();
+#define POP() (S[--sp])
+#define PUSH(v) (S[sp++] = (u64)(v))
+#define TOP() (S[sp - 1])
+#define ADDR(n_) u64 ea = (u64)(u32)POP() + ins.a; if (ea + (n_) > msz) throw Trap("memory access out of bounds")
+        for (;;) {
+            if (pc >= f.code.size()) break;
+            const Instr &ins = code[pc++];
+            switch (ins.op) {
+                case 0x00: throw Trap("unreachable executed in func " + std::to_string(fidx));
+                case 0x01: break;
+                case 0x02: labels[nlab++] = Label{ins.a + 1, (u32)sp, ins.b}; break;           // block: cont after end
+                case 0x03: labels[nlab++] = Label{pc - 1, (u32)sp, 0}; break;                 // loop: cont = the loop instr itself
+                case 0x04: {                                                                  // if
+                    u32 c = (u32)POP();
+                    labels[nlab++] = Label{(u32)ins.imm + 1, (u32)sp, ins.b};
+                    if (!c) { if (ins.a != (u32)ins.imm) pc = ins.a + 1; else { pc = (u32)ins.imm + 1; nlab--; } }
+                    break;
+                }
+                case 0x05: pc = ins.a + 1; nlab--; break;                                     // else reached from then: skip to after end
+                case 0x0B: nlab--; break;                                                     // end
+                case 0x0C: do_branch(labels, nlab, ins.a, pc, code); break;
+                case 0x0D: if ((u32)POP()) do_branch(labels, nlab, ins.a, pc, code); break;
+                case 0x0E: {
+                    const std::vector<u32> &t = m.br_tables[ins.a];
+                    u32 i = (u32)POP();
+                    u32 d = i < t.size() - 1 ? t[i] : t.back();
+                    do_branch(labels, nlab, d, pc, code);
+                    break;
+                }
+                case 0x0F: do_branch(labels, nlab, nlab - 1, pc, code); break;
+                case 0x10: call(ins.a); S = stack.data(); mem = m.mem.data(); msz = m.mem.size(); break;
+                case 0x11: {
+                    u32 i = (u32)POP();
+                    if (i >= m.table.size() || m.table[i] == 0xffffffffu) throw Trap("call_indirect: null entry");
+                    u32 tgt = m.table[i];
+                    const FuncType &want = m.types[ins.a], &have = m.types[m.funcs[tgt].type];
+                    if (want.params != have.params || want.results != have.results) throw Trap("call_indirect: signature mismatch");
+                    call(tgt); S = stack.data(); mem = m.mem.data(); msz = m.mem.size();
+                    break;
+                }
+                case 0x1A: sp--; break;
+                case 0x1B: { u32 c = (u32)POP(); u64 b = POP(); if (!c) TOP() = b; break; }
+                case 0x20: PUSH(loc[ins.a]); break;
+                case 0x21: loc[ins.a] = POP(); break;
+                case 0x22: loc[ins.a] = TOP(); break;
+                case 0x23: PUSH(m.globals[ins.a]); break;
+                case 0x24: m.globals[ins.a] = POP(); break;
+                // loads
+                case 0x28: { ADDR(4); u32 v; memcpy(&v, mem + ea, 4); PUSH(v); break; }
+                case 0x29: { ADDR(8); u64 v; memcpy(&v, mem + ea, 8); PUSH(v); break; }
+                case 0x2A: { ADDR(4); u32 v; memcpy(&v, mem + ea, 4); PUSH(v); break; }
+                case 0x2B: { ADDR(8); u64 v; memcpy(&v, mem + ea, 8); PUSH(v); break; }
+                case 0x2C: { ADDR(1); PUSH((u32)(i32)(int8_t)mem[ea]); break; }
+                case 0x2D: { ADDR(1); PUSH((u32)mem[ea]); break; }
+                case 0x2E: { ADDR(2); int16_t v; memcpy(&v, mem + ea, 2); PUSH((u32)(i32)v); break; }
+                case 0x2F: { ADDR(2); uint16_t v; memcpy(&v, mem + ea, 2); PUSH((u32)v); break; }
+                case 0x30: { ADDR(1); PUSH((u64)(i64)(int8_t)mem[ea]); break; }
+                case 0x31: { ADDR(1); PUSH((u64)mem[ea]); break; }
+                case 0x32: { ADDR(2); int16_t v; memcpy(&v, mem + ea, 2); PUSH((u64)(i64)v); break; }
+                case 0x33: { ADDR(2); uint16_t v; memcpy(&v, mem + ea, 2); PUSH((u64)v); break; }
+                case 0x34: { ADDR(4); i32 v; memcpy(&v, mem + ea, 4); PUSH((u64)(i64)v); break; }
+                case 0x35: { ADDR(4); u32 v; memcpy(&v, mem + ea, 4); PUSH((u64)v); break; }
+                // stores
+                case 0x36: { u32 v = (u32)POP(); ADDR(4); memcpy(mem + ea, &v, 4); break; }
+                case 0x37: { u64 v = POP(); ADDR(8); memcpy(mem + ea, &v, 8); break; }
+                case 0x38: { u32 v = (u32)POP(); ADDR(4); memcpy(mem + ea, &v, 4); break; }
+                case 0x39: { u64 v = POP(); ADDR(8); memcpy(mem + ea, &v, 8); break; }
+                case 0x3A: { u8 v = (u8)POP(); ADDR(1); mem[ea] = v; break; }
+                case 0x3B: { uint16_t v = (uint16_t)POP(); ADDR(2); memcpy(mem + ea, &v, 2); break; }
+                case 0x3C: { u8 v = (u8)POP(); ADDR(1); mem[ea] = v; break; }
+                case 0x3D: { uint16_t v = (uint16_t)POP(); ADDR(2); memcpy(mem + ea, &v, 2); break; }
+                case 0x3E: { u32 v = (u32)POP(); ADDR(4); memcpy(mem + ea, &v, 4); break; }
+                case 0x3F: PUSH((u32)(m.mem.size() >> 16)); break;
+                case 0x40: {
+                    u32 d = (u32)POP();
+                    u64 old = m.mem.size() >> 16;
+                    if (old + d > 65536) { PUSH((u32)-1); break; }
+                    m.mem.resize((size_t)(old + d) << 16, 0);
+                    mem = m.mem.data(); msz = m.mem.size();
+                    PUSH((u32)old);
+                    break;
+                }
+                case 0x41: PUSH((u32)ins.imm); break;
+                case 0x42: PUSH(ins.imm); break;
+                case 0x43: PUSH((u32)ins.imm); break;
+                case 0x44: PUSH(ins.imm); break;
+#define I32 (u32)
+#define CMP32(op_, T) { T b = (T)(u32)POP(); T a = (T)(u32)TOP(); TOP() = (u32)(a op_ b); break; }
+#define CMP64(op_, T) { T b = (T)POP(); T a = (T)TOP(); TOP() = (u32)(a op_ b); break; }
+                case 0x45: TOP() = (u32)((u32)TOP() == 0); break;
+                case 0x46: CMP32(==, u32) case 0x47: CMP32(!=, u32) case 0x48: CMP32(<, i32) case 0x49: CMP32(<, u32)
+                case 0x4A: CMP32(>, i32) case 0x4B: CMP32(>, u32) case 0x4C: CMP32(<=, i32) case 0x4D: CMP32(<=, u32)
+                case 0x4E: CMP32(>=, i32) case 0x4F: CMP32(>=, u32)
+                case 0x50: TOP() = (u32)(TOP() == 0); break;
+                case 0x51: CMP64(==, u64) case 0x52: CMP64(!=, u64) case 0x53: CMP64(<, i64) case 0x54: CMP64(<, u64)
+                case 0x55: CMP64(>, i64) case 0x56: CMP64(>, u64) case 0x57: CMP64(<=, i64) case 0x58: CMP64(<=, u64)
+                case 0x59: CMP64(>=, i64) case 0x5A: CMP64(>=, u64)
+#define F32A(v_) ({ u32 t_ = (u32)(v_); float f_; memcpy(&f_, &t_, 4); f_; })
+#define F64A(v_) ({ u64 t_ = (v_); double d_; memcpy(&d_, &t_, 8); d_; })
+#define PUSHF32(x_) { float f_ = (x_); u32 t_; memcpy(&t_, &f_, 4); PUSH(t_); }
+#define PUSHF64(x_) { double d_ = (x_); u64 t_; memcpy(&t_, &d_, 8); PUSH(t_); }
+#define FCMP32(op_) { float b = F32A(POP()); float a = F32A(POP()); PUSH((u32)(a op_ b)); break; }
+#define FCMP64(op_) { double b = F64A(POP()); double a = F64A(POP()); PUSH((u32)(a op_ b)); break; }
+                case 0x5B: FCMP32(==) case 0x5C: FCMP32(!=) case 0x5D: FCMP32(<) case 0x5E: FCMP32(>) case 0x5F: FCMP32(<=) case 0x60: FCMP32(>=)
+                case 0x61: FCMP64(==) case 0x62: FCMP64(!=) case 0x63: FCMP64(<) case 0x64: FCMP64(>) case 0x65: FCMP64(<=) case 0x66: FCMP64(>=)
+                case 0x67: { u32 v = (u32)TOP(); TOP() = v ? (u32)__builtin_clz(v) : 32; break; }
+                case 0x68: { u32 v = (u32)TOP(); TOP() = v ? (u32)__builtin_ctz(v) : 32; break; }
+                case 0x69: TOP() = (u32)__builtin_popcount((u32)TOP()); break;
+#define BIN32(expr_) { u32 b = (u32)POP(); u32 a = (u32)TOP(); (void)a; (void)b; TOP() = (u32)(expr_); break; }
+#define BIN64(expr_) { u64 b = POP(); u64 a = TOP(); (void)a; (void)b; TOP() = (u64)(expr_); break; }
+                case 0x6A: BIN32(a + b) case 0x6B: BIN32(a - b) case 0x6C: BIN32(a * b)
+                case 0x6D: { i32 b = (i32)(u32)POP(); i32 a = (i32)(u32)TOP(); if (b == 0) throw Trap("integer divide by zero"); if (a == INT32_MIN && b == -1) throw Trap("integer overflow"); TOP() = (u32)(a / b); break; }
+                case 0x6E: { u32 b = (u32)POP(); u32 a = (u32)TOP(); if (b == 0) throw Trap("integer divide by zero"); TOP() = a / b; break; }
+                case 0x6F: { i32 b = (i32)(u32)POP(); i32 a = (i32)(u32)TOP(); if (b == 0) throw Trap("integer divide by zero"); TOP() = (b == -1) ? 0u : (u32)(a % b); break; }
+                case 0x70: { u32 b = (u32)POP(); u32 a = (u32)TOP(); if (b == 0) throw Trap("integer divide by zero"); TOP() = a % b; break; }
+                case 0x71: BIN32(a & b) case 0x72: BIN32(a | b) case 0x73: BIN32(a ^ b)
+                case 0x74: BIN32(a << (b & 31)) case 0x75: BIN32((u32)((i32)a >> (b & 31))) case 0x76: BIN32(a >> (b & 31))
+                case 0x77: BIN32((a << (b & 31)) | (a >> ((32 - (b & 31)) & 31))) case 0x78: BIN32((a >> (b & 31)) | (a << ((32 - (b & 31)) & 31)))
+                case 0x79: { u64 v = TOP(); TOP() = v ? (u64)__builtin_clzll(v) : 64; break; }
+                case 0x7A: { u64 v = TOP(); TOP() = v ? (u64)__builtin_ctzll(v) : 64; break; }
+                case 0x7B: TOP() = (u64)__builtin_popcountll(TOP()); break;
+                case 0x7C: BIN64(a + b) case 0x7D: BIN64(a - b) case 0x7E: BIN64(a * b)
+                case 0x7F: { i64 b = (i64)POP(); i64 a = (i64)TOP(); if (b == 0) throw Trap("integer divide by zero"); if (a == INT64_MIN && b == -1) throw Trap("integer overflow"); TOP() = (u64)(a / b); break; }
+                case 0x80: { u64 b = POP(); u64 a = TOP(); if (b == 0) throw Trap("integer divide by zero"); TOP() = a / b; break; }
+                case 0x81: { i64 b = (i64)POP(); i64 a = (i64)TOP(); if (b == 0) throw Trap("integer divide by zero"); TOP() = (b == -1) ? 0ull : (u64)(a % b); break; }
+                case 0x82: { u64 b = POP(); u64 a = TOP(); if (b == 0) throw Trap("integer divide by zero"); TOP() = a % b; break; }
+                case 0x83: BIN64(a & b) case 0x84: BIN64(a | b) case 0x85: BIN64(a ^ b)
+                case 0x86: BIN64(a << (b & 63)) case 0x87: BIN64((u64)((i64)a >> (b & 63))) case 0x88: BIN64(a >> (b & 63))
+                case 0x89: BIN64((a << (b & 63)) | (a >> ((64 - (b & 63)) & 63))) case 0x8A: BIN64((a >> (b & 63)) | (a << ((64 - (b & 63)) & 63)))
+#define UN32(expr_) { float a = F32A(POP()); (void)a; PUSHF32(expr_); break; }
+#define UN64(expr_) { double a = F64A(POP()); (void)a; PUSHF64(expr_); break; }
+#define FB32(expr_) { float b = F32A(POP()); float a = F32A(POP()); PUSHF32(expr_); break; }
+#define FB64(expr_) { double b = F64A(POP()); double a = F64A(POP()); PUSHF64(expr_); break; }
+                case 0x8B: UN32(fabsf(a)) case 0x8C: UN32(-a) case 0x8D: UN32(ceilf(a)) case 0x8E: UN32(floorf(a)) case 0x8F: UN32(truncf(a))
+                case 0x90: UN32(nearbyintf(a)) case 0x91: UN32(sqrtf(a))
+                case 0x92: FB32(a + b) case 0x93: FB32(a - b) case 0x94: FB32(a * b) case 0x95: FB32(a / b)
+                case 0x96: FB32(fminf(a, b)) case 0x97: FB32(fmaxf(a, b)) case 0x98: FB32(copysignf(a, b))
+                case 0x99: UN64(fabs(a)) case 0x9A: UN64(-a) case 0x9B: UN64(ceil(a)) case 0x9C: UN64(floor(a)) case 0x9D: UN64(trunc(a))
+                case 0x9E: UN64(nearbyint(a)) case 0x9F: UN64(sqrt(a))
+                case 0xA0: FB64(a + b) case 0xA1: FB64(a - b) case 0xA2: FB64(a * b) case 0xA3: FB64(a / b)
+                case 0xA4: FB64(fmin(a, b)) case 0xA5: FB64(fmax(a, b)) case 0xA6: FB64(copysign(a, b))
+                case 0xA7: TOP() = (u32)TOP(); break;
+                case 0xA8: { float a = F32A(POP()); PUSH((u32)(i32)a); break; }
+                case 0xA9: { float a = F32A(POP()); PUSH((u32)a); break; }
+                case 0xAA: { double a = F64A(POP()); PUSH((u32)(i32)a); break; }
+                case 0xAB: { double a = F64A(POP()); PUSH((u32)a); break; }
+                case 0xAC: TOP() = (u64)(i64)(i32)(u32)TOP(); break;
+                case 0xAD: TOP() = (u64)(u32)TOP(); break;
+                case 0xAE: { float a = F32A(POP()); PUSH((u64)(i64)a); break; }
+                case 0xAF: { float a = F32A(POP()); PUSH((u64)a); break; }
+                case 0xB0: { double a = F64A(POP()); PUSH((u64)(i64)a); break; }
+                case 0xB1: { double a = F64A(POP()); PUSH((u64)a); break; }
+                case 0xB2: { i32 a = (i32)(u32)POP(); PUSHF32((float)a); break; }
+                case 0xB3: { u32 a = (u32)POP(); PUSHF32((float)a); break; }
+                case 0xB4: { i64 a = (i64)POP(); PUSHF32((float)a); break; }
+                case 0xB5: { u64 a = POP(); PUSHF32((float)a); break; }
+                case 0xB6: { double a = F64A(POP()); PUSHF32((float)a); break; }
+                case 0xB7: { i32 a = (i32)(u32)POP(); PUSHF64((double)a); break; }
+                case 0xB8: { u32 a = (u32)POP(); PUSHF64((double)a); break; }
+                case 0xB9: { i64 a = (i64)POP(); PUSHF64((double)a); break; }
+                case 0xBA: { u64 a = POP(); PUSHF64((double)a); break; }
+                case 0xBB: { float a = F32A(POP()); PUSHF64((double)a); break; }
+                case 0xBC: TOP() = (u32)TOP(); break;
+                case 0xBD: break;
+                case 0xBE: TOP() = (u32)TOP(); break;
+                case 0xBF: break;
+                case 0xC0: TOP() = (u32)(i32)(int8_t)TOP(); break;
+                case 0xC1: TOP() = (u32)(i32)(int16_t)TOP(); break;
+                case 0xC2: TOP() = (u64)(i64)(int8_t)TOP(); break;
+                case 0xC3: TOP() = (u64)(i64)(int16_t)TOP(); break;
+                case 0xC4: TOP() = (u64)(i64)(i32)TOP(); break;
+                default: throw Trap("unsupported opcode " + std::to_string(ins.op));
+            }
+        }
+        lsp = lsp_saved;
+        // function results sit on top; move them down to the frame base
+        size_t nr = ft.results.size();
+        if (nr) { u64 v = stack[sp - 1]; sp = fp; stack[sp++] = v; } else sp = fp;
+    }
+
+    // br `depth`: unwind to the label, carry its arity, continue at its continuation.
+    inline void do_branch(Label *labels, u32 &nlab, u32 depth, u32 &pc, const Instr *code) {
+        Label &L = labels[nlab - 1 - depth];
+        if (L.arity) { u64 v = stack[sp - 1]; sp = L.height; stack[sp++] = v; } else sp = L.height;
+        pc = L.cont;
+        // a loop label stays (its `loop` instruction re-pushes nothing: we jump to the instruction
+        // itself, which pushes the label again), every other label is popped together with the
+        // inner ones
+        nlab -= depth + 1;
+        (void)code;
+    }
+};
+
+// ------------------------------------------------------------------------------ decoding
+static void decode_function(Module &m, Func &f, Reader &r, const u8 *body_end) {
+    u32 ngroups = (u32)r.uleb();
+    for (u32 g = 0; g < ngroups; g++) {
+        u32 cnt = (u32)r.uleb();
+        u8 ty = r.byte();
+        for (u32 i = 0; i < cnt; i++) f.locals.push_back(ty);
+    }
+    std::vector<u32> open;  // indices of block/loop/if instrs
+    u32 depth = 0;
+    while (r.p < body_end) {
+        u8 op = r.byte();
+        Instr ins{op, 0, 0, 0};
+        switch (op) {
+            case 0x02: case 0x03: case 0x04: {
+                u8 bt = r.byte();
+                ins.b = (bt == 0x40) ? 0 : 1;
+                open.push_back((u32)f.code.size());
+                depth++;
+                if (depth > f.max_depth) f.max_depth = depth;
+                break;
+            }
+            case 0x05: {
+                u32 ifi = open.back();
+                f.code[ifi].a = (u32)f.code.size();  // else position
+                break;
+            }
+            case 0x0B: {
+                if (open.empty()) break;  // function-level end
+                u32 bi = open.back();
+                open.pop_back();
+                depth--;
+                u32 here = (u32)f.code.size();
+                Instr &b = f.code[bi];
+                if (b.op == 0x04) {
+                    b.imm = here;
+                    if (b.a == 0) b.a = here;  // no else
+                    else f.code[b.a].a = here;  // else instr jumps to end
+                } else {
+                    b.a = here;
+                }
+                break;
+            }
+            case 0x0C: case 0x0D: ins.a = (u32)r.uleb(); break;
+            case 0x0E: {
+                u32 n = (u32)r.uleb();
+                std::vector<u32> t(n + 1);
+                for (u32 i = 0; i <= n; i++) t[i] = (u32)r.uleb();
+                ins.a = (u32)m.br_tables.size();
+                m.br_tables.push_back(t);
+                break;
+            }
+            case 0x10: ins.a = (u32)r.uleb(); break;
+            case 0x11: ins.a = (u32)r.uleb(); r.byte(); break;
+            case 0x20: case 0x21: case 0x22: case 0x23: case 0x24: ins.a = (u32)r.uleb(); break;
+            case 0x3F: case 0x40: r.byte(); break;
+            case 0x41: ins.imm = (u64)(u32)(i32)r.sleb(32); break;
+            case 0x42: ins.imm = (u64)r.sleb(64); break;
+            case 0x43: { u32 v; memcpy(&v, r.p, 4); r.p += 4; ins.imm = v; break; }
+            case 0x44: { u64 v; memcpy(&v, r.p, 8); r.p += 8; ins.imm = v; break; }
+            default:
+                if (op >= 0x28 && op <= 0x3E) { r.uleb(); ins.a = (u32)r.uleb(); }
+                break;
+        }
+        f.code.push_back(ins);
+    }
+    // drop the function-level `end` so falling off the code vector returns
+    if (!f.code.empty() && f.code.back().op == 0x0B && open.empty()) f.code.pop_back();
+}
+
+static void load_module(Module &m, const std::vector<u8> &bin) {
+    Reader r{bin.data(), bin.data() + bin.size()};
+    if (bin.size() < 8 || memcmp(bin.data(), "\0asm\1\0\0\0", 8) != 0) throw Trap("not a wasm module");
+    r.p += 8;
+    std::vector<u32> func_types;
+    u32 n_imported = 0;
+    struct DataSeg { u32 off; std::vector<u8> bytes; };
+    std::vector<DataSeg> data;
+    while (r.p < r.end) {
+        u8 id = r.byte();
+        u32 size = (u32)r.uleb();
+        const u8 *send = r.p + size;
+        Reader s{r.p, send};
+        switch (id) {
+            case 1: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    s.byte();
+                    FuncType t;
+                    u32 np = (u32)s.uleb();
+                    for (u32 j = 0; j < np; j++) t.params.push_back(s.byte());
+                    u32 nr = (u32)s.uleb();
+                    for (u32 j = 0; j < nr; j++) t.results.push_back(s.byte());
+                    if (nr > 1) throw Trap("multi-value not supported");
+                    m.types.push_back(t);
+                }
+                break;
+            }
+            case 2: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    std::string mod = s.name(), nm = s.name();
+                    u8 kind = s.byte();
+                    if (kind != 0) throw Trap("only function imports are supported");
+                    Func f;
+                    f.imported = true;
+                    f.import_name = nm;
+                    f.type = (u32)s.uleb();
+                    m.funcs.push_back(f);
+                    n_imported++;
+                }
+                break;
+            }
+            case 3: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) func_types.push_back((u32)s.uleb());
+                break;
+            }
+            case 4: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    s.byte();
+                    u8 flags = s.byte();
+                    u32 mn = (u32)s.uleb();
+                    if (flags & 1) s.uleb();
+                    m.table.assign(mn, 0xffffffffu);
+                }
+                break;
+            }
+            case 5: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    u8 flags = s.byte();
+                    m.mem_pages = (u32)s.uleb();
+                    if (flags & 1) s.uleb();
+                }
+                break;
+            }
+            case 6: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    s.byte(); s.byte();
+                    u8 op = s.byte();
+                    u64 v = 0;
+                    if (op == 0x41) v = (u64)(u32)(i32)s.sleb(32);
+                    else if (op == 0x42) v = (u64)s.sleb(64);
+                    else throw Trap("unsupported global initialiser");
+                    s.byte();
+                    m.globals.push_back(v);
+                }
+                break;
+            }
+            case 7: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    Export e;
+                    e.name = s.name();
+                    e.kind = s.byte();
+                    e.index = (u32)s.uleb();
+                    m.exports.push_back(e);
+                }
+                break;
+            }
+            case 9: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    u32 flags = (u32)s.uleb();
+                    if (flags != 0) throw Trap("unsupported element segment kind");
+                    if (s.byte() != 0x41) throw Trap("unsupported element offset");
+                    u32 off = (u32)(i32)s.sleb(32);
+                    s.byte();
+                    u32 cnt = (u32)s.uleb();
+                    if (m.table.size() < off + cnt) m.table.resize(off + cnt, 0xffffffffu);
+                    for (u32 j = 0; j < cnt; j++) m.table[off + j] = (u32)s.uleb();
+                }
+                break;
+            }
+            case 10: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    u32 bsize = (u32)s.uleb();
+                    const u8 *bend = s.p + bsize;
+                    Func f;
+                    f.type = func_types[i];
+                    Reader br{s.p, bend};
+                    decode_function(m, f, br, bend);
+                    m.funcs.push_back(f);
+                    s.p = bend;
+                }
+                break;
+            }
+            case 11: {
+                u32 n = (u32)s.uleb();
+                for (u32 i = 0; i < n; i++) {
+                    u32 flags = (u32)s.uleb();
+                    if (flags != 0) throw Trap("unsupported data segment kind");
+                    if (s.byte() != 0x41) throw Trap("unsupported data offset");
+                    u32 off = (u32)(i32)s.sleb(32);
+                    s.byte();
+                    u32 len = (u32)s.uleb();
+                    data.push_back(DataSeg{off, std::vector<u8>(s.p, s.p + len)});
+                    s.p += len;
+                }
+                break;
+            }
+            default: break;  // custom and others
+        }
+        r.p = send;
+    }
+    m.mem.assign((size_t)m.mem_pages << 16, 0);
+    for (auto &d : data) {
+        if ((size_t)d.off + d.bytes.size() > m.mem.size()) throw Trap("data segment out of bounds");
+        memcpy(&m.mem[d.off], d.bytes.data(), d.bytes.size());
+    }
+    (void)n_imported;
+}
+
+static u32 find_export(const Module &m, const char *name) {
+    for (auto &e : m.exports)
+        if (e.kind == 0 && e.name == name) return e.index;
+    throw Trap(std::string("missing export ") + name);
+}
+
+static u64 call_export(VM &vm, const char *name, std::initializer_list<u64> args) {
+    u32 f = find_export(vm.m, name);
+    for (u64 a : args) vm.stack[vm.sp++] = a;
+    vm.call(f);
+    const FuncType &t = vm.m.types[vm.m.funcs[f].type];
+    return t.results.empty() ? 0 : vm.stack[--vm.sp];
+}
+
+static u32 pass_bytes(VM &vm, const std::vector<u8> &b) {
+    u32 p = (u32)call_export(vm, "__wbindgen_malloc", {(u64)b.size(), 1});
+    if ((size_t)p + b.size() > vm.m.mem.size()) throw Trap("malloc returned out-of-bounds pointer");
+    if (!b.empty()) memcpy(&vm.m.mem[p], b.data(), b.size());
+    return p;
+}
+
+static std::vector<u8> take_u8arr(VM &vm, u32 idx) {
+    JsVal v = vm.take_obj(idx);
+    if (v.kind != JsVal::U8ARR) throw Trap("expected a Uint8Array result");
+    u8 *p = vm.arr_ptr(v);
+    return std::vector<u8>(p, p + v.len);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 7) {
+        fprintf(stderr, "usage: %s module.wasm out.bin k circuit input-json seed [msm_func fft_func]\n", argv[0]);
+        return 2;
+    }
+    try {
+        std::ifstream in(argv[1], std::ios::binary);
+        std::vector<u8> bin((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        VM vm;
+        load_module(vm.m, bin);
+        vm.stack.assign(16u << 20, 0);
+        vm.heap_init();
+        u32 k = (u32)atoi(argv[3]);
+        u32 circuit = (u32)atoi(argv[4]);
+        std::string input = argv[5];
+        vm.rng = strtoull(argv[6], nullptr, 0);
+        if (argc >= 9) { vm.msm_func = (u32)atoi(argv[7]); vm.fft_func = (u32)atoi(argv[8]); }
+        vm.verbose = getenv("WASMRUN_VERBOSE") != nullptr;
+        vm.rec.f = fopen(argv[2], "wb");
+        if (!vm.rec.f) throw Trap("cannot open output file");
+        fprintf(stderr, "module: %zu types, %zu funcs, %zu exports, %u pages\n", vm.m.types.size(), vm.m.funcs.size(),
+                vm.m.exports.size(), vm.m.mem_pages);
+
+        // setup(k) -> params bytes
+        u32 h = (u32)call_export(vm, "setup", {k});
+        std::vector<u8> params = take_u8arr(vm, h);
+        fprintf(stderr, "setup(%u): %zu bytes of params (msm calls %llu, fft calls %llu)\n", k, params.size(),
+                (unsigned long long)vm.n_msm, (unsigned long long)vm.n_fft);
+        vm.rec.put32(10); vm.rec.put32((u32)params.size()); vm.rec.bytes(params.data(), params.size());
+
+        // Poseidon (circuit 2) wants the expected hash in the input; the web UI obtains it from
+        // wasm_simulate_circuit first (src/components/Circuits.tsx:93-104).  Do the same.
+        if (input.find("\"output\"") == std::string::npos && input.find("@SIMULATE@") != std::string::npos) {
+            std::string base = input;
+            base.replace(base.find("@SIMULATE@"), 10, "");
+            std::vector<u8> b(base.begin(), base.end());
+            u32 retptr = (u32)call_export(vm, "__wbindgen_add_to_stack_pointer", {(u64)(u32)-16});
+            u32 sp0 = pass_bytes(vm, b);
+            call_export(vm, "wasm_simulate_circuit", {retptr, sp0, (u64)b.size(), circuit});
+            u32 rp = vm.load32(retptr), rl = vm.load32(retptr + 4);
+            std::string out = vm.mem_str(rp, rl);
+            call_export(vm, "__wbindgen_add_to_stack_pointer", {16});
+            call_export(vm, "__wbindgen_free", {rp, rl, 1});
+            fprintf(stderr, "simulate: %s\n", out.c_str());
+            size_t close = base.rfind('}');
+            input = base.substr(0, close) + ", \"output\": \"" + out + "\"}";
+            fprintf(stderr, "input: %s\n", input.c_str());
+        }
+        vm.rec.put32(15); vm.rec.put32((u32)input.size()); vm.rec.bytes(input.data(), input.size());
+
+        // wasm_generate_proof(params, s, circuit) -> proof bytes
+        std::vector<u8> sbytes(input.begin(), input.end());
+        u32 p0 = pass_bytes(vm, params), p1 = pass_bytes(vm, sbytes);
+        h = (u32)call_export(vm, "wasm_generate_proof", {p0, (u64)params.size(), p1, (u64)sbytes.size(), circuit});
+        std::vector<u8> proof = take_u8arr(vm, h);
+        fprintf(stderr, "proof: %zu bytes (msm calls %llu, fft calls %llu)\n", proof.size(), (unsigned long long)vm.n_msm,
+                (unsigned long long)vm.n_fft);
+        vm.rec.put32(11); vm.rec.put32((u32)proof.size()); vm.rec.bytes(proof.data(), proof.size());
+        u64 msm_prove = vm.n_msm, fft_prove = vm.n_fft;
+
+        // wasm_verify_proof(params, proof, s, circuit) -> bool  (the reference verifier)
+        p0 = pass_bytes(vm, params);
+        p1 = pass_bytes(vm, proof);
+        u32 p2 = pass_bytes(vm, sbytes);
+        u32 ok = (u32)call_export(vm, "wasm_verify_proof",
+                                  {p0, (u64)params.size(), p1, (u64)proof.size(), p2, (u64)sbytes.size(), circuit});
+        fprintf(stderr, "verify: %u (msm calls %llu, fft calls %llu)\n", ok, (unsigned long long)vm.n_msm,
+                (unsigned long long)vm.n_fft);
+        vm.rec.put32(12); vm.rec.put32(ok);
+        vm.rec.put32(13); vm.rec.put32((u32)msm_prove);
+        vm.rec.put32(14); vm.rec.put32((u32)fft_prove);
+        fclose(vm.rec.f);
+        return ok ? 0 : 1;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "trap: %s\n", e.what());
+        return 3;
+    }
+}

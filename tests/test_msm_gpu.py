@@ -44,7 +44,7 @@ def test_msm_edge_scalars(h2b, spec, href):
     acc = None
     for p in spec.array_to_affine(pts[:50]):
         acc = spec.g1_add(acc, p)
-    got = spec.jacobian_array_to_affine(h2b.best_multiexp(spec.fr_array([1] * 50), pts[:50].copy()))
+    got = spec.projective_array_to_affine(h2b.best_multiexp(spec.fr_array([1] * 50), pts[:50].copy()))
     assert got == acc
 
 
@@ -66,7 +66,7 @@ def test_msm_degenerate_bases(h2b, spec, href):
     negs = spec.affine_to_array([spec.g1_neg(p) for p in spec.array_to_affine(half)])
     s = href.random_fr(64, 4)
     out = h2b.best_multiexp(np.concatenate([s, s]), np.concatenate([half, negs]))
-    assert spec.jacobian_array_to_affine(out) is None
+    assert spec.projective_array_to_affine(out) is None
 
 
 def test_msm_witness_like_sparse(h2b, spec, href):
@@ -151,7 +151,7 @@ def test_g1_fold(h2b, spec, href):
     acc = None
     for p in spec.array_to_affine(pts):
         acc = spec.g1_add(acc, p)
-    assert spec.jacobian_array_to_affine(h2b.g1_fold(jac)) == acc
+    assert spec.projective_array_to_affine(h2b.g1_fold(jac)) == acc
 
 
 def test_large_msm_linearity(h2b, spec, href):
