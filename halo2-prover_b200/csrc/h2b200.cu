@@ -33,8 +33,9 @@ thread_local std::string g_err;
 std::mutex g_mu;
 
 enum BufId {
-    BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_OFFSETS, BUF_CURSOR, BUF_TASKOFF, BUF_SORTED,
-    BUF_BUCKETS, BUF_PARTIALS, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
+    BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_CURSOR, BUF_NEOFF, BUF_NEID, BUF_SORTED, BUF_DIGITS, BUF_HEAD, BUF_TAIL,
+    BUF_TAILJ, BUF_TOTALS,
+    BUF_BUCKETS, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
     BUF_NTT_OUT, BUF_MISC,
     BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
 };
@@ -184,12 +185,16 @@ MsmCfg msm_plan(size_t n) {
     cfg.windows = W;
     cfg.bpw = 1u << (c - 1);
     cfg.nb = W * cfg.bpw;
-    // task = at most T consecutive entries of one bucket; T = 2x the mean bucket load (rounded up to a
-    // power of two, >= 64) so that ordinary buckets are one task and heavy ones split evenly
-    uint64_t mean2 = 2 * ((uint64_t)n / cfg.bpw + 1);
-    uint32_t t = 64;
-    while (t < mean2) t <<= 1;
-    cfg.task = t;
+    for (uint32_t w = 0; w + 1 < W; w++) {
+        uint32_t bit = c * w + c - 1;
+        cfg.half[bit >> 5] |= 1u << (bit & 31);
+    }
+    // slice = sorted entries per accumulation thread: enough slices to fill the GPU several times
+    // over, at most 512 entries (fix-up cost is one full addition per slice boundary)
+    uint64_t entries_bound = (uint64_t)n * W;
+    uint32_t L = 512;
+    while (L > 16 && entries_bound / L < (uint64_t)g->sm_count * 2048) L >>= 1;
+    cfg.slice = L;
     // reduction groups of 2^lgrp buckets: 16 per group once a window has >= 4096 buckets
     uint32_t lgrp = 0;
     while (lgrp < 4 && (cfg.bpw >> lgrp) > 256) lgrp++;
@@ -212,45 +217,52 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_
     if (n > (1u << 30)) return fail(H2B_ERR_ARG, "msm: n > 2^30 not supported");
     MsmCfg cfg = msm_plan(n);
     size_t entries = (size_t)n * cfg.windows;
-    size_t max_tasks = (size_t)cfg.nb + entries / cfg.task + 1;
-    uint32_t *counts, *offsets, *cursor, *task_off, *sorted;
-    XYZZ *buckets, *partials, *windows;
+    size_t max_slices = entries / cfg.slice + 1;
+    uint32_t *counts, *cursor, *ne_off, *ne_id, *sorted, *totals, *heavy, *digits;
+    int32_t *tail_j;
+    XYZZ *buckets, *head, *tail, *windows;
     uint2 *block_sums;
-    uint32_t *heavy;
     TRY(get_buf(BUF_COUNTS, (size_t)cfg.nb * 4, (void **)&counts));
-    TRY(get_buf(BUF_OFFSETS, (size_t)cfg.nb * 4, (void **)&offsets));
     TRY(get_buf(BUF_CURSOR, (size_t)cfg.nb * 4, (void **)&cursor));
-    TRY(get_buf(BUF_TASKOFF, ((size_t)cfg.nb + 1) * 4, (void **)&task_off));
+    TRY(get_buf(BUF_NEOFF, ((size_t)cfg.nb + 1) * 4, (void **)&ne_off));
+    TRY(get_buf(BUF_NEID, ((size_t)cfg.nb + 1) * 4, (void **)&ne_id));
     TRY(get_buf(BUF_SORTED, entries * 4, (void **)&sorted));
+    TRY(get_buf(BUF_DIGITS, entries * 4, (void **)&digits));
     TRY(get_buf(BUF_BUCKETS, (size_t)cfg.nb * sizeof(XYZZ), (void **)&buckets));
-    TRY(get_buf(BUF_PARTIALS, max_tasks * sizeof(XYZZ), (void **)&partials));
+    TRY(get_buf(BUF_HEAD, max_slices * sizeof(XYZZ), (void **)&head));
+    TRY(get_buf(BUF_TAIL, max_slices * sizeof(XYZZ), (void **)&tail));
+    TRY(get_buf(BUF_TAILJ, max_slices * 4, (void **)&tail_j));
     TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
     TRY(get_buf(BUF_BLOCKSUMS, 1024 * sizeof(uint2), (void **)&block_sums));
-    TRY(get_buf(BUF_HEAVY, (entries / cfg.task + 2) * 4, (void **)&heavy));
+    TRY(get_buf(BUF_TOTALS, 16, (void **)&totals));
+    TRY(get_buf(BUF_HEAVY, (max_slices + 2) * 4, (void **)&heavy));
 
     CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
     CU(cudaMemsetAsync(heavy, 0, 4, s));
+    CU(cudaMemsetAsync(tail_j, 0xff, max_slices * 4, s));
     CU(cudaMemsetAsync(buckets, 0, (size_t)cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
     uint32_t nblk = (uint32_t)((n + 255) / 256);
-    msm_digits_kernel<0><<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, nullptr);
+    msm_digits_kernel<<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, digits);
     LAUNCHED();
     uint32_t ipt = (cfg.nb + 1024 * 1024 - 1) / (1024 * 1024);
     uint32_t sblocks = (cfg.nb + 1024 * ipt - 1) / (1024 * ipt);
-    msm_scan_sums_kernel<<<sblocks, 1024, 0, s>>>(counts, cfg.nb, cfg.task, ipt, block_sums);
+    msm_scan_sums_kernel<<<sblocks, 1024, 0, s>>>(counts, cfg.nb, ipt, block_sums);
     LAUNCHED();
-    msm_scan_blocks_kernel<<<1, 1024, 0, s>>>(block_sums, sblocks, cfg.nb, task_off);
+    msm_scan_blocks_kernel<<<1, 1024, 0, s>>>(block_sums, sblocks, totals);
     LAUNCHED();
-    msm_scan_apply_kernel<<<sblocks, 1024, 0, s>>>(counts, cfg.nb, cfg.task, ipt, block_sums, offsets, cursor,
-                                                  task_off, heavy);
+    msm_scan_apply_kernel<<<sblocks, 1024, 0, s>>>(counts, cfg.nb, ipt, block_sums, cursor, ne_off, ne_id);
     LAUNCHED();
-    msm_digits_kernel<1><<<nblk, 256, 0, s>>>(d_scalars, cfg, cursor, sorted);
+    msm_scatter_kernel<<<dim3(nblk, cfg.windows), 256, 0, s>>>(digits, cfg, cursor, sorted);
     LAUNCHED();
     time_begin(s);
-    msm_accumulate_kernel<<<(uint32_t)((max_tasks + 127) / 128), 128, 0, s>>>(
-        d_bases, sorted, offsets, counts, task_off, cfg, buckets, partials);
+    uint32_t ablocks = (uint32_t)((max_slices + 127) / 128);
+    msm_accumulate_kernel<<<ablocks, 128, 0, s>>>(d_bases, sorted, ne_off, ne_id, totals, cfg, buckets, head, tail,
+                                                  tail_j);
     LAUNCHED();
     time_end(s);
-    msm_combine_kernel<<<g->sm_count * 4, 128, 0, s>>>(counts, task_off, heavy, cfg, partials, buckets);
+    msm_fixup_kernel<<<ablocks, 128, 0, s>>>(ne_off, ne_id, totals, cfg, head, tail, tail_j, buckets, heavy);
+    LAUNCHED();
+    msm_fixup_heavy_kernel<<<g->sm_count * 4, 128, 0, s>>>(ne_off, ne_id, cfg, head, tail, tail_j, heavy, buckets);
     LAUNCHED();
     uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
     uint32_t rthreads = G < 256 ? G : 256;      // power of two

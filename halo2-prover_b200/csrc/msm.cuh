@@ -9,13 +9,17 @@
 // to affine before the transcript, so the Projective representative is free);
 // Montgomery-form inputs; (0,0) bases and zero scalars contribute nothing.
 // The algorithm is NOT the reference's per-thread unsigned-window loop:
-//   1. digits   : scalar -> canonical -> signed c-bit digits; per-(window,|digit|)
-//                 bucket histogram with global atomics
-//   2. scan     : exclusive scan of bucket sizes, and of per-bucket task counts
-//   3. scatter  : counting-sort of (point index, sign) into bucket order
-//   4. accumulate: one thread per task (<= T consecutive entries of one bucket),
-//                 XYZZ mixed additions (8M + 2S) over gathered affine bases
-//   5. combine  : buckets that were split into several tasks are folded
+//   1. digits   : scalar -> canonical -> signed c-bit digits (carry-free recoding), stored
+//                 window-major; per-(window,|digit|) bucket histogram with global atomics
+//   2. scan     : exclusive scan of bucket sizes; compacted list of non-empty buckets
+//   3. scatter  : window-major counting-sort of (point index, sign) into bucket order
+//   4. accumulate: one thread per SLICE of L consecutive sorted entries, whatever buckets they
+//                 belong to -- every lane performs the same number of XYZZ mixed additions
+//                 (8M + 2S) over gathered affine bases, so skewed scalars and the short top
+//                 window cost nothing extra; buckets wholly inside a slice are stored
+//                 directly, pieces of buckets that straddle slices go to per-slice slots
+//   5. fixup    : straddling buckets are folded from their pieces (thread per bucket, one
+//                 block per bucket when a bucket spans many slices)
 //   6. reduce   : per window, sum_k k * B_k by running sums over bucket groups and
 //                 a shared-memory tree across groups
 //   7. final    : Horner over windows (c doublings per window) -> projective
@@ -30,61 +34,83 @@ struct MsmCfg {
     uint32_t windows;  // W
     uint32_t bpw;      // buckets per window = 2^(c-1)
     uint32_t nb;       // W * bpw
-    uint32_t task;     // T: max entries per accumulation task
+    uint32_t slice;    // L: sorted entries per accumulation thread
     uint32_t lgrp;     // log2 of buckets per reduction group
+    uint32_t half[8];  // sum over windows w < W-1 of 2^(c*w + c-1): turns unsigned windows into signed digits
 };
 
-// Signed digit of window w.  `carry` is threaded from window 0 upwards.
-H2B_DI int32_t next_digit(const uint32_t (&s)[9], uint32_t w, uint32_t c, uint32_t &carry,
-                          bool last_window) {
-    uint32_t off = w * c;
-    uint32_t idx = off >> 5, sh = off & 31;
-    uint64_t two = ((uint64_t)s[idx + 1 < 9 ? idx + 1 : 8] << 32) | s[idx];
-    uint32_t d = (uint32_t)(two >> sh) & ((1u << c) - 1);
-    d += carry;
-    if (!last_window && d > (1u << (c - 1))) {
-        carry = 1;
-        return (int32_t)d - (int32_t)(1u << c);
-    }
-    carry = 0;
-    return (int32_t)d;
+// Signed digits without a sequential carry: with s' = s + half (one 256-bit addition),
+//   digit_w = ((s' >> c*w) mod 2^c) - 2^(c-1)   for w < W-1      in [-2^(c-1), 2^(c-1))
+//   digit_top = s' >> c*(W-1)                                    in [0, 2^(c-1)]
+// and sum_w digit_w * 2^(c*w) = s.  Bucket of a non-zero digit: w * 2^(c-1) + |digit| - 1.
+H2B_DI int32_t digit_at(const uint32_t (&sp)[9], uint32_t w, const MsmCfg &cfg) {
+    const uint32_t off = w * cfg.c;
+    const uint32_t idx = off >> 5, sh = off & 31;
+    const uint64_t two = ((uint64_t)sp[idx + 1] << 32) | sp[idx];
+    const uint32_t raw = (uint32_t)(two >> sh);
+    if (w + 1 == cfg.windows) return (int32_t)raw;
+    return (int32_t)(raw & ((1u << cfg.c) - 1)) - (int32_t)(1u << (cfg.c - 1));
 }
 
-// mode 0: histogram; mode 1: scatter (cursor holds the running write position per bucket)
-template <int MODE>
-__global__ void msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg,
-                                  uint32_t *__restrict__ counts_or_cursor,
-                                  uint32_t *__restrict__ sorted) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// Pass 1 over the scalars: Montgomery -> canonical, add `half`, and for every window write the
+// encoded digit (0 = none, else bucket-in-window + 1, sign in bit 31) to digits[w * n + i]
+// (coalesced per window) and count it in the bucket histogram.
+__global__ void __launch_bounds__(256)
+msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg, uint32_t *__restrict__ counts,
+                  uint32_t *__restrict__ digits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cfg.n) return;
     Fe s = Fr::from_mont(load_fe_ro(&scalars[i]));
     uint32_t l[9];
-#pragma unroll
-    for (int k = 0; k < 8; k++) l[k] = s.l[k];
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]), "=r"(l[4]), "=r"(l[5]), "=r"(l[6]), "=r"(l[7])
+        : "r"(s.l[0]), "r"(s.l[1]), "r"(s.l[2]), "r"(s.l[3]), "r"(s.l[4]), "r"(s.l[5]), "r"(s.l[6]),
+          "r"(s.l[7]), "r"(cfg.half[0]), "r"(cfg.half[1]), "r"(cfg.half[2]), "r"(cfg.half[3]),
+          "r"(cfg.half[4]), "r"(cfg.half[5]), "r"(cfg.half[6]), "r"(cfg.half[7]));
     l[8] = 0;
-    uint32_t carry = 0;
     for (uint32_t w = 0; w < cfg.windows; w++) {
-        int32_t d = next_digit(l, w, cfg.c, carry, w + 1 == cfg.windows);
-        if (d == 0) continue;
-        uint32_t neg = d < 0;
-        uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-        uint32_t bucket = w * cfg.bpw + mag - 1;
-        if (MODE == 0) {
-            atomicAdd(&counts_or_cursor[bucket], 1u);
-        } else {
-            uint32_t pos = atomicAdd(&counts_or_cursor[bucket], 1u);
-            sorted[pos] = i | (neg << 31);
+        const int32_t d = digit_at(l, w, cfg);
+        uint32_t enc = 0;
+        if (d != 0) {
+            const uint32_t neg = d < 0;
+            const uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+            enc = mag | (neg << 31);
+            atomicAdd(&counts[w * cfg.bpw + mag - 1], 1u);
         }
+        digits[(size_t)w * cfg.n + i] = enc;
     }
+}
+
+// Pass 2, window-major (blockIdx.y = window, so the blocks of one window run together and its
+// ~n * 4 B region of `sorted` stays L2-resident while it is being filled): counting-sort scatter.
+__global__ void __launch_bounds__(256)
+msm_scatter_kernel(const uint32_t *__restrict__ digits, MsmCfg cfg, uint32_t *__restrict__ cursor,
+                   uint32_t *__restrict__ sorted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = blockIdx.y;
+    if (i >= cfg.n) return;
+    const uint32_t enc = __ldg(&digits[(size_t)w * cfg.n + i]);
+    if (enc == 0) return;
+    const uint32_t mag = enc & 0x7fffffffu;
+    const uint32_t pos = atomicAdd(&cursor[w * cfg.bpw + mag - 1], 1u);
+    sorted[pos] = i | (enc & 0x80000000u);
 }
 
 // Exclusive scans over the nb buckets in three small launches (block sums, scan of block sums,
 // rescan with offsets):
-//   offsets[b] / cursor[b] = sum_{b' < b} counts[b']
-//   task_off[b]            = sum_{b' < b} ceil(counts[b'] / T);  task_off[nb] = total
+//   cursor[b]  = sum_{b' < b} counts[b']                       (write position of the scatter)
+//   ne_off[j], ne_id[j] = offset and id of the j-th NON-EMPTY bucket; ne_off[J] = total entries
+//   totals[0] = total entries, totals[1] = J
 // Blocks of 1024 threads, `ipt` consecutive buckets per thread, at most 1024 blocks.
 __global__ void __launch_bounds__(1024)
-msm_scan_sums_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t T, uint32_t ipt,
+msm_scan_sums_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t ipt,
                      uint2 *__restrict__ block_sums) {
     __shared__ uint32_t wa[32], wb[32];
     const uint32_t tid = threadIdx.x;
@@ -95,7 +121,7 @@ msm_scan_sums_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t 
         if (b < nb) {
             uint32_t cnt = counts[b];
             sa += cnt;
-            sb += (cnt + T - 1) / T;
+            sb += cnt != 0;
         }
     }
     for (int d = 16; d > 0; d >>= 1) {
@@ -114,10 +140,9 @@ msm_scan_sums_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t 
         if (tid == 0) block_sums[blockIdx.x] = make_uint2(sa, sb);
     }
 }
-// One block: exclusive scan of the (<= 1024) block sums in place; totals to task_off[nb].
+// One block: exclusive scan of the (<= 1024) block sums in place; totals out.
 __global__ void __launch_bounds__(1024)
-msm_scan_blocks_kernel(uint2 *__restrict__ block_sums, uint32_t nblocks, uint32_t nb,
-                       uint32_t *__restrict__ task_off) {
+msm_scan_blocks_kernel(uint2 *__restrict__ block_sums, uint32_t nblocks, uint32_t *__restrict__ totals) {
     __shared__ uint32_t sh_a[1024], sh_b[1024];
     const uint32_t tid = threadIdx.x;
     uint2 v = tid < nblocks ? block_sums[tid] : make_uint2(0, 0);
@@ -133,13 +158,12 @@ msm_scan_blocks_kernel(uint2 *__restrict__ block_sums, uint32_t nblocks, uint32_
         __syncthreads();
     }
     if (tid < nblocks) block_sums[tid] = make_uint2(sh_a[tid] - v.x, sh_b[tid] - v.y);
-    if (tid == 1023) task_off[nb] = sh_b[1023];
+    if (tid == 1023) { totals[0] = sh_a[1023]; totals[1] = sh_b[1023]; }
 }
 __global__ void __launch_bounds__(1024)
-msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t T, uint32_t ipt,
-                      const uint2 *__restrict__ block_sums, uint32_t *__restrict__ offsets,
-                      uint32_t *__restrict__ cursor, uint32_t *__restrict__ task_off,
-                      uint32_t *__restrict__ heavy /* [0] = count, [1..] = bucket ids */) {
+msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t ipt,
+                      const uint2 *__restrict__ block_sums, uint32_t *__restrict__ cursor,
+                      uint32_t *__restrict__ ne_off, uint32_t *__restrict__ ne_id) {
     __shared__ uint32_t sh_a[1024], sh_b[1024];
     const uint32_t tid = threadIdx.x;
     const uint32_t lo = (blockIdx.x * 1024 + tid) * ipt;
@@ -149,7 +173,7 @@ msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t
         if (b < nb) {
             uint32_t cnt = counts[b];
             sa += cnt;
-            sb += (cnt + T - 1) / T;
+            sb += cnt != 0;
         }
     }
     sh_a[tid] = sa;
@@ -169,47 +193,59 @@ msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t
         uint32_t b = lo + k;
         if (b < nb) {
             uint32_t cnt = counts[b];
-            offsets[b] = ra;
             cursor[b] = ra;
-            task_off[b] = rb;
+            if (cnt) {
+                ne_off[rb] = ra;
+                ne_id[rb] = b;
+                rb++;
+            }
             ra += cnt;
-            rb += (cnt + T - 1) / T;
-            if (cnt > T) heavy[1 + atomicAdd(&heavy[0], 1u)] = b;  // split into several tasks
         }
     }
+    // the thread that owns the last bucket closes the list: ne_off[J] = total
+    if (lo < nb && lo + ipt >= nb) ne_off[rb] = ra;
 }
 
-// One thread per task.  task_off is non-decreasing; the owning bucket is the last b with
-// task_off[b] <= t among buckets that have tasks (binary search for upper bound).
+// One thread per slice of cfg.slice consecutive sorted entries.
+//   piece kinds: DIRECT (bucket begins and ends inside the slice) -> bucket_sums[id]
+//                HEAD   (bucket began in an earlier slice)         -> head[s]
+//                TAIL   (bucket begins here, continues past the slice end) -> tail[s], tail_j[s] = j
 __global__ void __launch_bounds__(128)
 msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                      const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ counts,
-                      const uint32_t *__restrict__ task_off, MsmCfg cfg,
-                      XYZZ *__restrict__ bucket_sums, XYZZ *__restrict__ partials) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total = task_off[cfg.nb];
-    if (t >= total) return;
-    uint32_t lo = 0, hi = cfg.nb;  // find largest b in [0, nb) with task_off[b] <= t
+                      const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
+                      const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *__restrict__ bucket_sums,
+                      XYZZ *__restrict__ head, XYZZ *__restrict__ tail, int32_t *__restrict__ tail_j) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = totals[0], J = totals[1];
+    const uint64_t begin64 = (uint64_t)s * cfg.slice;
+    if (begin64 >= total) return;
+    const uint32_t begin = (uint32_t)begin64;
+    const uint32_t end = min(begin + cfg.slice, total);
+    uint32_t lo = 0, hi = J;  // largest j in [0, J) with ne_off[j] <= begin  (ne_off[0] == 0)
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (task_off[mid] <= t) lo = mid; else hi = mid;
+        if (ne_off[mid] <= begin) lo = mid; else hi = mid;
     }
-    // lo may sit on a run of empty buckets sharing the same offset; the owner is the last one
-    // of that run, which is what the search returns (largest b with task_off[b] <= t).
-    uint32_t b = lo;
-    uint32_t cnt = counts[b];
-    uint32_t chunk = t - task_off[b];
-    uint32_t begin = offsets[b] + chunk * cfg.task;
-    uint32_t end = min(offsets[b] + cnt, begin + cfg.task);
+    uint32_t j = lo;
+    uint32_t bend = ne_off[j + 1];
+    bool started_before = ne_off[j] < begin;
 
     XYZZ acc = xyzz_identity();
     uint32_t e = begin;
     uint32_t v = sorted[e];
     Affine p = load_affine(&bases[v & 0x7fffffffu]);
     while (true) {
+        if (e == bend) {  // bucket j is complete
+            if (started_before) store_xyzz(&head[s], acc);
+            else store_xyzz(&bucket_sums[ne_id[j]], acc);
+            acc = xyzz_identity();
+            started_before = false;
+            j++;
+            bend = ne_off[j + 1];
+        }
         uint32_t vn = 0;
         Affine pn;
-        bool more = e + 1 < end;
+        const bool more = e + 1 < end;
         if (more) {  // prefetch the next point while this one is added
             vn = sorted[e + 1];
             pn = load_affine(&bases[vn & 0x7fffffffu]);
@@ -223,34 +259,63 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
         p = pn;
         e++;
     }
-    uint32_t ntasks = (cnt + cfg.task - 1) / cfg.task;
-    if (ntasks == 1) store_xyzz(&bucket_sums[b], acc);
-    else store_xyzz(&partials[t], acc);
+    if (started_before) {
+        store_xyzz(&head[s], acc);           // middle or last piece of a long bucket
+    } else if (bend > end) {
+        store_xyzz(&tail[s], acc);           // first piece of a bucket that continues
+        tail_j[s] = (int32_t)j;
+    } else {
+        store_xyzz(&bucket_sums[ne_id[j]], acc);
+    }
 }
 
-// Buckets that were split into several tasks ("heavy": skewed scalars, or the short top window):
-// one block per heavy bucket folds its partial sums -- threads stride over the partials, then a
-// shared-memory tree.  The grid is persistent and walks the heavy list built by the scan.
+// Buckets that straddle slices.  The slice holding the first piece (tail) owns the bucket:
+// sum = tail[s] + head[s+1] + ... + head[s_last].  Short spans are folded by the owning thread;
+// long ones (skewed scalars, short top window) are queued and folded by one block each.
 __global__ void __launch_bounds__(128)
-msm_combine_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ task_off,
-                   const uint32_t *__restrict__ heavy, MsmCfg cfg, const XYZZ *__restrict__ partials,
-                   XYZZ *__restrict__ bucket_sums) {
+msm_fixup_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
+                 const uint32_t *__restrict__ totals, MsmCfg cfg, const XYZZ *__restrict__ head,
+                 const XYZZ *__restrict__ tail, const int32_t *__restrict__ tail_j,
+                 XYZZ *__restrict__ bucket_sums, uint32_t *__restrict__ heavy) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = totals[0];
+    if ((uint64_t)s * cfg.slice >= total) return;
+    const int32_t j = tail_j[s];
+    if (j < 0) return;
+    const uint32_t s_last = (ne_off[j + 1] - 1) / cfg.slice;
+    if (s_last - s > 16) {
+        heavy[1 + atomicAdd(&heavy[0], 1u)] = s;
+        return;
+    }
+    XYZZ acc = load_xyzz(&tail[s]);
+    for (uint32_t t = s + 1; t <= s_last; t++) {
+        XYZZ q = load_xyzz(&head[t]);
+        xyzz_add(acc, q);
+    }
+    store_xyzz(&bucket_sums[ne_id[j]], acc);
+}
+__global__ void __launch_bounds__(128)
+msm_fixup_heavy_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id, MsmCfg cfg,
+                       const XYZZ *__restrict__ head, const XYZZ *__restrict__ tail,
+                       const int32_t *__restrict__ tail_j, const uint32_t *__restrict__ heavy,
+                       XYZZ *__restrict__ bucket_sums) {
     __shared__ uint4 comb_smem[128 * 8];
     XYZZ *sh = reinterpret_cast<XYZZ *>(comb_smem);
     const uint32_t nheavy = heavy[0], tid = threadIdx.x;
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
-        const uint32_t b = heavy[1 + h];
-        const uint32_t ntasks = (counts[b] + cfg.task - 1) / cfg.task;
-        const uint32_t t0 = task_off[b];
+        const uint32_t s = heavy[1 + h];
+        const int32_t j = tail_j[s];
+        const uint32_t s_last = (ne_off[j + 1] - 1) / cfg.slice;
         XYZZ acc = xyzz_identity();
-        for (uint32_t k = tid; k < ntasks; k += 128) {
-            XYZZ q = load_xyzz(&partials[t0 + k]);
+        if (tid == 0) acc = load_xyzz(&tail[s]);
+        for (uint32_t t = s + 1 + tid; t <= s_last; t += 128) {
+            XYZZ q = load_xyzz(&head[t]);
             xyzz_add(acc, q);
         }
         store_xyzz(&sh[tid], acc);
         __syncthreads();
         for (uint32_t stride = 64; stride > 0; stride >>= 1) {
-            if (tid < stride && tid + stride < ntasks) {
+            if (tid < stride) {
                 XYZZ a = load_xyzz(&sh[tid]);
                 XYZZ b2 = load_xyzz(&sh[tid + stride]);
                 xyzz_add(a, b2);
@@ -258,7 +323,7 @@ msm_combine_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restri
             }
             __syncthreads();
         }
-        if (tid == 0) store_xyzz(&bucket_sums[b], load_xyzz(&sh[0]));
+        if (tid == 0) store_xyzz(&bucket_sums[ne_id[j]], load_xyzz(&sh[0]));
         __syncthreads();
     }
 }
@@ -331,12 +396,18 @@ msm_window_fold_kernel(const XYZZ *__restrict__ window_partials, uint32_t per_wi
     if (lane == 0) store_xyzz(&window_sums[w], load_xyzz(&sh[0]));
 }
 
-// Horner over windows, high to low; result as a homogeneous projective point (96 B).
-__global__ void msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *out) {
+// Horner over windows, high to low; result as a homogeneous projective point (96 B).  One thread;
+// the doubling is inlined so the accumulator stays in registers (the chain of c * W doublings is
+// the latency floor of every MSM, however small).
+__global__ void __launch_bounds__(32, 1) msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     XYZZ acc = xyzz_identity();
+#pragma unroll 1
     for (int w = (int)cfg.windows - 1; w >= 0; w--) {
-        for (uint32_t d = 0; d < cfg.c; d++) acc = xyzz_dbl_ni(acc);
+        if (!xyzz_is_identity(acc)) {
+#pragma unroll 1
+            for (uint32_t d = 0; d < cfg.c; d++) acc = xyzz_dbl(acc);
+        }
         XYZZ s = load_xyzz(&window_sums[w]);
         xyzz_add(acc, s);
     }
