@@ -396,25 +396,69 @@ msm_window_fold_kernel(const XYZZ *__restrict__ window_partials, uint32_t per_wi
     if (lane == 0) store_xyzz(&window_sums[w], load_xyzz(&sh[0]));
 }
 
-// Horner over windows, high to low; result as a homogeneous projective point (96 B).  One thread;
-// the doubling is inlined so the accumulator stays in registers (the chain of c * W doublings is
-// the latency floor of every MSM, however small).
-__global__ void __launch_bounds__(32, 1) msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// The c * W doublings of the final Horner are a pure latency chain (one modmul is ~900 cycles for a
+// single thread because its carry chains serialise), and it is the floor of every MSM however small.
+// Four lanes share one doubling: the 9 products of dbl-2008-s-1 are issued as 3 rounds of
+// independent products, one per lane, and exchanged with warp shuffles.
+H2B_DI Fe fe_bcast4(const Fe &v, int src) {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xfu, v.l[i], src);
+    return r;
+}
+H2B_DI Fe fe_sel(bool c, const Fe &a, const Fe &b) {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+// p is replicated in lanes 0..3 and is not the identity.
+H2B_DI void xyzz_dbl_coop4(XYZZ &p, uint32_t lane) {
+    const Fe u = Fq::dbl(p.y);
+    // round 1: lane 0: V = U^2, lane 1: XX = X^2
+    const Fe a1 = fe_sel(lane == 0, u, p.x);
+    const Fe r1 = Fq::mul(a1, a1);
+    const Fe v = fe_bcast4(r1, 0), xx = fe_bcast4(r1, 1);
+    const Fe m = Fq::add(Fq::dbl(xx), xx);
+    // round 2: lane 0: W = U*V, lane 1: S = X*V, lane 2: M^2, lane 3: ZZ' = V*ZZ
+    const Fe a2 = fe_sel(lane == 0, u, fe_sel(lane == 1, p.x, fe_sel(lane == 2, m, v)));
+    const Fe b2 = fe_sel(lane == 2, m, fe_sel(lane == 3, p.zz, v));
+    const Fe r2 = Fq::mul(a2, b2);
+    const Fe w = fe_bcast4(r2, 0), sx = fe_bcast4(r2, 1), mm = fe_bcast4(r2, 2), zz3 = fe_bcast4(r2, 3);
+    const Fe x3 = Fq::sub(Fq::sub(mm, sx), sx);
+    // round 3: lane 0: W*Y, lane 1: ZZZ' = W*ZZZ, lane 2: M*(S - X')
+    const Fe a3 = fe_sel(lane == 2, m, w);
+    const Fe b3 = fe_sel(lane == 0, p.y, fe_sel(lane == 1, p.zzz, Fq::sub(sx, x3)));
+    const Fe r3 = Fq::mul(a3, b3);
+    const Fe wy = fe_bcast4(r3, 0), zzz3 = fe_bcast4(r3, 1), msx = fe_bcast4(r3, 2);
+    p.x = x3;
+    p.y = Fq::sub(msx, wy);
+    p.zz = zz3;
+    p.zzz = zzz3;
+}
+
+// Horner over windows, high to low; result as a homogeneous projective point (96 B).
+// Launched with one warp; lanes 0..3 cooperate, the accumulator is replicated in them.
+__global__ void __launch_bounds__(32, 1)
+msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *out) {
+    const uint32_t lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 4) return;
     XYZZ acc = xyzz_identity();
 #pragma unroll 1
     for (int w = (int)cfg.windows - 1; w >= 0; w--) {
-        if (!xyzz_is_identity(acc)) {
+        if (!xyzz_is_identity(acc)) {  // uniform across the 4 lanes
 #pragma unroll 1
-            for (uint32_t d = 0; d < cfg.c; d++) acc = xyzz_dbl(acc);
+            for (uint32_t d = 0; d < cfg.c; d++) xyzz_dbl_coop4(acc, lane);
         }
         XYZZ s = load_xyzz(&window_sums[w]);
         xyzz_add(acc, s);
     }
-    Projective j = xyzz_to_projective(acc);
-    store_fe(&out->x, j.x);
-    store_fe(&out->y, j.y);
-    store_fe(&out->z, j.z);
+    if (lane == 0) {
+        Projective j = xyzz_to_projective(acc);
+        store_fe(&out->x, j.x);
+        store_fe(&out->y, j.y);
+        store_fe(&out->z, j.z);
+    }
 }
 
 // out[i] = [scalars[i]] * base, affine ((0,0) for the identity): the per-element fixed-base

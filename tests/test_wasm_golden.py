@@ -37,7 +37,10 @@ def _bases(ent_msm, z, g, gl):
 def test_manifest_is_a_verified_reference_proof(name):
     ent = MANIFEST[name]
     assert ent["verified_by_reference_verifier"] is True
-    assert ent["msm_calls_total"] == len(ent["msm"]) and ent["fft_calls_total"] == len(ent["fft"])
+    if ent["all_records_committed"]:
+        assert ent["msm_calls_total"] == len(ent["msm"]) and ent["fft_calls_total"] == len(ent["fft"])
+    else:
+        assert 0 < len(ent["msm"]) <= ent["msm_calls_total"] and 0 < len(ent["fft"]) <= ent["fft_calls_total"]
     assert ent["proof_bytes"] > 0
 
 
