@@ -67,7 +67,11 @@ struct Ctx {
     uint64_t launches = 0;
     uint32_t msm_window = 0;
     int timing = 0;
-    cudaEvent_t last_done = nullptr;
+    cudaEvent_t last_done = nullptr, copy_fence = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    uint32_t e2e_chunks = 4;
+    size_t e2e_min_n = (size_t)1 << 21;
     cudaStream_t last_stream = nullptr;
     std::vector<cudaEvent_t> tev0, tev1;  // timing event pairs
     uint32_t tev_used = 0;
@@ -189,12 +193,6 @@ MsmCfg msm_plan(size_t n) {
         uint32_t bit = c * w + c - 1;
         cfg.half[bit >> 5] |= 1u << (bit & 31);
     }
-    // slice = sorted entries per accumulation thread: enough slices to fill the GPU several times
-    // over, at most 512 entries (fix-up cost is one full addition per slice boundary)
-    uint64_t entries_bound = (uint64_t)n * W;
-    uint32_t L = 512;
-    while (L > 16 && entries_bound / L < (uint64_t)g->sm_count * 2048) L >>= 1;
-    cfg.slice = L;
     // reduction groups of 2^lgrp buckets: 16 per group once a window has >= 4096 buckets
     uint32_t lgrp = 0;
     while (lgrp < 4 && (cfg.bpw >> lgrp) > 256) lgrp++;
@@ -202,25 +200,47 @@ MsmCfg msm_plan(size_t n) {
     return cfg;
 }
 
-int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_out, cudaStream_t s) {
-    if (n == 0) {
-        // G1::identity() = (0, R, 0)
-        Projective id;
-        memset(&id, 0, sizeof id);
-        const uint32_t one[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
-                                 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
-        memcpy(id.y.l, one, sizeof one);
-        CU(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));  // `id` lives on this stack frame
-        return H2B_OK;
-    }
-    if (n > (1u << 30)) return fail(H2B_ERR_ARG, "msm: n > 2^30 not supported");
-    MsmCfg cfg = msm_plan(n);
-    size_t entries = (size_t)n * cfg.windows;
+// An MSM is: begin (clear the buckets) -> one or more chunks over contiguous point ranges, each
+// adding into the same buckets -> finish (bucket reduction, window fold, Horner).  Chunking lets the
+// host-buffer entry points overlap the H2D copy of chunk k+1 with the accumulation of chunk k.
+struct MsmRun {
+    MsmCfg cfg;       // window geometry from the TOTAL size
+    XYZZ *buckets;
+};
+
+int msm_identity_out(Projective *d_out, cudaStream_t s) {
+    // G1::identity() = (0, R, 0)
+    Projective id;
+    memset(&id, 0, sizeof id);
+    const uint32_t one[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                             0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    memcpy(id.y.l, one, sizeof one);
+    CU(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));  // `id` lives on this stack frame
+    return H2B_OK;
+}
+
+int msm_begin(size_t n_total, MsmRun *run, cudaStream_t s) {
+    if (n_total > (1u << 30)) return fail(H2B_ERR_ARG, "msm: n > 2^30 not supported");
+    run->cfg = msm_plan(n_total);
+    TRY(get_buf(BUF_BUCKETS, (size_t)run->cfg.nb * sizeof(XYZZ), (void **)&run->buckets));
+    CU(cudaMemsetAsync(run->buckets, 0, (size_t)run->cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
+    return H2B_OK;
+}
+
+// Points [0, m) of (d_scalars, d_bases): digits -> scan -> scatter -> accumulate -> fix-up.
+int msm_chunk(const MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m, cudaStream_t s) {
+    if (m == 0) return H2B_OK;
+    MsmCfg cfg = run.cfg;
+    cfg.n = (uint32_t)m;
+    size_t entries = m * cfg.windows;
+    uint32_t L = 512;  // slice: enough slices to fill the GPU several times over, at most 512 entries
+    while (L > 16 && entries / L < (size_t)g->sm_count * 2048) L >>= 1;
+    cfg.slice = L;
     size_t max_slices = entries / cfg.slice + 1;
     uint32_t *counts, *cursor, *ne_off, *ne_id, *sorted, *totals, *heavy, *digits;
     int32_t *tail_j;
-    XYZZ *buckets, *head, *tail, *windows;
+    XYZZ *head, *tail;
     uint2 *block_sums;
     TRY(get_buf(BUF_COUNTS, (size_t)cfg.nb * 4, (void **)&counts));
     TRY(get_buf(BUF_CURSOR, (size_t)cfg.nb * 4, (void **)&cursor));
@@ -228,11 +248,9 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_
     TRY(get_buf(BUF_NEID, ((size_t)cfg.nb + 1) * 4, (void **)&ne_id));
     TRY(get_buf(BUF_SORTED, entries * 4, (void **)&sorted));
     TRY(get_buf(BUF_DIGITS, entries * 4, (void **)&digits));
-    TRY(get_buf(BUF_BUCKETS, (size_t)cfg.nb * sizeof(XYZZ), (void **)&buckets));
     TRY(get_buf(BUF_HEAD, max_slices * sizeof(XYZZ), (void **)&head));
     TRY(get_buf(BUF_TAIL, max_slices * sizeof(XYZZ), (void **)&tail));
     TRY(get_buf(BUF_TAILJ, max_slices * 4, (void **)&tail_j));
-    TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
     TRY(get_buf(BUF_BLOCKSUMS, 1024 * sizeof(uint2), (void **)&block_sums));
     TRY(get_buf(BUF_TOTALS, 16, (void **)&totals));
     TRY(get_buf(BUF_HEAVY, (max_slices + 2) * 4, (void **)&heavy));
@@ -240,8 +258,7 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_
     CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
     CU(cudaMemsetAsync(heavy, 0, 4, s));
     CU(cudaMemsetAsync(tail_j, 0xff, max_slices * 4, s));
-    CU(cudaMemsetAsync(buckets, 0, (size_t)cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
-    uint32_t nblk = (uint32_t)((n + 255) / 256);
+    uint32_t nblk = (uint32_t)((m + 255) / 256);
     msm_digits_kernel<<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, digits);
     LAUNCHED();
     uint32_t ipt = (cfg.nb + 1024 * 1024 - 1) / (1024 * 1024);
@@ -256,26 +273,86 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_
     LAUNCHED();
     time_begin(s);
     uint32_t ablocks = (uint32_t)((max_slices + 127) / 128);
-    msm_accumulate_kernel<<<ablocks, 128, 0, s>>>(d_bases, sorted, ne_off, ne_id, totals, cfg, buckets, head, tail,
+    msm_accumulate_kernel<<<ablocks, 128, 0, s>>>(d_bases, sorted, ne_off, ne_id, totals, cfg, run.buckets, head, tail,
                                                   tail_j);
     LAUNCHED();
     time_end(s);
-    msm_fixup_kernel<<<ablocks, 128, 0, s>>>(ne_off, ne_id, totals, cfg, head, tail, tail_j, buckets, heavy);
+    msm_fixup_kernel<<<ablocks, 128, 0, s>>>(ne_off, ne_id, totals, cfg, head, tail, tail_j, run.buckets, heavy);
     LAUNCHED();
-    msm_fixup_heavy_kernel<<<g->sm_count * 4, 128, 0, s>>>(ne_off, ne_id, cfg, head, tail, tail_j, heavy, buckets);
+    msm_fixup_heavy_kernel<<<g->sm_count * 4, 128, 0, s>>>(ne_off, ne_id, cfg, head, tail, tail_j, heavy, run.buckets);
     LAUNCHED();
+    return H2B_OK;
+}
+
+int msm_finish(const MsmRun &run, Projective *d_out, cudaStream_t s) {
+    const MsmCfg &cfg = run.cfg;
+    XYZZ *windows, *wpart;
     uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
     uint32_t rthreads = G < 256 ? G : 256;      // power of two
     uint32_t per_window = G / rthreads;         // blocks (= partials) per window
-    XYZZ *wpart;
+    TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
     TRY(get_buf(BUF_WPART, (size_t)cfg.windows * per_window * sizeof(XYZZ), (void **)&wpart));
-    msm_reduce_kernel<<<dim3(per_window, cfg.windows), rthreads, rthreads * sizeof(XYZZ), s>>>(buckets, cfg, wpart);
+    msm_reduce_kernel<<<dim3(per_window, cfg.windows), rthreads, rthreads * sizeof(XYZZ), s>>>(run.buckets, cfg, wpart);
     LAUNCHED();
     msm_window_fold_kernel<<<cfg.windows, 32, 0, s>>>(wpart, per_window, windows);
     LAUNCHED();
     msm_final_kernel<<<1, 32, 0, s>>>(windows, cfg, d_out);
     LAUNCHED();
     return H2B_OK;
+}
+
+int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_out, cudaStream_t s) {
+    if (n == 0) return msm_identity_out(d_out, s);
+    MsmRun run;
+    TRY(msm_begin(n, &run, s));
+    TRY(msm_chunk(run, d_scalars, d_bases, n, s));
+    return msm_finish(run, d_out, s);
+}
+
+// Host scalars (and optionally host bases) -> device in `chunks` pieces on the copy stream while
+// the compute stream works on the pieces that have landed.
+int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const Affine *d_bases_resident, size_t n,
+                      Projective *d_out) {
+    cudaStream_t s = g->stream;
+    if (n == 0) return msm_identity_out(d_out, s);
+    uint32_t chunks = n >= g->e2e_min_n ? g->e2e_chunks : 1;
+    Fe *ds;
+    Affine *db = nullptr;
+    TRY(get_buf(BUF_SCALARS, n * sizeof(Fe), (void **)&ds));
+    if (h_bases) TRY(get_buf(BUF_BASES, n * sizeof(Affine), (void **)&db));
+    const Affine *bases = h_bases ? db : d_bases_resident;
+    MsmRun run;
+    TRY(msm_begin(n, &run, s));
+    if (chunks <= 1) {
+        CU(cudaMemcpyAsync(ds, h_scalars, n * sizeof(Fe), cudaMemcpyHostToDevice, s));
+        if (h_bases) CU(cudaMemcpyAsync(db, h_bases, n * sizeof(Affine), cudaMemcpyHostToDevice, s));
+        TRY(msm_chunk(run, ds, bases, n, s));
+        return msm_finish(run, d_out, s);
+    }
+    // the copy stream must not overwrite staging that earlier work on `s` may still read
+    CU(cudaEventRecord(g->copy_fence, s));
+    CU(cudaStreamWaitEvent(g->copy_stream, g->copy_fence, 0));
+    size_t per = (n + chunks - 1) / chunks;
+    per = (per + 255) & ~(size_t)255;
+    std::vector<size_t> lo, hi;
+    for (size_t a = 0; a < n; a += per) { lo.push_back(a); hi.push_back(a + per < n ? a + per : n); }
+    while (g->chunk_events.size() < lo.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g->chunk_events.push_back(e);
+    }
+    for (size_t k = 0; k < lo.size(); k++) {
+        size_t m = hi[k] - lo[k];
+        CU(cudaMemcpyAsync(ds + lo[k], h_scalars + 4 * lo[k], m * sizeof(Fe), cudaMemcpyHostToDevice, g->copy_stream));
+        if (h_bases)
+            CU(cudaMemcpyAsync(db + lo[k], h_bases + 8 * lo[k], m * sizeof(Affine), cudaMemcpyHostToDevice, g->copy_stream));
+        CU(cudaEventRecord(g->chunk_events[k], g->copy_stream));
+    }
+    for (size_t k = 0; k < lo.size(); k++) {
+        CU(cudaStreamWaitEvent(s, g->chunk_events[k], 0));
+        TRY(msm_chunk(run, ds + lo[k], bases + lo[k], hi[k] - lo[k], s));
+    }
+    return msm_finish(run, d_out, s);
 }
 
 // ------------------------------------------------------------------------------ NTT
@@ -701,6 +778,8 @@ int h2b_init(int device) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_fence, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return fail(H2B_ERR_CUDA, "h2b_init: stream/event creation failed", cudaGetLastError());
@@ -716,6 +795,11 @@ int h2b_init(int device) {
         if (v >= 9 && v <= 11) g_ntt_tile_log = (uint32_t)v;
     }
     if (g_ntt_tile_log == 9 && g_ntt_max_radix > 9) g_ntt_max_radix = 9;
+    const char *ec = getenv("H2B_E2E_CHUNKS");
+    if (ec) {
+        int v = atoi(ec);
+        if (v >= 1 && v <= 64) c->e2e_chunks = (uint32_t)v;
+    }
     g = c;
     return H2B_OK;
 }
@@ -731,6 +815,9 @@ void h2b_shutdown(void) {
     for (auto &kv : g->twiddles) cudaFree(kv.second);
     for (auto e : g->tev0) cudaEventDestroy(e);
     for (auto e : g->tev1) cudaEventDestroy(e);
+    for (auto e : g->chunk_events) cudaEventDestroy(e);
+    cudaEventDestroy(g->copy_fence);
+    cudaStreamDestroy(g->copy_stream);
     cudaEventDestroy(g->last_done);
     cudaStreamDestroy(g->stream);
     delete g;
@@ -742,6 +829,14 @@ int h2b_set_msm_window(uint32_t c) {
     TRY(ensure_ctx());
     if (c != 0 && (c < 2 || c > 22)) return fail(H2B_ERR_ARG, "msm window must be 0 or in [2, 22]");
     g->msm_window = c;
+    return H2B_OK;
+}
+int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (chunks < 1 || chunks > 64) return fail(H2B_ERR_ARG, "e2e chunks must be in [1, 64]");
+    g->e2e_chunks = chunks;
+    g->e2e_min_n = min_n;
     return H2B_OK;
 }
 uint64_t h2b_kernel_launches(void) {
@@ -788,13 +883,10 @@ int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     TRY(ensure_ctx());
     if (!out || (n && (!coeffs || !bases))) return fail(H2B_ERR_ARG, "best_multiexp: null pointer");
     CU(cudaSetDevice(g->device));
-    void *ds = nullptr, *db = nullptr, *dout;
-    if (n) {
-        TRY(stage_in(BUF_SCALARS, coeffs, n * 32, &ds));
-        TRY(stage_in(BUF_BASES, bases, n * 64, &db));
-    }
+    TRY(enter(g->stream));
+    void *dout;
     TRY(get_buf(BUF_OUT, 96, &dout));
-    TRY(msm_run((const Fe *)ds, (const Affine *)db, n, (Projective *)dout, g->stream));
+    TRY(msm_run_pipelined(coeffs, bases, nullptr, n, (Projective *)dout));
     CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return leave(g->stream, H2B_OK);
@@ -849,10 +941,10 @@ int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]
     if (n > it->second.n) return fail(H2B_ERR_ARG, "commit: bases.len() < size");  // commitment.rs:319/:363
     if (!out || (n && !scalars)) return fail(H2B_ERR_ARG, "commit: null pointer");
     CU(cudaSetDevice(g->device));
-    void *ds = nullptr, *dout;
-    if (n) TRY(stage_in(BUF_SCALARS, scalars, n * 32, &ds));
+    TRY(enter(g->stream));
+    void *dout;
     TRY(get_buf(BUF_OUT, 96, &dout));
-    TRY(msm_run((const Fe *)ds, it->second.d, n, (Projective *)dout, g->stream));
+    TRY(msm_run_pipelined(scalars, nullptr, it->second.d, n, (Projective *)dout));
     CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return leave(g->stream, H2B_OK);

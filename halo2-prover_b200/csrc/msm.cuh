@@ -206,6 +206,17 @@ msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t
     if (lo < nb && lo + ipt >= nb) ne_off[rb] = ra;
 }
 
+// bucket_sums[id] += acc.  Each bucket has exactly one writer per chunk; the first chunk finds the
+// identity (all-zero) there and stores directly.
+H2B_DI void bucket_accumulate(XYZZ *slot, XYZZ &acc) {
+    const Fe zz = load_fe(&slot->zz);
+    if (!Fq::is_zero(zz)) {
+        XYZZ prev = load_xyzz(slot);
+        xyzz_add(acc, prev);
+    }
+    store_xyzz(slot, acc);
+}
+
 // One thread per slice of cfg.slice consecutive sorted entries.
 //   piece kinds: DIRECT (bucket begins and ends inside the slice) -> bucket_sums[id]
 //                HEAD   (bucket began in an earlier slice)         -> head[s]
@@ -213,7 +224,7 @@ msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t
 __global__ void __launch_bounds__(128)
 msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restrict__ sorted,
                       const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
-                      const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *__restrict__ bucket_sums,
+                      const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *bucket_sums,
                       XYZZ *__restrict__ head, XYZZ *__restrict__ tail, int32_t *__restrict__ tail_j) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = totals[0], J = totals[1];
@@ -237,7 +248,7 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
     while (true) {
         if (e == bend) {  // bucket j is complete
             if (started_before) store_xyzz(&head[s], acc);
-            else store_xyzz(&bucket_sums[ne_id[j]], acc);
+            else bucket_accumulate(&bucket_sums[ne_id[j]], acc);
             acc = xyzz_identity();
             started_before = false;
             j++;
@@ -265,7 +276,7 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
         store_xyzz(&tail[s], acc);           // first piece of a bucket that continues
         tail_j[s] = (int32_t)j;
     } else {
-        store_xyzz(&bucket_sums[ne_id[j]], acc);
+        bucket_accumulate(&bucket_sums[ne_id[j]], acc);
     }
 }
 
@@ -292,7 +303,7 @@ msm_fixup_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict
         XYZZ q = load_xyzz(&head[t]);
         xyzz_add(acc, q);
     }
-    store_xyzz(&bucket_sums[ne_id[j]], acc);
+    bucket_accumulate(&bucket_sums[ne_id[j]], acc);
 }
 __global__ void __launch_bounds__(128)
 msm_fixup_heavy_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id, MsmCfg cfg,
@@ -323,7 +334,10 @@ msm_fixup_heavy_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__re
             }
             __syncthreads();
         }
-        if (tid == 0) store_xyzz(&bucket_sums[ne_id[j]], load_xyzz(&sh[0]));
+        if (tid == 0) {
+            XYZZ total = load_xyzz(&sh[0]);
+            bucket_accumulate(&bucket_sums[ne_id[j]], total);
+        }
         __syncthreads();
     }
 }

@@ -124,6 +124,10 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
 /* ---- tuning / introspection ------------------------------------------------------- */
 /* Override the MSM window (0 = automatic). */
 int h2b_set_msm_window(uint32_t c);
+/* Host-buffer MSM entry points (h2b_best_multiexp, h2b_commit) split inputs of at least `min_n`
+ * points into `chunks` contiguous pieces so the H2D copy of a piece overlaps the bucket accumulation
+ * of the previous one (default 4 pieces from 2^21 points). */
+int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n);
 /* Number of kernel launches issued by the library since h2b_init (for bench accounting). */
 uint64_t h2b_kernel_launches(void);
 /* Dominant-kernel timing (MSM: the bucket-accumulation kernel; NTT: all passes of one transform).

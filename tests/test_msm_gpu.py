@@ -171,3 +171,24 @@ def test_large_msm_linearity(h2b, spec, href):
     lo = h2b.best_multiexp(b[: n // 2].copy(), pts[: n // 2].copy())
     hi = h2b.best_multiexp(b[n // 2:].copy(), pts[n // 2:].copy())
     assert (href.g1_to_affine(h2b.g1_fold(np.stack([lo, hi]))) == href.g1_to_affine(rb)).all()
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 7])
+def test_chunked_host_path_matches_oracle(h2b, spec, href, chunks):
+    """h2b_best_multiexp / h2b_commit overlap H2D with compute by splitting the points into chunks that
+    accumulate into the same buckets; force that path at a size the oracle checks quickly."""
+    import ctypes as C
+    from halo2_prover_b200 import _ffi
+    n = 6000
+    sc, pts = href.random_fr(n, 91), href.random_g1(n, 92)
+    sc[::5] = sc[0]          # skew: repeated scalar values straddle chunk boundaries
+    pts[7::11] = 0           # identity bases
+    want = _affine(href, href.best_multiexp(sc, pts))
+    _ffi.check(_ffi.lib().h2b_set_e2e_chunking(chunks, C.c_size_t(1000)))
+    try:
+        assert (_affine(href, h2b.best_multiexp(sc, pts)) == want).all()
+        params = h2b.ParamsKZG(13, np.concatenate([pts, href.random_g1((1 << 13) - n, 93)]))
+        assert (_affine(href, params.commit(sc)) == want).all()
+        params.release()
+    finally:
+        _ffi.check(_ffi.lib().h2b_set_e2e_chunking(4, C.c_size_t(1 << 21)))
