@@ -35,7 +35,7 @@ std::mutex g_mu;
 enum BufId {
     BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_CURSOR, BUF_NEOFF, BUF_NEID, BUF_SORTED, BUF_DIGITS, BUF_HEAD, BUF_TAIL,
     BUF_TAILJ, BUF_TOTALS,
-    BUF_BUCKETS, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
+    BUF_BUCKETS, BUF_BUCKETS2, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
     BUF_NTT_OUT, BUF_MISC,
     BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
 };
@@ -205,7 +205,8 @@ MsmCfg msm_plan(size_t n) {
 // host-buffer entry points overlap the H2D copy of chunk k+1 with the accumulation of chunk k.
 struct MsmRun {
     MsmCfg cfg;       // window geometry from the TOTAL size
-    XYZZ *buckets;
+    XYZZ *buckets;    // running bucket sums (all-zero = identity)
+    uint32_t chunks_done = 0;
 };
 
 int msm_identity_out(Projective *d_out, cudaStream_t s) {
@@ -229,7 +230,7 @@ int msm_begin(size_t n_total, MsmRun *run, cudaStream_t s) {
 }
 
 // Points [0, m) of (d_scalars, d_bases): digits -> scan -> scatter -> accumulate -> fix-up.
-int msm_chunk(const MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m, cudaStream_t s) {
+int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m, cudaStream_t s) {
     if (m == 0) return H2B_OK;
     MsmCfg cfg = run.cfg;
     cfg.n = (uint32_t)m;
@@ -255,6 +256,14 @@ int msm_chunk(const MsmRun &run, const Fe *d_scalars, const Affine *d_bases, siz
     TRY(get_buf(BUF_TOTALS, 16, (void **)&totals));
     TRY(get_buf(BUF_HEAVY, (max_slices + 2) * 4, (void **)&heavy));
 
+    // the first chunk fills the running buckets directly; later chunks fill a scratch set that a
+    // uniform merge kernel adds in (doing that addition inside the accumulation loop would stall
+    // whole warps on every lane's bucket boundary)
+    XYZZ *target = run.buckets;
+    if (run.chunks_done > 0) {
+        TRY(get_buf(BUF_BUCKETS2, (size_t)cfg.nb * sizeof(XYZZ), (void **)&target));
+        CU(cudaMemsetAsync(target, 0, (size_t)cfg.nb * sizeof(XYZZ), s));
+    }
     CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
     CU(cudaMemsetAsync(heavy, 0, 4, s));
     CU(cudaMemsetAsync(tail_j, 0xff, max_slices * 4, s));
@@ -273,14 +282,19 @@ int msm_chunk(const MsmRun &run, const Fe *d_scalars, const Affine *d_bases, siz
     LAUNCHED();
     time_begin(s);
     uint32_t ablocks = (uint32_t)((max_slices + 127) / 128);
-    msm_accumulate_kernel<<<ablocks, 128, 0, s>>>(d_bases, sorted, ne_off, ne_id, totals, cfg, run.buckets, head, tail,
+    msm_accumulate_kernel<<<ablocks, 128, 0, s>>>(d_bases, sorted, ne_off, ne_id, totals, cfg, target, head, tail,
                                                   tail_j);
     LAUNCHED();
     time_end(s);
-    msm_fixup_kernel<<<ablocks, 128, 0, s>>>(ne_off, ne_id, totals, cfg, head, tail, tail_j, run.buckets, heavy);
+    msm_fixup_kernel<<<ablocks, 128, 0, s>>>(ne_off, ne_id, totals, cfg, head, tail, tail_j, target, heavy);
     LAUNCHED();
-    msm_fixup_heavy_kernel<<<g->sm_count * 4, 128, 0, s>>>(ne_off, ne_id, cfg, head, tail, tail_j, heavy, run.buckets);
+    msm_fixup_heavy_kernel<<<g->sm_count * 4, 128, 0, s>>>(ne_off, ne_id, cfg, head, tail, tail_j, heavy, target);
     LAUNCHED();
+    if (run.chunks_done > 0) {
+        msm_merge_kernel<<<(cfg.nb + 127) / 128, 128, 0, s>>>(run.buckets, target, cfg.nb);
+        LAUNCHED();
+    }
+    run.chunks_done++;
     return H2B_OK;
 }
 

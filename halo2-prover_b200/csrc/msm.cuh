@@ -206,17 +206,6 @@ msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t
     if (lo < nb && lo + ipt >= nb) ne_off[rb] = ra;
 }
 
-// bucket_sums[id] += acc.  Each bucket has exactly one writer per chunk; the first chunk finds the
-// identity (all-zero) there and stores directly.
-H2B_DI void bucket_accumulate(XYZZ *slot, XYZZ &acc) {
-    const Fe zz = load_fe(&slot->zz);
-    if (!Fq::is_zero(zz)) {
-        XYZZ prev = load_xyzz(slot);
-        xyzz_add(acc, prev);
-    }
-    store_xyzz(slot, acc);
-}
-
 // One thread per slice of cfg.slice consecutive sorted entries.
 //   piece kinds: DIRECT (bucket begins and ends inside the slice) -> bucket_sums[id]
 //                HEAD   (bucket began in an earlier slice)         -> head[s]
@@ -224,7 +213,7 @@ H2B_DI void bucket_accumulate(XYZZ *slot, XYZZ &acc) {
 __global__ void __launch_bounds__(128)
 msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restrict__ sorted,
                       const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
-                      const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *bucket_sums,
+                      const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *__restrict__ bucket_sums,
                       XYZZ *__restrict__ head, XYZZ *__restrict__ tail, int32_t *__restrict__ tail_j) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = totals[0], J = totals[1];
@@ -248,7 +237,7 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
     while (true) {
         if (e == bend) {  // bucket j is complete
             if (started_before) store_xyzz(&head[s], acc);
-            else bucket_accumulate(&bucket_sums[ne_id[j]], acc);
+            else store_xyzz(&bucket_sums[ne_id[j]], acc);
             acc = xyzz_identity();
             started_before = false;
             j++;
@@ -276,7 +265,7 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
         store_xyzz(&tail[s], acc);           // first piece of a bucket that continues
         tail_j[s] = (int32_t)j;
     } else {
-        bucket_accumulate(&bucket_sums[ne_id[j]], acc);
+        store_xyzz(&bucket_sums[ne_id[j]], acc);
     }
 }
 
@@ -303,7 +292,7 @@ msm_fixup_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict
         XYZZ q = load_xyzz(&head[t]);
         xyzz_add(acc, q);
     }
-    bucket_accumulate(&bucket_sums[ne_id[j]], acc);
+    store_xyzz(&bucket_sums[ne_id[j]], acc);
 }
 __global__ void __launch_bounds__(128)
 msm_fixup_heavy_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id, MsmCfg cfg,
@@ -334,12 +323,21 @@ msm_fixup_heavy_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__re
             }
             __syncthreads();
         }
-        if (tid == 0) {
-            XYZZ total = load_xyzz(&sh[0]);
-            bucket_accumulate(&bucket_sums[ne_id[j]], total);
-        }
+        if (tid == 0) store_xyzz(&bucket_sums[ne_id[j]], load_xyzz(&sh[0]));
         __syncthreads();
     }
+}
+
+// dst[b] += src[b] for every bucket: merges the bucket sums of a later chunk into the running ones.
+__global__ void __launch_bounds__(128)
+msm_merge_kernel(XYZZ *__restrict__ dst, const XYZZ *__restrict__ src, uint32_t nb) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    XYZZ q = load_xyzz(&src[b]);
+    if (xyzz_is_identity(q)) return;
+    XYZZ acc = load_xyzz(&dst[b]);
+    xyzz_add(acc, q);
+    store_xyzz(&dst[b], acc);
 }
 
 // Per window: sum_{k=1..bpw} k * B_k.  Grid = (blocks per window, windows); thread g of a window
