@@ -396,10 +396,30 @@ def main() -> None:
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries exactly ONE JSON line: anything libraries print meanwhile (e.g. the NCCL version
+    # banner) is diverted to stderr by pointing fd 1 at fd 2 until the line is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    real_print = print
+
+    def capture(*a, **k):
+        lines.append(" ".join(str(x) for x in a))
+
+    globals()["print"] = capture
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        globals()["print"] = real_print
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    for ln in lines:
+        real_print(ln, flush=True)
 
 
 if __name__ == "__main__":
