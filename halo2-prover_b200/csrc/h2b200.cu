@@ -430,27 +430,36 @@ int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log
     return H2B_OK;
 }
 
-uint32_t g_ntt_tile_log = 9;  // log2 elements per multi-pass tile (9, 10 or 11); 9 measured best on B200
+uint32_t g_ntt_tile_log = 10;  // log2 elements per multi-pass tile (8, 9 or 10); 10 measured best on B200
 
 int dispatch_pass(uint32_t S, bool single, const Fe *in, Fe *out, const Fe *W, uint32_t log_n,
                   uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s) {
-    if (!single && g_ntt_tile_log == 10) {
-        switch (S) {
-            case 5: return launch_pass<5, 32, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 6: return launch_pass<6, 16, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 8, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 4, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 9: return launch_pass<9, 2, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 10: return launch_pass<10, 1, 256>(in, out, W, log_n, log_ns, last, io, s);
-        }
-    }
+    // threads per block = tile elements / 8 (one radix-8 group per thread and round)
     if (!single && g_ntt_tile_log == 9) {
         switch (S) {
-            case 5: return launch_pass<5, 16, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 6: return launch_pass<6, 8, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 4, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 2, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 9: return launch_pass<9, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 5: return launch_pass<5, 16, 64>(in, out, W, log_n, log_ns, last, io, s);
+            case 6: return launch_pass<6, 8, 64>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 4, 64>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 2, 64>(in, out, W, log_n, log_ns, last, io, s);
+            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s);
+        }
+    }
+    if (!single && g_ntt_tile_log == 10) {
+        switch (S) {
+            case 5: return launch_pass<5, 32, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 6: return launch_pass<6, 16, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 8, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 4, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 9: return launch_pass<9, 2, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
+        }
+    }
+    if (!single && g_ntt_tile_log == 8) {
+        switch (S) {
+            case 5: return launch_pass<5, 8, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 6: return launch_pass<6, 4, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 2, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
         }
     }
     if (single) {
@@ -461,25 +470,16 @@ int dispatch_pass(uint32_t S, bool single, const Fe *in, Fe *out, const Fe *W, u
             case 4: return launch_pass<4, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
             case 5: return launch_pass<5, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
             case 6: return launch_pass<6, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 1, 64>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 9: return launch_pass<9, 1, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 10: return launch_pass<10, 1, 512>(in, out, W, log_n, log_ns, last, io, s);
-        }
-    } else {
-        switch (S) {
-            case 5: return launch_pass<5, 64, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 6: return launch_pass<6, 32, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 16, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 8, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 9: return launch_pass<9, 4, 256>(in, out, W, log_n, log_ns, last, io, s);
-            case 10: return launch_pass<10, 2, 256>(in, out, W, log_n, log_ns, last, io, s);
+            case 7: return launch_pass<7, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s);
+            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
         }
     }
-    return fail(H2B_ERR_ARG, "ntt: unsupported radix");
+    return fail(H2B_ERR_ARG, "ntt: unsupported radix / tile configuration");
 }
 
-uint32_t g_ntt_max_radix = 8;
+uint32_t g_ntt_max_radix = 10;  // two passes up to 2^20, three up to 2^28 (measured best on B200)
 
 // Transform `src` (n_in valid elements of a 2^log_n domain) into `dst`; `dst` may equal `src`.
 // dst_full: `dst` holds 2^log_n elements and may carry intermediate passes; otherwise (truncated
@@ -806,9 +806,10 @@ int h2b_init(int device) {
     const char *tl = getenv("H2B_NTT_TILE_LOG");
     if (tl) {
         int v = atoi(tl);
-        if (v >= 9 && v <= 11) g_ntt_tile_log = (uint32_t)v;
+        if (v >= 8 && v <= 10) g_ntt_tile_log = (uint32_t)v;
     }
     if (g_ntt_tile_log == 9 && g_ntt_max_radix > 9) g_ntt_max_radix = 9;
+    if (g_ntt_tile_log == 8 && g_ntt_max_radix > 8) g_ntt_max_radix = 8;
     const char *ec = getenv("H2B_E2E_CHUNKS");
     if (ec) {
         int v = atoi(ec);

@@ -10,10 +10,11 @@
 // X[K] = sum_n x[n] * omega^(n*K), Montgomery in / Montgomery out, fully reduced.
 // The algorithm is NOT the reference's (bit-reverse + radix-2 DIT sweeps over the
 // whole array).  It is an autosort (Stockham) decimation-in-frequency transform
-// split into at most four passes; each pass stages a [2^S rows] x [C columns] tile
-// in shared memory with 128-bit coalesced loads of C adjacent elements per row,
-// runs S butterfly levels on chip, multiplies by the inter-pass twiddle from a
-// cached table of powers of omega, and stores C adjacent elements per output row.
+// split into at most four passes; each pass works on a [2^S rows] x [C columns] tile:
+// 128-bit coalesced loads of C adjacent elements per row straight into registers,
+// S butterfly levels in rounds of three levels held in registers (8 rows per thread,
+// shared memory only between rounds), the inter-pass twiddle from a cached table of
+// powers of omega, and stores of C adjacent elements per output row.
 // The scaling steps of the domain transforms are fused into the first load
 // (coset powers, zero padding) and the last store (1/n, inverse coset powers,
 // truncation), so every transform costs exactly its passes and nothing else.
@@ -59,6 +60,114 @@ H2B_DI uint32_t bitrev_s(uint32_t u) {
     return __brev(u) >> (32 - S);
 }
 
+H2B_DI Fe fe_from_u4(const uint4 &a, const uint4 &b) {
+    Fe r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+// RB decimation-in-frequency levels on 2^RB rows held in registers.  The rows are
+// u_t = row_base + t * st of the tile (row_base mod st = lo), the levels are the tile levels
+// lvl .. lvl + RB - 1; the butterfly (u, u + h) of tile level L uses omega_R^((u mod h) << L).
+template <int RB>
+H2B_DI void dif_levels(Fe (&a)[1 << RB], uint32_t lo, uint32_t st, uint32_t lvl,
+                       const uint4 *__restrict__ t_lo, const uint4 *__restrict__ t_hi) {
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        const int half = 1 << (RB - 1 - q);
+#pragma unroll
+        for (int t = 0; t < (1 << RB); t++) {
+            if (t & half) continue;
+            const Fe x = a[t], y = a[t + half];
+            a[t] = Fr::add(x, y);
+            Fe d = Fr::sub(x, y);
+            const uint32_t e = (lo + (uint32_t)(t & (half - 1)) * st) << (lvl + q);
+            if (e != 0) d = Fr::mul(d, fe_from_u4(t_lo[e], t_hi[e]));
+            a[t + half] = d;
+        }
+    }
+}
+
+struct PassArgs {
+    const Fe *in;
+    Fe *out;
+    const Fe *W;
+    uint32_t log_n, log_ns, last, q0, M;
+};
+
+// Rounds of a pass: 3 levels per round while possible (2 + 2 when four remain), the first round
+// reads global memory, the last one writes it, intermediate results live in shared memory.
+template <int S, int C, int NT, int LVL>
+H2B_DI void pass_rounds(const PassArgs &pa, const NttIo &io, uint4 *s_lo, uint4 *s_hi,
+                        const uint4 *t_lo, const uint4 *t_hi, uint32_t tid) {
+    constexpr int REM = S - LVL;
+    constexpr int RB = (REM >= 3 && REM != 4) ? 3 : (REM >= 2 ? 2 : 1);
+    constexpr bool FIRST = LVL == 0, LAST = LVL + RB == S;
+    constexpr uint32_t ST = (1u << S) >> (LVL + RB);
+    constexpr uint32_t GROUPS = ((1u << S) * C) >> RB;
+    for (uint32_t g = tid; g < GROUPS; g += NT) {
+        const uint32_t col = g % C, rest = g / C;
+        const uint32_t lo = rest % ST, hi = rest / ST;
+        const uint32_t row_base = hi * (ST << RB) + lo;
+        Fe a[1 << RB];
+        if (FIRST) {
+#pragma unroll
+            for (int t = 0; t < (1 << RB); t++) {
+                const uint32_t idx = pa.q0 + col + (row_base + t * ST) * pa.M;
+                Fe v;
+                if (idx < io.n_in) {
+                    v = load_fe(&pa.in[idx]);
+                    if (io.pro) {
+                        const uint32_t m3 = idx % 3;
+                        if (m3) v = Fr::mul(v, io.pro_c[m3]);
+                    }
+                } else {
+                    v = Fr::zero();
+                }
+                a[t] = v;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < (1 << RB); t++) {
+                const uint32_t e = (row_base + t * ST) * C + col;
+                a[t] = fe_from_u4(s_lo[e], s_hi[e]);
+            }
+        }
+        dif_levels<RB>(a, lo, ST, LVL, t_lo, t_hi);
+        if (LAST) {
+            // ST == 1: the rows are row_base .. row_base + 2^RB - 1; row u holds output K = bitrev_S(u)
+            const uint32_t q = pa.q0 + col;
+            const uint32_t jp = q >> pa.log_ns, p = q & ((1u << pa.log_ns) - 1);
+#pragma unroll
+            for (int t = 0; t < (1 << RB); t++) {
+                const uint32_t u = row_base + t * ST;
+                const uint32_t k = bitrev_s<S>(u);
+                const uint32_t oidx = (jp << (pa.log_ns + S)) + p + (k << pa.log_ns);
+                if (oidx >= io.n_out) continue;
+                Fe v = a[t];
+                if (!pa.last) {
+                    const uint32_t ex = (jp * k) << pa.log_ns;  // < N
+                    if (ex) v = Fr::mul(v, load_fe_ro(&pa.W[ex]));
+                }
+                if (io.epi) v = Fr::mul(v, io.epi_c[oidx % 3]);
+                store_fe(&pa.out[oidx], v);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < (1 << RB); t++) {
+                const uint32_t e = (row_base + t * ST) * C + col;
+                s_lo[e] = make_uint4(a[t].l[0], a[t].l[1], a[t].l[2], a[t].l[3]);
+                s_hi[e] = make_uint4(a[t].l[4], a[t].l[5], a[t].l[6], a[t].l[7]);
+            }
+        }
+    }
+    if constexpr (!LAST) {
+        __syncthreads();
+        pass_rounds<S, C, NT, LVL + RB>(pa, io, s_lo, s_hi, t_lo, t_hi, tid);
+    }
+}
+
 // One pass.  S = log2 radix, C = columns per tile, NT = threads per block.
 template <int S, int C, int NT>
 __global__ void __launch_bounds__(NT)
@@ -72,89 +181,21 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, uint32_t log_n,
     uint4 *t_lo = smem_u4 + 2 * TILE;   // inner twiddles (omega^M)^t, t < R/2
     uint4 *t_hi = t_lo + (R / 2 > 0 ? R / 2 : 1);
 
-    const uint32_t M = 1u << (log_n - S);        // columns in the whole pass
-    const uint32_t q0 = blockIdx.x * C;
+    PassArgs pa;
+    pa.in = in; pa.out = out; pa.W = W;
+    pa.log_n = log_n; pa.log_ns = log_ns; pa.last = last;
+    pa.M = 1u << (log_n - S);           // columns in the whole pass
+    pa.q0 = blockIdx.x * C;
     const uint32_t tid = threadIdx.x;
 
     // inner twiddles: W[t * M]
     for (uint32_t t = tid; t < R / 2; t += NT) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(&W[(size_t)t * M]);
+        const uint4 *p = reinterpret_cast<const uint4 *>(&W[(size_t)t * pa.M]);
         t_lo[t] = __ldg(p);
         t_hi[t] = __ldg(p + 1);
     }
-    // load tile: element (r, col) <- in[q0 + col + r*M]
-    for (uint32_t e = tid; e < TILE; e += NT) {
-        uint32_t col = e % C, r = e / C;
-        uint32_t idx = q0 + col + r * M;
-        Fe v;
-        if (idx < io.n_in) {
-            v = load_fe(&in[idx]);
-            if (io.pro) {
-                uint32_t m3 = idx % 3;
-                if (m3) v = Fr::mul(v, io.pro_c[m3]);
-            }
-        } else {
-            v = Fr::zero();
-        }
-        s_lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        s_hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-    }
     __syncthreads();
-
-    // S decimation-in-frequency levels, natural order in -> bit-reversed rows out
-#pragma unroll 1
-    for (int lvl = 0; lvl < S; lvl++) {
-        const uint32_t h = (uint32_t)R >> (lvl + 1);  // half span in rows
-        for (uint32_t b = tid; b < (uint32_t)(TILE / 2); b += NT) {
-            uint32_t col = b % C, i = b / C;           // i in [0, R/2)
-            uint32_t lo_i = i & (h - 1);
-            uint32_t row0 = ((i - lo_i) << 1) + lo_i;
-            uint32_t e0 = row0 * C + col, e1 = e0 + h * C;
-            uint4 a0 = s_lo[e0], a1 = s_hi[e0], b0 = s_lo[e1], b1 = s_hi[e1];
-            Fe x, y;
-            x.l[0] = a0.x; x.l[1] = a0.y; x.l[2] = a0.z; x.l[3] = a0.w;
-            x.l[4] = a1.x; x.l[5] = a1.y; x.l[6] = a1.z; x.l[7] = a1.w;
-            y.l[0] = b0.x; y.l[1] = b0.y; y.l[2] = b0.z; y.l[3] = b0.w;
-            y.l[4] = b1.x; y.l[5] = b1.y; y.l[6] = b1.z; y.l[7] = b1.w;
-            Fe sum = Fr::add(x, y);
-            Fe dif = Fr::sub(x, y);
-            uint32_t tw = lo_i << lvl;  // exponent of omega^M, < R/2
-            if (tw != 0) {
-                uint4 w0 = t_lo[tw], w1 = t_hi[tw];
-                Fe w;
-                w.l[0] = w0.x; w.l[1] = w0.y; w.l[2] = w0.z; w.l[3] = w0.w;
-                w.l[4] = w1.x; w.l[5] = w1.y; w.l[6] = w1.z; w.l[7] = w1.w;
-                dif = Fr::mul(dif, w);
-            }
-            s_lo[e0] = make_uint4(sum.l[0], sum.l[1], sum.l[2], sum.l[3]);
-            s_hi[e0] = make_uint4(sum.l[4], sum.l[5], sum.l[6], sum.l[7]);
-            s_lo[e1] = make_uint4(dif.l[0], dif.l[1], dif.l[2], dif.l[3]);
-            s_hi[e1] = make_uint4(dif.l[4], dif.l[5], dif.l[6], dif.l[7]);
-        }
-        __syncthreads();
-    }
-
-    // store: row u holds output K = bitrev_S(u)
-    const uint32_t ns_mask = (1u << log_ns) - 1;
-    for (uint32_t e = tid; e < TILE; e += NT) {
-        uint32_t col = e % C, k = e / C;  // iterate K in natural order so stores walk forward
-        uint32_t u = S ? bitrev_s<(S ? S : 1)>(k) : 0;
-        uint32_t q = q0 + col;
-        uint32_t jp = q >> log_ns, p = q & ns_mask;
-        uint32_t oidx = (jp << (log_ns + S)) + p + (k << log_ns);
-        if (oidx >= io.n_out) continue;
-        uint32_t se = u * C + col;
-        uint4 a0 = s_lo[se], a1 = s_hi[se];
-        Fe v;
-        v.l[0] = a0.x; v.l[1] = a0.y; v.l[2] = a0.z; v.l[3] = a0.w;
-        v.l[4] = a1.x; v.l[5] = a1.y; v.l[6] = a1.z; v.l[7] = a1.w;
-        if (!last) {
-            uint32_t ex = (jp * k) << log_ns;  // < N
-            if (ex) v = Fr::mul(v, load_fe_ro(&W[ex]));
-        }
-        if (io.epi) v = Fr::mul(v, io.epi_c[oidx % 3]);
-        store_fe(&out[oidx], v);
-    }
+    pass_rounds<S, C, NT, 0>(pa, io, s_lo, s_hi, t_lo, t_hi, tid);
 }
 
 // a[i] *= c[i % m]  (parallelize-style elementwise maps: divide_by_vanishing_poly, log_n = 0 scaling)
