@@ -275,6 +275,10 @@ def run_b200(args) -> None:
                "sample": f"first 2^{args.ref_log_n} points of the workload; C restatement of halo2_proofs@6b43b6b "
                          "best_multiexp (not the Rust binary); result equal to the GPU's on the same sample"}
 
+    replay = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        replay = bench_proof_replay(args, h2b, _ffi)
+
     if rank == 0:
         peaks = measured_peaks()
         acc_ms = ktot.value / max(kcalls.value, 1)
@@ -304,10 +308,69 @@ def run_b200(args) -> None:
                                  "peak_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if hbm_peak else "absent"}},
             "cpu_baseline": cpu,
             "ntt": ntt,
+            "proof_replay": replay,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_proof_replay(args, h2b, _ffi) -> dict:
+    """The hot-path calls of ONE Poseidon (W3/R2/L2) proof at 2^k rows, in the order and count
+    create_proof issues them (16 commits = MSM(2^k), 7 lagrange_to_coeff(2^k),
+    7 coeff_to_extended(k -> k+3), 1 extended_to_coeff), through the host-buffer C ABI exactly as the
+    patched halo2_proofs would call it, next to the same calls on the CPU restatement.  This is the
+    MSM/NTT share of a proof, not a proof: witness synthesis, gate evaluation and the transcript stay
+    on the host in the reference and are out of scope here."""
+    import h2ref
+    k = args.proof_k
+    n = 1 << k
+    threads = os.cpu_count() or 1
+    d = h2b.EvaluationDomain(6, k)           # Pow5 chip: degree 6 -> extended_k = k + 3
+    dc = h2ref.domain_new(6, k)
+    g = h2ref.random_g1(1 << 10, 5)
+    g = np.ascontiguousarray(np.tile(g, (n >> 10, 1))) if n >= 1024 else g[:n].copy()
+    params = h2b.ParamsKZG(k, g, g)
+    cols = [rand_fr_np(n, 300 + i) for i in range(7)]
+    ext_in = rand_fr_np(1 << d.extended_k, 399)
+
+    def gpu_once():
+        outs = []
+        for i in range(16):
+            outs.append(params.commit_lagrange(cols[i % 7]) if i < 8 else params.commit(cols[i % 7]))
+        for i in range(7):
+            d.lagrange_to_coeff(cols[i].copy())
+        for i in range(7):
+            d.coeff_to_extended(cols[i])
+        d.extended_to_coeff(ext_in)
+        return outs
+
+    def cpu_once():
+        outs = []
+        for i in range(16):
+            outs.append(h2ref.best_multiexp(cols[i % 7], g, threads))
+        for i in range(7):
+            h2ref.lagrange_to_coeff(dc, cols[i], threads)
+        for i in range(7):
+            h2ref.coeff_to_extended(dc, cols[i], threads)
+        h2ref.extended_to_coeff(dc, ext_in, threads)
+        return outs
+
+    gpu_once()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        go = gpu_once()
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    t0 = time.perf_counter()
+    co = cpu_once()
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    same = all((h2ref.g1_to_affine(a) == h2ref.g1_to_affine(b)).all() for a, b in zip(go, co))
+    params.release()
+    return {"what": "MSM/NTT calls of one Poseidon-shaped proof (hot path only, host buffers, sequential calls)",
+            "k": k, "extended_k": int(d.extended_k), "calls": {"msm": 16, "lagrange_to_coeff": 7, "coeff_to_extended": 7,
+                                                            "extended_to_coeff": 1},
+            "gpu_ms": gpu_ms, "cpu_ms": cpu_ms, "cpu_threads": threads, "commitments_equal": bool(same)}
 
 
 def bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, imad_gops) -> dict:
@@ -393,6 +456,7 @@ def main() -> None:
     ap.add_argument("--log-n", type=int, default=24, help="log2 points per GPU")
     ap.add_argument("--ntt-k", type=int, default=20)
     ap.add_argument("--ref-log-n", type=int, default=18, help="log2 points of the bounded CPU sample")
+    ap.add_argument("--proof-k", type=int, default=14, help="rows (log2) of the proof-shaped replay")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

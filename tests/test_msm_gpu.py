@@ -192,3 +192,52 @@ def test_chunked_host_path_matches_oracle(h2b, spec, href, chunks):
         params.release()
     finally:
         _ffi.check(_ffi.lib().h2b_set_e2e_chunking(4, C.c_size_t(1 << 21)))
+
+
+def test_max_size_msm_2p26_linearity(h2b, spec, href):
+    """BASELINE's largest MSM (2^26 points: 4 GiB of bases, 2 GiB of scalars), device-resident, checked through
+    linearity: MSM(a, P) + MSM(b, P) == MSM(a + b, P), and a range split folds to the whole."""
+    import ctypes as C
+    import torch
+    from halo2_prover_b200 import _ffi, arithmetic
+    n = 1 << 26
+    L = _ffi.lib()
+    rng = np.random.default_rng(5)
+
+    def rand(nn):
+        a = rng.integers(0, np.iinfo(np.uint64).max, size=(nn, 4), dtype=np.uint64, endpoint=True)
+        a[:, 3] &= np.uint64((1 << 60) - 1)
+        return a
+
+    s = torch.cuda.Stream()
+    gen = spec.affine_to_array([spec.G1_GENERATOR])[0]
+    with torch.cuda.stream(s):
+        seeds = torch.from_numpy(rand(n).view(np.int64)).cuda()
+        bases = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        _ffi.check(L.h2b_dev_fixed_base_mul(C.c_void_p(seeds.data_ptr()), C.c_size_t(n), _ffi.u64p(gen),
+                                            C.c_void_p(bases.data_ptr()), C.c_void_p(s.cuda_stream)))
+        del seeds
+        a_h, b_h = rand(n), rand(n)
+        a, b = torch.from_numpy(a_h.view(np.int64)).cuda(), torch.from_numpy(b_h.view(np.int64)).cuda()
+        # a + b < 2^61 * 2^192 < r: plain integer addition of the limbs IS the field addition here
+        ab_h = np.zeros_like(a_h)
+        carry = np.zeros(n, dtype=np.uint64)
+        for limb in range(4):
+            t = a_h[:, limb] + b_h[:, limb]
+            c1 = (t < a_h[:, limb]).astype(np.uint64)
+            t2 = t + carry
+            c2 = (t2 < t).astype(np.uint64)
+            ab_h[:, limb] = t2
+            carry = c1 + c2
+        ab = torch.from_numpy(ab_h.view(np.int64)).cuda()
+        outs = torch.empty((5, 12), dtype=torch.int64, device="cuda")
+        arithmetic.dev_msm(a, bases, outs[0], stream=s)
+        arithmetic.dev_msm(b, bases, outs[1], stream=s)
+        arithmetic.dev_msm(ab, bases, outs[2], stream=s)
+        arithmetic.dev_msm(b[: n // 2], bases[: n // 2], outs[3], stream=s)
+        arithmetic.dev_msm(b[n // 2:], bases[n // 2:], outs[4], stream=s)
+        s.synchronize()
+    o = outs.cpu().numpy().view(np.uint64)
+    assert (href.g1_to_affine(href.g1_add(o[0], o[1])) == href.g1_to_affine(o[2])).all()
+    assert (href.g1_to_affine(href.g1_add(o[3], o[4])) == href.g1_to_affine(o[1])).all()
+    assert spec.g1_is_on_curve(spec.projective_array_to_affine(o[2]))
