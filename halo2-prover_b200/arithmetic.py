@@ -54,7 +54,9 @@ def _stream_ptr(stream) -> C.c_void_p:
     if stream is None:
         import torch
         stream = torch.cuda.current_stream()
-    return C.c_void_p(stream.cuda_stream)
+    # torch's default stream is handle 0, which this ABI reads as "the library's own stream": name the
+    # legacy default stream explicitly (cudaStreamLegacy) so the caller's synchronize() covers the work
+    return C.c_void_p(stream.cuda_stream or 1)
 
 
 def dev_msm(coeffs_t, bases_t, out_t, n: int | None = None, stream=None) -> None:

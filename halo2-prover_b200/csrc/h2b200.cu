@@ -50,8 +50,10 @@ struct TwKey {
     }
 };
 struct Srs {
-    Affine *d = nullptr;
+    Affine *d = nullptr;      // the registered bases (n x 64 B)
     size_t n = 0;
+    Affine *table = nullptr;  // precomputed windows: table[w * n + i] = 2^(c*w) * d[i], or null
+    uint32_t c = 0, windows = 0;
 };
 
 struct Ctx {
@@ -66,6 +68,8 @@ struct Ctx {
     std::map<uint64_t, h2b_domain> domains;
     uint64_t launches = 0;
     uint32_t msm_window = 0;
+    uint32_t srs_window = 0;   // 0 = automatic
+    int srs_precompute = 1;
     int timing = 0;
     cudaEvent_t last_done = nullptr, copy_fence = nullptr;
     cudaStream_t copy_stream = nullptr;
@@ -169,26 +173,40 @@ uint32_t ceil_log2(size_t n) {
     return l;
 }
 
-MsmCfg msm_plan(size_t n) {
-    MsmCfg cfg{};
-    cfg.n = (uint32_t)n;
-    uint32_t lg = ceil_log2(n);
-    // window: measured optimum on B200 is lg(n) - 5 for n >= 2^19 (17 at 2^22..2^24; beyond that the
-    // shrinking bucket load costs more in lane divergence than the saved window gains)
-    uint32_t c = g->msm_window ? g->msm_window : (lg >= 19 ? lg - 5 : (lg > 4 ? lg - 4 : 0));
-    if (!g->msm_window) {
-        if (c < 4) c = 4;
-        if (c > 17) c = 17;
-    }
-    if (c < 2) c = 2;
-    if (c > 22) c = 22;
-    cfg.c = c;
+uint32_t msm_windows_for(uint32_t c) {
     uint32_t W = (254 + c - 1) / c;
     uint32_t top_bits = 254 - (W - 1) * c;
     if (top_bits > c - 1) W += 1;  // the (unsigned) top digit plus carry must fit 2^(c-1)
+    return W;
+}
+
+// Window geometry.  srs == nullptr: independent windows (one bucket set per window, Horner at the
+// end).  srs with a precomputed table: its c, all windows share one bucket set.
+MsmCfg msm_plan(size_t n, const Srs *srs = nullptr) {
+    MsmCfg cfg{};
+    cfg.n = (uint32_t)n;
+    uint32_t c;
+    if (srs && srs->table) {
+        c = srs->c;
+        cfg.shared = 1;
+        cfg.stride = (uint32_t)srs->n;
+    } else {
+        uint32_t lg = ceil_log2(n);
+        // window: measured optimum on B200 is lg(n) - 5 for n >= 2^19 (17 at 2^22..2^24; beyond that the
+        // bucket reduction and the scatter cost more than the saved window gains)
+        c = g->msm_window ? g->msm_window : (lg >= 19 ? lg - 5 : (lg > 4 ? lg - 4 : 0));
+        if (!g->msm_window) {
+            if (c < 4) c = 4;
+            if (c > 17) c = 17;
+        }
+        if (c < 2) c = 2;
+        if (c > 22) c = 22;
+    }
+    cfg.c = c;
+    uint32_t W = msm_windows_for(c);
     cfg.windows = W;
     cfg.bpw = 1u << (c - 1);
-    cfg.nb = W * cfg.bpw;
+    cfg.nb = cfg.shared ? cfg.bpw : W * cfg.bpw;
     for (uint32_t w = 0; w + 1 < W; w++) {
         uint32_t bit = c * w + c - 1;
         cfg.half[bit >> 5] |= 1u << (bit & 31);
@@ -198,6 +216,16 @@ MsmCfg msm_plan(size_t n) {
     while (lgrp < 4 && (cfg.bpw >> lgrp) > 256) lgrp++;
     cfg.lgrp = lgrp;
     return cfg;
+}
+
+// Shared-bucket window for a registered SRS of n points (tunable: H2B_SRS_WINDOW).
+uint32_t srs_window_for(size_t n) {
+    if (g->srs_window) return g->srs_window;
+    uint32_t lg = ceil_log2(n);
+    uint32_t c = lg > 2 ? lg - 2 : 1;
+    if (c < 6) c = 6;
+    if (c > 24) c = 24;
+    return c;
 }
 
 // An MSM is: begin (clear the buckets) -> one or more chunks over contiguous point ranges, each
@@ -221,19 +249,21 @@ int msm_identity_out(Projective *d_out, cudaStream_t s) {
     return H2B_OK;
 }
 
-int msm_begin(size_t n_total, MsmRun *run, cudaStream_t s) {
+int msm_begin(size_t n_total, MsmRun *run, cudaStream_t s, const Srs *srs = nullptr) {
     if (n_total > (1u << 30)) return fail(H2B_ERR_ARG, "msm: n > 2^30 not supported");
-    run->cfg = msm_plan(n_total);
+    run->cfg = msm_plan(n_total, srs);
     TRY(get_buf(BUF_BUCKETS, (size_t)run->cfg.nb * sizeof(XYZZ), (void **)&run->buckets));
     CU(cudaMemsetAsync(run->buckets, 0, (size_t)run->cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
     return H2B_OK;
 }
 
 // Points [0, m) of (d_scalars, d_bases): digits -> scan -> scatter -> accumulate -> fix-up.
-int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m, cudaStream_t s) {
+// In shared-bucket mode d_bases is the SRS table and `ioff` the chunk's first point inside the SRS.
+int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m, cudaStream_t s, size_t ioff = 0) {
     if (m == 0) return H2B_OK;
     MsmCfg cfg = run.cfg;
     cfg.n = (uint32_t)m;
+    cfg.ioff = (uint32_t)ioff;
     size_t entries = m * cfg.windows;
     uint32_t L = 512;  // slice: enough slices to fill the GPU several times over, at most 512 entries
     while (L > 16 && entries / L < (size_t)g->sm_count * 2048) L >>= 1;
@@ -299,7 +329,8 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
 }
 
 int msm_finish(const MsmRun &run, Projective *d_out, cudaStream_t s) {
-    const MsmCfg &cfg = run.cfg;
+    MsmCfg cfg = run.cfg;
+    if (cfg.shared) cfg.windows = 1;  // one bucket set: sum_k k * B_k is the result, no Horner
     XYZZ *windows, *wpart;
     uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
     uint32_t rthreads = G < 256 ? G : 256;      // power of two
@@ -325,7 +356,7 @@ int msm_run(const Fe *d_scalars, const Affine *d_bases, size_t n, Projective *d_
 
 // Host scalars (and optionally host bases) -> device in `chunks` pieces on the copy stream while
 // the compute stream works on the pieces that have landed.
-int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const Affine *d_bases_resident, size_t n,
+int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const Srs *srs, size_t n,
                       Projective *d_out) {
     cudaStream_t s = g->stream;
     if (n == 0) return msm_identity_out(d_out, s);
@@ -334,9 +365,10 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
     Affine *db = nullptr;
     TRY(get_buf(BUF_SCALARS, n * sizeof(Fe), (void **)&ds));
     if (h_bases) TRY(get_buf(BUF_BASES, n * sizeof(Affine), (void **)&db));
-    const Affine *bases = h_bases ? db : d_bases_resident;
+    const bool shared = srs && srs->table;
+    const Affine *bases = h_bases ? db : (shared ? srs->table : srs->d);
     MsmRun run;
-    TRY(msm_begin(n, &run, s));
+    TRY(msm_begin(n, &run, s, h_bases ? nullptr : srs));
     if (chunks <= 1) {
         CU(cudaMemcpyAsync(ds, h_scalars, n * sizeof(Fe), cudaMemcpyHostToDevice, s));
         if (h_bases) CU(cudaMemcpyAsync(db, h_bases, n * sizeof(Affine), cudaMemcpyHostToDevice, s));
@@ -364,7 +396,8 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
     }
     for (size_t k = 0; k < lo.size(); k++) {
         CU(cudaStreamWaitEvent(s, g->chunk_events[k], 0));
-        TRY(msm_chunk(run, ds + lo[k], bases + lo[k], hi[k] - lo[k], s));
+        if (shared) TRY(msm_chunk(run, ds + lo[k], bases, hi[k] - lo[k], s, lo[k]));
+        else TRY(msm_chunk(run, ds + lo[k], bases + lo[k], hi[k] - lo[k], s));
     }
     return msm_finish(run, d_out, s);
 }
@@ -810,6 +843,13 @@ int h2b_init(int device) {
     }
     if (g_ntt_tile_log == 9 && g_ntt_max_radix > 9) g_ntt_max_radix = 9;
     if (g_ntt_tile_log == 8 && g_ntt_max_radix > 8) g_ntt_max_radix = 8;
+    const char *sw = getenv("H2B_SRS_WINDOW");
+    if (sw) {
+        int v = atoi(sw);
+        if (v >= 2 && v <= 24) c->srs_window = (uint32_t)v;
+    }
+    const char *sp = getenv("H2B_SRS_PRECOMPUTE");
+    if (sp) c->srs_precompute = atoi(sp) != 0;
     const char *ec = getenv("H2B_E2E_CHUNKS");
     if (ec) {
         int v = atoi(ec);
@@ -826,7 +866,10 @@ void h2b_shutdown(void) {
     cudaDeviceSynchronize();
     for (int i = 0; i < BUF_COUNT; i++)
         if (g->buf[i]) cudaFree(g->buf[i]);
-    for (auto &kv : g->srs) cudaFree(kv.second.d);
+    for (auto &kv : g->srs) {
+        cudaFree(kv.second.d);
+        if (kv.second.table) cudaFree(kv.second.table);
+    }
     for (auto &kv : g->twiddles) cudaFree(kv.second);
     for (auto e : g->tev0) cudaEventDestroy(e);
     for (auto e : g->tev1) cudaEventDestroy(e);
@@ -844,6 +887,14 @@ int h2b_set_msm_window(uint32_t c) {
     TRY(ensure_ctx());
     if (c != 0 && (c < 2 || c > 22)) return fail(H2B_ERR_ARG, "msm window must be 0 or in [2, 22]");
     g->msm_window = c;
+    return H2B_OK;
+}
+int h2b_set_srs_precompute(int enabled, uint32_t c) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (c != 0 && (c < 2 || c > 24)) return fail(H2B_ERR_ARG, "srs window must be 0 or in [2, 24]");
+    g->srs_precompute = enabled != 0;
+    g->srs_window = c;
     return H2B_OK;
 }
 int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n) {
@@ -893,6 +944,25 @@ int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out
     return leave(s, msm_run((const Fe *)d_coeffs, (const Affine *)d_bases, n, (Projective *)d_out, s));
 }
 
+int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    auto it = g->srs.find(srs);
+    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit: unknown SRS handle");
+    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit: bases.len() < size");  // commitment.rs:319/:363
+    if (!d_out || (n && !d_coeffs)) return fail(H2B_ERR_ARG, "commit: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    if (n == 0) return leave(s, msm_identity_out((Projective *)d_out, s));
+    const Srs &sr = it->second;
+    MsmRun run;
+    int rc = msm_begin(n, &run, s, &sr);
+    if (rc == H2B_OK) rc = msm_chunk(run, (const Fe *)d_coeffs, sr.table ? sr.table : sr.d, n, s, 0);
+    if (rc == H2B_OK) rc = msm_finish(run, (Projective *)d_out, s);
+    return leave(s, rc);
+}
+
 int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out[12]) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
@@ -924,6 +994,31 @@ int h2b_srs_register(const uint64_t *bases, size_t n, uint64_t *handle) {
         cudaFree(s.d);
         return fail(H2B_ERR_CUDA, "cudaMemcpy(srs)", e);
     }
+    // Static bases: precompute 2^(c*w) * P_i once so that every window of a commit feeds ONE bucket set
+    // (fewer, wider windows; no Horner).  Skipped when the table would not fit comfortably.
+    if (g->srs_precompute && n >= 1024) {
+        uint32_t c = srs_window_for(n), W = msm_windows_for(c);
+        size_t bytes = (size_t)W * n * sizeof(Affine), free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes <= free_b / 3 && (size_t)W * n < (1u << 31)) {
+            e = cudaMalloc(&s.table, bytes);
+            if (e == cudaSuccess) {
+                msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, s.table);
+                g->launches++;
+                e = cudaStreamSynchronize(g->stream);
+                if (e != cudaSuccess) {
+                    cudaFree(s.table);
+                    cudaFree(s.d);
+                    return fail(H2B_ERR_CUDA, "srs precompute", e);
+                }
+                s.c = c;
+                s.windows = W;
+            } else {
+                (void)cudaGetLastError();
+                s.table = nullptr;
+            }
+        }
+    }
     *handle = g->next_handle++;
     g->srs[*handle] = s;
     return H2B_OK;
@@ -936,6 +1031,7 @@ int h2b_srs_release(uint64_t handle) {
     CU(cudaSetDevice(g->device));
     CU(cudaStreamSynchronize(g->stream));
     cudaFree(it->second.d);
+    if (it->second.table) cudaFree(it->second.table);
     g->srs.erase(it);
     return H2B_OK;
 }
@@ -959,7 +1055,7 @@ int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]
     TRY(enter(g->stream));
     void *dout;
     TRY(get_buf(BUF_OUT, 96, &dout));
-    TRY(msm_run_pipelined(scalars, nullptr, it->second.d, n, (Projective *)dout));
+    TRY(msm_run_pipelined(scalars, nullptr, &it->second, n, (Projective *)dout));
     CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return leave(g->stream, H2B_OK);

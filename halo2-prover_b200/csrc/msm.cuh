@@ -37,6 +37,11 @@ struct MsmCfg {
     uint32_t slice;    // L: sorted entries per accumulation thread
     uint32_t lgrp;     // log2 of buckets per reduction group
     uint32_t half[8];  // sum over windows w < W-1 of 2^(c*w + c-1): turns unsigned windows into signed digits
+    // Precomputed-window mode (registered SRS): table[w * stride + i] = 2^(c*w) * P_i, so every
+    // window feeds ONE shared bucket set (bucket = |digit| - 1) and no Horner pass is needed.
+    uint32_t shared;   // 1: shared buckets over a precomputed table
+    uint32_t stride;   // points per window block of the table (the registered SRS length)
+    uint32_t ioff;     // index of this chunk's first point inside the SRS
 };
 
 // Signed digits without a sequential carry: with s' = s + half (one 256-bit addition),
@@ -82,7 +87,7 @@ msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg, uint32_t *__restri
             const uint32_t neg = d < 0;
             const uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
             enc = mag | (neg << 31);
-            atomicAdd(&counts[w * cfg.bpw + mag - 1], 1u);
+            atomicAdd(&counts[(cfg.shared ? 0u : w * cfg.bpw) + mag - 1], 1u);
         }
         digits[(size_t)w * cfg.n + i] = enc;
     }
@@ -99,8 +104,9 @@ msm_scatter_kernel(const uint32_t *__restrict__ digits, MsmCfg cfg, uint32_t *__
     const uint32_t enc = __ldg(&digits[(size_t)w * cfg.n + i]);
     if (enc == 0) return;
     const uint32_t mag = enc & 0x7fffffffu;
-    const uint32_t pos = atomicAdd(&cursor[w * cfg.bpw + mag - 1], 1u);
-    sorted[pos] = i | (enc & 0x80000000u);
+    const uint32_t pos = atomicAdd(&cursor[(cfg.shared ? 0u : w * cfg.bpw) + mag - 1], 1u);
+    const uint32_t idx = cfg.shared ? w * cfg.stride + cfg.ioff + i : i;
+    sorted[pos] = idx | (enc & 0x80000000u);
 }
 
 // Exclusive scans over the nb buckets in three small launches (block sums, scan of block sums,
@@ -470,6 +476,40 @@ msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *o
         store_fe(&out->x, j.x);
         store_fe(&out->y, j.y);
         store_fe(&out->z, j.z);
+    }
+}
+
+// table[w * n + i] = 2^(c*w) * bases[i] in affine form, w in [0, W): the one-time precomputation
+// behind the shared-bucket mode of a registered SRS (the bases of ParamsKZG are static).
+__global__ void __launch_bounds__(128)
+msm_precompute_kernel(const Affine *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W,
+                      Affine *__restrict__ table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine p = load_affine(&bases[i]);
+    store_fe(&table[i].x, p.x);
+    store_fe(&table[i].y, p.y);
+    const bool is_id = affine_is_identity(p);
+    XYZZ acc = xyzz_from_affine(p);
+#pragma unroll 1
+    for (uint32_t w = 1; w < W; w++) {
+        Affine r;
+        if (is_id) {
+            r.x = Fq::zero();
+            r.y = Fq::zero();
+        } else {
+#pragma unroll 1
+            for (uint32_t d = 0; d < c; d++) acc = xyzz_dbl_ni(acc);
+            const Fe t = Fq::inv(Fq::mul(acc.zz, acc.zzz));
+            r.x = Fq::mul(Fq::mul(acc.x, t), acc.zzz);  // X / ZZ
+            r.y = Fq::mul(Fq::mul(acc.y, t), acc.zz);   // Y / ZZZ
+            acc.x = r.x;                                 // renormalise: keeps the chain exact and short
+            acc.y = r.y;
+            acc.zz = Fq::one();
+            acc.zzz = Fq::one();
+        }
+        store_fe(&table[(size_t)w * n + i].x, r.x);
+        store_fe(&table[(size_t)w * n + i].y, r.y);
     }
 }
 

@@ -46,6 +46,14 @@ class ParamsKZG:
     def commit_lagrange(self, poly: np.ndarray, _blind=None) -> np.ndarray:
         return self._commit("g_lagrange", poly)
 
+    def dev_commit(self, coeffs_t, out_t, which: str = "g", stream=None) -> None:
+        """Device-resident commit: coeffs_t (n,4) int64 cuda tensor, out_t (12,) -- h2b_dev_commit."""
+        from .arithmetic import _ptr, _stream_ptr
+        size = coeffs_t.shape[0]
+        assert self.n >= size, "assert!(bases.len() >= size)"  # commitment.rs:319 / :363
+        _ffi.check(_ffi.lib().h2b_dev_commit(C.c_uint64(self._handles[which]), _ptr(coeffs_t), C.c_size_t(size),
+                                             _ptr(out_t), _stream_ptr(stream)))
+
     def device_bases(self, which: str = "g"):
         """(device pointer, length) of a registered base array."""
         p = C.c_void_p()

@@ -110,6 +110,9 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a);
 
 /* ---- device-resident variants (inputs/outputs already in HBM) ---------------------- */
 int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out /* 96 B */, void *stream);
+/* ParamsKZG::commit with the polynomial already in HBM: d_coeffs (n x 32 B) against bases[0..n] of a
+ * registered SRS (commitment.rs:319, :363); uses the SRS's precomputed window table when it has one. */
+int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out /* 96 B */, void *stream);
 /* Device address of a registered SRS (n x 64 bytes). */
 int h2b_srs_device_ptr(uint64_t srs, void **d_bases, size_t *n);
 int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *stream);
@@ -124,6 +127,10 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
 /* ---- tuning / introspection ------------------------------------------------------- */
 /* Override the MSM window (0 = automatic). */
 int h2b_set_msm_window(uint32_t c);
+/* h2b_srs_register precomputes 2^(c*w) * P_i for the static bases (default on) so that all windows of a
+ * commit share one bucket set; `c` overrides that table's window (0 = automatic).  Applies to SRS
+ * registered after the call. */
+int h2b_set_srs_precompute(int enabled, uint32_t c);
 /* Host-buffer MSM entry points (h2b_best_multiexp, h2b_commit) split inputs of at least `min_n`
  * points into `chunks` contiguous pieces so the H2D copy of a piece overlaps the bucket accumulation
  * of the previous one (default 4 pieces from 2^21 points). */

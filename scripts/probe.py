@@ -42,7 +42,8 @@ def main():
     import bn254
     gen = bn254.affine_to_array([bn254.G1_GENERATOR])[0]
     with torch.cuda.stream(s):
-        nmax = 1 << max(sizes + [4])
+        csizes = [int(x) for x in os.environ.get("PROBE_COMMIT", "").split(",") if x]
+        nmax = 1 << max(sizes + csizes + [4])
         sc_all = torch.from_numpy(rand_fr_np(nmax, 1).view(np.int64)).cuda()
         seeds = torch.from_numpy(rand_fr_np(nmax, 2).view(np.int64)).cuda()
         bases = torch.empty((nmax, 8), dtype=torch.int64, device="cuda")
@@ -75,6 +76,40 @@ def main():
                 print(f"MSM 2^{lg} c={cwin}: {ms:.3f} ms/step ({n / ms * 1e3:.3e} pts/s), accumulate {kms:.3f} ms", flush=True)
                 res[f"msm_{lg}_c{cwin}"] = {"ms": ms, "acc_ms": kms}
         _ffi.check(L.h2b_set_msm_window(0))
+        # commit against a registered SRS (precomputed window table, shared buckets), device-resident scalars
+        for lg in [int(x) for x in os.environ.get("PROBE_COMMIT", "").split(",") if x]:
+            n = 1 << lg
+            hb = bases[:n].cpu().numpy().view(np.uint64)
+            for cwin in [int(x) for x in os.environ.get("PROBE_SRS_C", "0").split(",")]:
+                _ffi.check(L.h2b_set_srs_precompute(1, cwin))
+                h = C.c_uint64(0)
+                t0 = time.time()
+                _ffi.check(L.h2b_srs_register(_ffi.u64p(hb), C.c_size_t(n), C.byref(h)))
+                treg = time.time() - t0
+                for _ in range(2):
+                    _ffi.check(L.h2b_dev_commit(h, C.c_void_p(sc_all.data_ptr()), C.c_size_t(n), C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(s.cuda_stream)))
+                s.synchronize()
+                _ffi.check(L.h2b_set_kernel_timing(1))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 3
+                e0.record(s)
+                for _ in range(reps):
+                    _ffi.check(L.h2b_dev_commit(h, C.c_void_p(sc_all.data_ptr()), C.c_size_t(n), C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(s.cuda_stream)))
+                e1.record(s)
+                s.synchronize()
+                tot, calls = C.c_double(), C.c_uint32()
+                _ffi.check(L.h2b_kernel_time_collect(C.byref(tot), C.byref(calls)))
+                _ffi.check(L.h2b_set_kernel_timing(0))
+                ms = e0.elapsed_time(e1) / reps
+                kms = tot.value / max(calls.value, 1)
+                print(f"COMMIT 2^{lg} srs_c={cwin}: {ms:.3f} ms/step ({n / ms * 1e3:.3e} pts/s), accumulate {kms:.3f} ms, "
+                      f"register {treg:.2f} s", flush=True)
+                res[f"commit_{lg}_c{cwin}"] = {"ms": ms, "acc_ms": kms, "register_s": treg}
+                _ffi.check(L.h2b_srs_release(h))
+            del hb
+        _ffi.check(L.h2b_set_srs_precompute(1, 0))
         del bases, seeds, sc_all
         import bn254 as o
         for k in [int(x) for x in os.environ.get("PROBE_NTT", "10,14,16,18,20,22,24").split(",") if x not in ("", "none")]:

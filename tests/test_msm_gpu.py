@@ -118,6 +118,64 @@ def test_commit_against_registered_srs(h2b, spec, href):
     params.release()
 
 
+@pytest.mark.parametrize("srs_c", [0, 7, 13, 16])
+def test_commit_precomputed_window_table(h2b, spec, href, srs_c):
+    """Registered bases get a table 2^(c*w) * P_i so all windows of a commit share one bucket set; the result
+    must equal best_multiexp on the plain bases for every table window, with identity bases, repeated
+    scalars, r-1 / 0 / 1 scalars, for a prefix of the SRS, and with the table disabled."""
+    import ctypes as C
+    from halo2_prover_b200 import _ffi
+    n = 1 << 12
+    g = href.random_g1(n, 61)
+    g[5::97] = 0  # identity bases inside the SRS
+    poly = href.random_fr(n, 62)
+    poly[::7] = poly[3]
+    poly[1] = spec.fr_array([spec.R_MOD - 1])[0]
+    poly[2] = 0
+    poly[4] = spec.fr_array([1])[0]
+    want = _affine(href, href.best_multiexp(poly, g))
+    want_short = _affine(href, href.best_multiexp(poly[:1500].copy(), g[:1500].copy()))
+    try:
+        _ffi.check(_ffi.lib().h2b_set_srs_precompute(1, srs_c))
+        params = h2b.ParamsKZG(12, g)
+        assert (_affine(href, params.commit(poly)) == want).all()
+        assert (_affine(href, params.commit(poly[:1500].copy())) == want_short).all()
+        params.release()
+        _ffi.check(_ffi.lib().h2b_set_srs_precompute(0, 0))
+        params = h2b.ParamsKZG(12, g)
+        assert (_affine(href, params.commit(poly)) == want).all()
+        params.release()
+    finally:
+        _ffi.check(_ffi.lib().h2b_set_srs_precompute(1, 0))
+
+
+def test_dev_commit_matches_best_multiexp_2p18(h2b, spec, href):
+    """Device-resident commit (h2b_dev_commit) over a 2^18-point SRS == the oracle's best_multiexp."""
+    import ctypes as C
+    import torch
+    from halo2_prover_b200 import _ffi
+    n = 1 << 18
+    g = np.tile(href.random_g1(1 << 14, 71), (n >> 14, 1))
+    poly = href.random_fr(n, 72)
+    want = _affine(href, href.best_multiexp(poly, g))
+    params = h2b.ParamsKZG(18, g)
+    d_poly = torch.from_numpy(poly.view(np.int64)).cuda()
+    out = torch.empty(12, dtype=torch.int64, device="cuda")
+    params.dev_commit(d_poly, out)          # torch's default stream
+    torch.cuda.current_stream().synchronize()
+    assert (_affine(href, out.cpu().numpy().view(np.uint64)) == want).all()
+    out.zero_()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    params.dev_commit(d_poly[: n // 2], out, stream=s)   # a prefix of the SRS, caller's stream
+    s.synchronize()
+    want = _affine(href, href.best_multiexp(poly[: n // 2].copy(), g[: n // 2].copy()))
+    assert (_affine(href, out.cpu().numpy().view(np.uint64)) == want).all()
+    want = _affine(href, href.best_multiexp(poly, g))
+    assert (_affine(href, params.commit(poly)) == want).all()
+    params.release()
+
+
 def test_commit_is_p_of_s_times_g(h2b, spec, href):
     """Synthetic SRS with known s: commit(p) == [p(s)] G."""
     k, s = 6, 0x1234567
