@@ -334,15 +334,33 @@ def bench_proof_replay(args, h2b, _ffi) -> dict:
     cols = [rand_fr_np(n, 300 + i) for i in range(7)]
     ext_in = rand_fr_np(1 << d.extended_k, 399)
 
-    def gpu_once():
+    split = {"msm": 0.0, "lagrange_to_coeff": 0.0, "coeff_to_extended": 0.0, "extended_to_coeff": 0.0}
+
+    def gpu_once(batched=False):
         outs = []
-        for i in range(16):
-            outs.append(params.commit_lagrange(cols[i % 7]) if i < 8 else params.commit(cols[i % 7]))
+        t = time.perf_counter()
+        if batched:
+            # create_proof commits the advice columns, then the permutation / lookup products, then the h pieces:
+            # independent commits of one phase go down as one h2b_commit_many call
+            outs.extend(params.commit_lagrange_many([cols[i % 7] for i in range(8)]))
+            outs.extend(params.commit_many([cols[i % 7] for i in range(8, 16)]))
+        else:
+            for i in range(16):
+                outs.append(params.commit_lagrange(cols[i % 7]) if i < 8 else params.commit(cols[i % 7]))
+        t1 = time.perf_counter()
+        split["msm"] += t1 - t
+        scratch = [c.copy() for c in cols]
+        t = time.perf_counter()
         for i in range(7):
-            d.lagrange_to_coeff(cols[i].copy())
+            d.lagrange_to_coeff(scratch[i])
+        t1 = time.perf_counter()
+        split["lagrange_to_coeff"] += t1 - t
         for i in range(7):
             d.coeff_to_extended(cols[i])
+        t = time.perf_counter()
+        split["coeff_to_extended"] += t - t1
         d.extended_to_coeff(ext_in)
+        split["extended_to_coeff"] += time.perf_counter() - t
         return outs
 
     def cpu_once():
@@ -357,11 +375,21 @@ def bench_proof_replay(args, h2b, _ffi) -> dict:
         return outs
 
     gpu_once()
-    t0 = time.perf_counter()
+    for key in split:
+        split[key] = 0.0
     reps = 3
     for _ in range(reps):
         go = gpu_once()
-    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    gpu_ms = sum(split.values()) / reps * 1e3
+    by_call = {k2: v / reps * 1e3 for k2, v in split.items()}
+    gpu_once(batched=True)
+    for key in split:
+        split[key] = 0.0
+    for _ in range(reps):
+        gb = gpu_once(batched=True)
+    gpu_batched_ms = sum(split.values()) / reps * 1e3
+    by_call_batched = {k2: v / reps * 1e3 for k2, v in split.items()}
+    same_b = all((h2ref.g1_to_affine(a) == h2ref.g1_to_affine(b)).all() for a, b in zip(go, gb))
     t0 = time.perf_counter()
     co = cpu_once()
     cpu_ms = (time.perf_counter() - t0) * 1e3
@@ -370,7 +398,8 @@ def bench_proof_replay(args, h2b, _ffi) -> dict:
     return {"what": "MSM/NTT calls of one Poseidon-shaped proof (hot path only, host buffers, sequential calls)",
             "k": k, "extended_k": int(d.extended_k), "calls": {"msm": 16, "lagrange_to_coeff": 7, "coeff_to_extended": 7,
                                                             "extended_to_coeff": 1},
-            "gpu_ms": gpu_ms, "cpu_ms": cpu_ms, "cpu_threads": threads, "commitments_equal": bool(same)}
+            "gpu_ms": gpu_ms, "gpu_ms_by_call": by_call, "gpu_batched_ms": gpu_batched_ms,
+            "gpu_batched_ms_by_call": by_call_batched, "batched_equals_single": bool(same_b), "cpu_ms": cpu_ms, "cpu_threads": threads, "commitments_equal": bool(same)}
 
 
 def bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, imad_gops) -> dict:

@@ -8,6 +8,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -182,9 +184,10 @@ uint32_t msm_windows_for(uint32_t c) {
 
 // Window geometry.  srs == nullptr: independent windows (one bucket set per window, Horner at the
 // end).  srs with a precomputed table: its c, all windows share one bucket set.
-MsmCfg msm_plan(size_t n, const Srs *srs = nullptr) {
+MsmCfg msm_plan(size_t n, const Srs *srs = nullptr, uint32_t cols = 1) {
     MsmCfg cfg{};
     cfg.n = (uint32_t)n;
+    cfg.cols = cols;
     uint32_t c;
     if (srs && srs->table) {
         c = srs->c;
@@ -206,7 +209,7 @@ MsmCfg msm_plan(size_t n, const Srs *srs = nullptr) {
     uint32_t W = msm_windows_for(c);
     cfg.windows = W;
     cfg.bpw = 1u << (c - 1);
-    cfg.nb = cfg.shared ? cfg.bpw : W * cfg.bpw;
+    cfg.nb = cfg.shared ? cols * cfg.bpw : W * cfg.bpw;
     for (uint32_t w = 0; w + 1 < W; w++) {
         uint32_t bit = c * w + c - 1;
         cfg.half[bit >> 5] |= 1u << (bit & 31);
@@ -249,9 +252,9 @@ int msm_identity_out(Projective *d_out, cudaStream_t s) {
     return H2B_OK;
 }
 
-int msm_begin(size_t n_total, MsmRun *run, cudaStream_t s, const Srs *srs = nullptr) {
+int msm_begin(size_t n_total, MsmRun *run, cudaStream_t s, const Srs *srs = nullptr, uint32_t cols = 1) {
     if (n_total > (1u << 30)) return fail(H2B_ERR_ARG, "msm: n > 2^30 not supported");
-    run->cfg = msm_plan(n_total, srs);
+    run->cfg = msm_plan(n_total, srs, cols);
     TRY(get_buf(BUF_BUCKETS, (size_t)run->cfg.nb * sizeof(XYZZ), (void **)&run->buckets));
     CU(cudaMemsetAsync(run->buckets, 0, (size_t)run->cfg.nb * sizeof(XYZZ), s));  // all-zero XYZZ = identity
     return H2B_OK;
@@ -264,7 +267,7 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     MsmCfg cfg = run.cfg;
     cfg.n = (uint32_t)m;
     cfg.ioff = (uint32_t)ioff;
-    size_t entries = m * cfg.windows;
+    size_t entries = m * cfg.cols * cfg.windows;
     uint32_t L = 512;  // slice: enough slices to fill the GPU several times over, at most 512 entries
     while (L > 16 && entries / L < (size_t)g->sm_count * 2048) L >>= 1;
     cfg.slice = L;
@@ -297,7 +300,7 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
     CU(cudaMemsetAsync(heavy, 0, 4, s));
     CU(cudaMemsetAsync(tail_j, 0xff, max_slices * 4, s));
-    uint32_t nblk = (uint32_t)((m + 255) / 256);
+    uint32_t nblk = (uint32_t)((m * cfg.cols + 255) / 256);
     msm_digits_kernel<<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, digits);
     LAUNCHED();
     uint32_t ipt = (cfg.nb + 1024 * 1024 - 1) / (1024 * 1024);
@@ -330,10 +333,12 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
 
 int msm_finish(const MsmRun &run, Projective *d_out, cudaStream_t s) {
     MsmCfg cfg = run.cfg;
-    if (cfg.shared) cfg.windows = 1;  // one bucket set: sum_k k * B_k is the result, no Horner
+    if (cfg.shared) cfg.windows = cfg.cols;  // one bucket set per column: sum_k k * B_k is the result, no Horner
     XYZZ *windows, *wpart;
     uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
     uint32_t rthreads = G < 256 ? G : 256;      // power of two
+    // few groups in total (small MSMs): narrower blocks put the serial group chains on different SMs
+    while (rthreads > 32 && (uint64_t)(G / rthreads) * cfg.windows < 2u * g->sm_count) rthreads >>= 1;
     uint32_t per_window = G / rthreads;         // blocks (= partials) per window
     TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
     TRY(get_buf(BUF_WPART, (size_t)cfg.windows * per_window * sizeof(XYZZ), (void **)&wpart));
@@ -341,6 +346,11 @@ int msm_finish(const MsmRun &run, Projective *d_out, cudaStream_t s) {
     LAUNCHED();
     msm_window_fold_kernel<<<cfg.windows, 32, 0, s>>>(wpart, per_window, windows);
     LAUNCHED();
+    if (cfg.shared && cfg.cols > 1) {
+        msm_batch_out_kernel<<<(cfg.cols + 31) / 32, 32, 0, s>>>(windows, cfg.cols, d_out);
+        LAUNCHED();
+        return H2B_OK;
+    }
     msm_final_kernel<<<1, 32, 0, s>>>(windows, cfg, d_out);
     LAUNCHED();
     return H2B_OK;
@@ -963,6 +973,72 @@ int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out, vo
     return leave(s, rc);
 }
 
+// m polynomials of n scalars each (device, one after the other) against bases[0..n] of one SRS.  With a window
+// table every column gets its own bucket set inside ONE pass of the kernels (columns take the place of
+// windows in the reduction), so the fixed latency of a small MSM is paid once per batch, not per column.
+int commit_many_device(const Srs &sr, const Fe *d_scalars, size_t n, size_t m, Projective *d_out, cudaStream_t s) {
+    if (m == 0) return H2B_OK;
+    if (n == 0) {
+        for (size_t q = 0; q < m; q++) TRY(msm_identity_out(d_out + q, s));
+        return H2B_OK;
+    }
+    if (!sr.table) {  // no table: one MSM per column
+        for (size_t q = 0; q < m; q++) TRY(msm_run(d_scalars + q * n, sr.d, n, d_out + q, s));
+        return H2B_OK;
+    }
+    // bound one pass: sorted entries < 2^28 and at most 1 GiB of buckets
+    const uint64_t per_col_entries = (uint64_t)n * sr.windows, per_col_buckets = (uint64_t)1 << (sr.c - 1);
+    size_t step = m;
+    while (step > 1 && (step * per_col_entries > (1ull << 28) || step * per_col_buckets * sizeof(XYZZ) > (1ull << 30)))
+        step = (step + 1) / 2;
+    for (size_t q0 = 0; q0 < m; q0 += step) {
+        const size_t cols = std::min(step, m - q0);
+        MsmRun run;
+        TRY(msm_begin(n, &run, s, &sr, (uint32_t)cols));
+        TRY(msm_chunk(run, d_scalars + q0 * n, sr.table, n, s, 0));
+        TRY(msm_finish(run, d_out + q0, s));
+    }
+    return H2B_OK;
+}
+
+int h2b_dev_commit_many(uint64_t srs, const void *d_coeffs, size_t n, size_t m, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    auto it = g->srs.find(srs);
+    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit_many: unknown SRS handle");
+    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit_many: bases.len() < size");  // commitment.rs:319/:363
+    if (m && (!d_out || (n && !d_coeffs))) return fail(H2B_ERR_ARG, "commit_many: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, commit_many_device(it->second, (const Fe *)d_coeffs, n, m, (Projective *)d_out, s));
+}
+
+int h2b_commit_many(uint64_t srs, const uint64_t *const *polys, size_t n, size_t m, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    auto it = g->srs.find(srs);
+    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit_many: unknown SRS handle");
+    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit_many: bases.len() < size");  // commitment.rs:319/:363
+    if (m == 0) return H2B_OK;
+    if (!out || !polys) return fail(H2B_ERR_ARG, "commit_many: null pointer");
+    for (size_t q = 0; q < m && n; q++)
+        if (!polys[q]) return fail(H2B_ERR_ARG, "commit_many: null column");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = g->stream;
+    TRY(enter(s));
+    Fe *ds = nullptr;
+    void *dout;
+    if (n) TRY(get_buf(BUF_SCALARS, m * n * sizeof(Fe), (void **)&ds));
+    TRY(get_buf(BUF_OUT, m * sizeof(Projective), &dout));
+    for (size_t q = 0; q < m && n; q++)
+        CU(cudaMemcpyAsync(ds + q * n, polys[q], n * sizeof(Fe), cudaMemcpyHostToDevice, s));
+    TRY(commit_many_device(it->second, ds, n, m, (Projective *)dout, s));
+    CU(cudaMemcpyAsync(out, dout, m * sizeof(Projective), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return leave(s, H2B_OK);
+}
+
 int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out[12]) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
@@ -996,7 +1072,7 @@ int h2b_srs_register(const uint64_t *bases, size_t n, uint64_t *handle) {
     }
     // Static bases: precompute 2^(c*w) * P_i once so that every window of a commit feeds ONE bucket set
     // (fewer, wider windows; no Horner).  Skipped when the table would not fit comfortably.
-    if (g->srs_precompute && n >= 1024) {
+    if (g->srs_precompute && n >= 2) {
         uint32_t c = srs_window_for(n), W = msm_windows_for(c);
         size_t bytes = (size_t)W * n * sizeof(Affine), free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);

@@ -42,6 +42,9 @@ struct MsmCfg {
     uint32_t shared;   // 1: shared buckets over a precomputed table
     uint32_t stride;   // points per window block of the table (the registered SRS length)
     uint32_t ioff;     // index of this chunk's first point inside the SRS
+    // Batched commit (shared mode only): `cols` polynomials of n scalars each, laid out one after the
+    // other, against the same bases; column q owns buckets [q * bpw, (q + 1) * bpw).
+    uint32_t cols;     // >= 1
 };
 
 // Signed digits without a sequential carry: with s' = s + half (one 256-bit addition),
@@ -63,8 +66,10 @@ H2B_DI int32_t digit_at(const uint32_t (&sp)[9], uint32_t w, const MsmCfg &cfg) 
 __global__ void __launch_bounds__(256)
 msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg, uint32_t *__restrict__ counts,
                   uint32_t *__restrict__ digits) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cfg.n) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // column-major: i = column * n + point
+    const uint32_t total = cfg.n * cfg.cols;
+    if (i >= total) return;
+    const uint32_t colbase = cfg.cols > 1 ? (i / cfg.n) * cfg.bpw : 0u;
     Fe s = Fr::from_mont(load_fe_ro(&scalars[i]));
     uint32_t l[9];
     asm("add.cc.u32 %0, %8, %16;\n\t"
@@ -87,9 +92,9 @@ msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg, uint32_t *__restri
             const uint32_t neg = d < 0;
             const uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
             enc = mag | (neg << 31);
-            atomicAdd(&counts[(cfg.shared ? 0u : w * cfg.bpw) + mag - 1], 1u);
+            atomicAdd(&counts[(cfg.shared ? colbase : w * cfg.bpw) + mag - 1], 1u);
         }
-        digits[(size_t)w * cfg.n + i] = enc;
+        digits[(size_t)w * total + i] = enc;
     }
 }
 
@@ -100,12 +105,14 @@ msm_scatter_kernel(const uint32_t *__restrict__ digits, MsmCfg cfg, uint32_t *__
                    uint32_t *__restrict__ sorted) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t w = blockIdx.y;
-    if (i >= cfg.n) return;
-    const uint32_t enc = __ldg(&digits[(size_t)w * cfg.n + i]);
+    const uint32_t total = cfg.n * cfg.cols;
+    if (i >= total) return;
+    const uint32_t enc = __ldg(&digits[(size_t)w * total + i]);
     if (enc == 0) return;
     const uint32_t mag = enc & 0x7fffffffu;
-    const uint32_t pos = atomicAdd(&cursor[(cfg.shared ? 0u : w * cfg.bpw) + mag - 1], 1u);
-    const uint32_t idx = cfg.shared ? w * cfg.stride + cfg.ioff + i : i;
+    const uint32_t col = cfg.cols > 1 ? i / cfg.n : 0u;
+    const uint32_t pos = atomicAdd(&cursor[(cfg.shared ? col * cfg.bpw : w * cfg.bpw) + mag - 1], 1u);
+    const uint32_t idx = cfg.shared ? w * cfg.stride + cfg.ioff + (i - col * cfg.n) : i;
     sorted[pos] = idx | (enc & 0x80000000u);
 }
 
@@ -477,6 +484,17 @@ msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *o
         store_fe(&out->y, j.y);
         store_fe(&out->z, j.z);
     }
+}
+
+// Batched commit: column q's result is its single window sum (shared buckets, no Horner).
+__global__ void __launch_bounds__(32)
+msm_batch_out_kernel(const XYZZ *__restrict__ window_sums, uint32_t cols, Projective *__restrict__ out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= cols) return;
+    const Projective j = xyzz_to_projective(load_xyzz(&window_sums[q]));
+    store_fe(&out[q].x, j.x);
+    store_fe(&out[q].y, j.y);
+    store_fe(&out[q].z, j.z);
 }
 
 // table[w * n + i] = 2^(c*w) * bases[i] in affine form, w in [0, W): the one-time precomputation

@@ -46,6 +46,27 @@ class ParamsKZG:
     def commit_lagrange(self, poly: np.ndarray, _blind=None) -> np.ndarray:
         return self._commit("g_lagrange", poly)
 
+    def _commit_many(self, which: str, polys) -> np.ndarray:
+        polys = [_ffi.as_u64(p, 4) for p in polys]
+        m = len(polys)
+        out = np.zeros((m, 12), dtype=np.uint64)
+        if m == 0:
+            return out
+        size = polys[0].shape[0]
+        assert all(p.shape[0] == size for p in polys), "commit_many: columns of one batch have one length"
+        assert self.n >= size, "assert!(bases.len() >= size)"  # commitment.rs:319 / :363
+        ptrs = (C.POINTER(C.c_uint64) * m)(*[_ffi.u64p(p) for p in polys])
+        _ffi.check(_ffi.lib().h2b_commit_many(C.c_uint64(self._handles[which]), ptrs, C.c_size_t(size), C.c_size_t(m),
+                                              _ffi.u64p(out)))
+        return out
+
+    def commit_many(self, polys) -> np.ndarray:
+        """[commit(p) for p in polys] in one pass; (m, 12) uint64."""
+        return self._commit_many("g", polys)
+
+    def commit_lagrange_many(self, polys) -> np.ndarray:
+        return self._commit_many("g_lagrange", polys)
+
     def dev_commit(self, coeffs_t, out_t, which: str = "g", stream=None) -> None:
         """Device-resident commit: coeffs_t (n,4) int64 cuda tensor, out_t (12,) -- h2b_dev_commit."""
         from .arithmetic import _ptr, _stream_ptr

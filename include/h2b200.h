@@ -108,11 +108,20 @@ int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out
 /* EvaluationDomain::divide_by_vanishing_poly: a[i] *= t_evaluations[i % n_t], 2^extended_k, in place. */
 int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a);
 
+/* m polynomials of n scalars each committed against bases[0..n] of ONE registered SRS in a single pass
+ * (the A advice columns, the permutation products or the h pieces of create_proof, which upstream
+ * commits one by one: plonk/prover.rs advice `.map(|poly| params.commit_lagrange(poly, blind))`).
+ * polys[q] points at column q (n x 4 u64, host); out receives m x 12 u64.  Results are identical
+ * to m calls of h2b_commit; the fixed latency of a small MSM is paid once per batch. */
+int h2b_commit_many(uint64_t srs, const uint64_t *const *polys, size_t n, size_t m, uint64_t *out);
+
 /* ---- device-resident variants (inputs/outputs already in HBM) ---------------------- */
 int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out /* 96 B */, void *stream);
 /* ParamsKZG::commit with the polynomial already in HBM: d_coeffs (n x 32 B) against bases[0..n] of a
  * registered SRS (commitment.rs:319, :363); uses the SRS's precomputed window table when it has one. */
 int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out /* 96 B */, void *stream);
+/* h2b_commit_many with the m columns already in HBM, one after the other (m x n x 32 B); d_out: m x 96 B. */
+int h2b_dev_commit_many(uint64_t srs, const void *d_coeffs, size_t n, size_t m, void *d_out, void *stream);
 /* Device address of a registered SRS (n x 64 bytes). */
 int h2b_srs_device_ptr(uint64_t srs, void **d_bases, size_t *n);
 int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *stream);

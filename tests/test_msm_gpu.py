@@ -176,6 +176,31 @@ def test_dev_commit_matches_best_multiexp_2p18(h2b, spec, href):
     params.release()
 
 
+@pytest.mark.parametrize("k,m", [(4, 3), (10, 9), (13, 5)])
+def test_commit_many_equals_single_commits(h2b, spec, href, k, m):
+    """h2b_commit_many (every column its own bucket set inside one pass) == m x h2b_commit == the oracle,
+    including an all-zero column, a column of one repeated scalar and identity bases."""
+    n = 1 << k
+    g = href.random_g1(n, 80 + k)
+    if n > 8:
+        g[3::17] = 0
+    cols = [href.random_fr(n, 90 + q) for q in range(m)]
+    cols[1][:] = 0
+    cols[2][:] = cols[2][0]
+    params = h2b.ParamsKZG(k, g, g)
+    got = params.commit_many(cols)
+    for q in range(m):
+        want = _affine(href, href.best_multiexp(cols[q], g))
+        assert (_affine(href, got[q]) == want).all(), q
+        assert (_affine(href, params.commit(cols[q])) == want).all(), q
+    short = [c[: n // 2 + 1].copy() for c in cols[:2]]
+    got = params.commit_lagrange_many(short)
+    for q in range(2):
+        assert (_affine(href, got[q]) == _affine(href, href.best_multiexp(short[q], g[: n // 2 + 1].copy()))).all()
+    assert params.commit_many([]).shape == (0, 12)
+    params.release()
+
+
 def test_commit_is_p_of_s_times_g(h2b, spec, href):
     """Synthetic SRS with known s: commit(p) == [p(s)] G."""
     k, s = 6, 0x1234567
