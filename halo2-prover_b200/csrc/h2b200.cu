@@ -456,7 +456,7 @@ int get_twiddles(const uint64_t omega[4], uint32_t log_n, cudaStream_t s, const 
 
 template <int S, int C, int NT>
 int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log_ns, bool last,
-                const NttIo &io, cudaStream_t s) {
+                const NttIo &io, cudaStream_t s, uint32_t batch) {
     constexpr int R = 1 << S;
     size_t smem = ((size_t)2 * R * C + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
     static bool attr_set = false;
@@ -468,7 +468,7 @@ int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log
     uint32_t M = 1u << (log_n - S);
     uint32_t blocks = M / C;
     if (blocks == 0) return fail(H2B_ERR_ARG, "ntt: tile wider than the pass");
-    ntt_pass_kernel<S, C, NT><<<blocks, NT, smem, s>>>(in, out, W, log_n, log_ns, last ? 1u : 0u, io);
+    ntt_pass_kernel<S, C, NT><<<dim3(blocks, batch), NT, smem, s>>>(in, out, W, log_n, log_ns, last ? 1u : 0u, io);
     LAUNCHED();
     return H2B_OK;
 }
@@ -476,47 +476,47 @@ int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log
 uint32_t g_ntt_tile_log = 10;  // log2 elements per multi-pass tile (8, 9 or 10); 10 measured best on B200
 
 int dispatch_pass(uint32_t S, bool single, const Fe *in, Fe *out, const Fe *W, uint32_t log_n,
-                  uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s) {
+                  uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s, uint32_t batch) {
     // threads per block = tile elements / 8 (one radix-8 group per thread and round)
     if (!single && g_ntt_tile_log == 9) {
         switch (S) {
-            case 5: return launch_pass<5, 16, 64>(in, out, W, log_n, log_ns, last, io, s);
-            case 6: return launch_pass<6, 8, 64>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 4, 64>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 2, 64>(in, out, W, log_n, log_ns, last, io, s);
-            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s);
+            case 5: return launch_pass<5, 16, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 6: return launch_pass<6, 8, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 7: return launch_pass<7, 4, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 8: return launch_pass<8, 2, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
         }
     }
     if (!single && g_ntt_tile_log == 10) {
         switch (S) {
-            case 5: return launch_pass<5, 32, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 6: return launch_pass<6, 16, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 8, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 4, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 9: return launch_pass<9, 2, 128>(in, out, W, log_n, log_ns, last, io, s);
-            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 5: return launch_pass<5, 32, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 6: return launch_pass<6, 16, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 7: return launch_pass<7, 8, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 8: return launch_pass<8, 4, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 9: return launch_pass<9, 2, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
         }
     }
     if (!single && g_ntt_tile_log == 8) {
         switch (S) {
-            case 5: return launch_pass<5, 8, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 6: return launch_pass<6, 4, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 2, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
+            case 5: return launch_pass<5, 8, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 6: return launch_pass<6, 4, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 7: return launch_pass<7, 2, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
         }
     }
     if (single) {
         switch (S) {
-            case 1: return launch_pass<1, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 2: return launch_pass<2, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 3: return launch_pass<3, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 4: return launch_pass<4, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 5: return launch_pass<5, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 6: return launch_pass<6, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 7: return launch_pass<7, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s);
-            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s);
-            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s);
+            case 1: return launch_pass<1, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 2: return launch_pass<2, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 3: return launch_pass<3, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 4: return launch_pass<4, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 5: return launch_pass<5, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 6: return launch_pass<6, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 7: return launch_pass<7, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
         }
     }
     return fail(H2B_ERR_ARG, "ntt: unsupported radix / tile configuration");
@@ -527,9 +527,19 @@ uint32_t g_ntt_max_radix = 10;  // two passes up to 2^20, three up to 2^28 (meas
 // Transform `src` (n_in valid elements of a 2^log_n domain) into `dst`; `dst` may equal `src`.
 // dst_full: `dst` holds 2^log_n elements and may carry intermediate passes; otherwise (truncated
 // output) intermediates stay in library scratch and only the last pass touches `dst`.
+// batch > 1: `batch` independent transforms, transform b at src + b * io.bin / dst + b * io.bout.
 int ntt_run(const Fe *src, Fe *dst, uint32_t log_n, const uint64_t omega[4], NttIo io, cudaStream_t s,
-            bool dst_full = true) {
+            bool dst_full = true, uint32_t batch = 1) {
     if (log_n > 28) return fail(H2B_ERR_ARG, "ntt: log_n > 28 (Fr::S)");
+    if (batch == 0) return H2B_OK;
+    if (log_n == 0 && batch > 1) {
+        for (uint32_t b = 0; b < batch; b++) {
+            NttIo one = io;
+            one.bin = one.bout = 0;
+            TRY(ntt_run(src + (size_t)b * io.bin, dst + (size_t)b * io.bout, 0, omega, one, s, dst_full, 1));
+        }
+        return H2B_OK;
+    }
     if (log_n == 0) {
         // length-1 transform is the identity; only the fused scalings remain (index 0: pro is a no-op)
         if (io.n_out == 0) return H2B_OK;
@@ -558,19 +568,25 @@ int ntt_run(const Fe *src, Fe *dst, uint32_t log_n, const uint64_t omega[4], Ntt
         for (uint32_t i = 0; i < P; i++) radix[i] = base + (i < rem ? 1 : 0);
     }
     Fe *tmp = nullptr, *tmp2 = dst;
-    if (P > 1) TRY(get_buf(BUF_NTT_T, ((size_t)1 << log_n) * sizeof(Fe), (void **)&tmp));
-    if (P > 2 && !dst_full) TRY(get_buf(BUF_NTT_T2, ((size_t)1 << log_n) * sizeof(Fe), (void **)&tmp2));
+    const uint32_t N = 1u << log_n;
+    uint32_t tmp2_stride = io.bout;
+    if (P > 1) TRY(get_buf(BUF_NTT_T, (size_t)batch * N * sizeof(Fe), (void **)&tmp));
+    if (P > 2 && !dst_full) {
+        TRY(get_buf(BUF_NTT_T2, (size_t)batch * N * sizeof(Fe), (void **)&tmp2));
+        tmp2_stride = N;
+    }
     time_begin(s);
     const Fe *cur = src;
-    uint32_t log_ns = 0;
+    uint32_t log_ns = 0, cur_stride = io.bin;
     for (uint32_t i = 0; i < P; i++) {
         bool last = (i + 1 == P);
         Fe *to = last ? dst : ((i & 1) == 0 ? tmp : tmp2);
         NttIo pio = io;
-        if (i != 0) { pio.pro = 0; pio.n_in = 1u << log_n; }
-        if (!last) { pio.epi = 0; pio.n_out = 1u << log_n; }
-        TRY(dispatch_pass(radix[i], single, cur, to, W, log_n, log_ns, last, pio, s));
+        if (i != 0) { pio.pro = 0; pio.n_in = 1u << log_n; pio.bin = cur_stride; }
+        if (!last) { pio.epi = 0; pio.n_out = 1u << log_n; pio.bout = (to == tmp) ? N : tmp2_stride; }
+        TRY(dispatch_pass(radix[i], single, cur, to, W, log_n, log_ns, last, pio, s, batch));
         cur = to;
+        cur_stride = pio.bout;
         log_ns += radix[i];
     }
     time_end(s);
@@ -701,19 +717,24 @@ int check_domain(const h2b_domain *d) {
     return H2B_OK;
 }
 
-int dev_lagrange_to_coeff(const h2b_domain *d, Fe *a, cudaStream_t s) {
+// batch columns lie one after the other: a + b * 2^k
+int dev_lagrange_to_coeff(const h2b_domain *d, Fe *a, cudaStream_t s, uint32_t batch = 1) {
     NttIo io = io_plain(d->k);
     io.epi = 1;
     for (int i = 0; i < 3; i++) memcpy(&io.epi_c[i], d->ifft_divisor, 32);
-    return ntt_run(a, a, d->k, d->omega_inv, io, s);
+    io.bin = io.bout = 1u << d->k;
+    return ntt_run(a, a, d->k, d->omega_inv, io, s, true, batch);
 }
-int dev_coeff_to_extended(const h2b_domain *d, const Fe *in, Fe *out, cudaStream_t s) {
+// batch: in + b * 2^k -> out + b * 2^extended_k
+int dev_coeff_to_extended(const h2b_domain *d, const Fe *in, Fe *out, cudaStream_t s, uint32_t batch = 1) {
     NttIo io = io_plain(d->extended_k);
     io.n_in = 1u << d->k;
     io.pro = 1;
     memcpy(&io.pro_c[1], d->g_coset, 32);      // i % 3 == 1 -> zeta
     memcpy(&io.pro_c[2], d->g_coset_inv, 32);  // i % 3 == 2 -> zeta^2
-    return ntt_run(in, out, d->extended_k, d->extended_omega, io, s);
+    io.bin = 1u << d->k;
+    io.bout = 1u << d->extended_k;
+    return ntt_run(in, out, d->extended_k, d->extended_omega, io, s, true, batch);
 }
 int dev_extended_to_coeff(const h2b_domain *d, const Fe *in, Fe *out, cudaStream_t s) {
     // ifft with extended_omega_inv; the last pass multiplies by 1/2^ext_k * {1, zeta^2, zeta}[i % 3]
@@ -1260,6 +1281,83 @@ int h2b_coeff_to_extended(const h2b_domain *d, const uint64_t *in, uint64_t *out
     CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return leave(g->stream, H2B_OK);
+}
+// Batched column transforms (create_proof runs lagrange_to_coeff over every advice / instance / product
+// column and coeff_to_extended over every column inside evaluate_h, one call each): the
+// columns are copied in one after the other, transformed by ONE launch per pass (gridDim.y = columns),
+// and copied back.  Sub-batches keep the device staging below 1 GiB.
+int h2b_lagrange_to_coeff_many(const h2b_domain *d, uint64_t *const *cols, size_t m) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (m == 0) return H2B_OK;
+    if (!cols) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: null pointer");
+    for (size_t q = 0; q < m; q++)
+        if (!cols[q]) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: null column");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = g->stream;
+    TRY(enter(s));
+    const size_t n = (size_t)1 << d->k, bytes = n * 32;
+    size_t step = std::max<size_t>(1, std::min<size_t>(m, ((size_t)1 << 30) / bytes));
+    for (size_t q0 = 0; q0 < m; q0 += step) {
+        const size_t cnt = std::min(step, m - q0);
+        Fe *da;
+        TRY(get_buf(BUF_NTT_A, cnt * bytes, (void **)&da));
+        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(da + q * n, cols[q0 + q], bytes, cudaMemcpyHostToDevice, s));
+        TRY(dev_lagrange_to_coeff(d, da, s, (uint32_t)cnt));
+        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(cols[q0 + q], da + q * n, bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return leave(s, H2B_OK);
+}
+int h2b_coeff_to_extended_many(const h2b_domain *d, const uint64_t *const *in, uint64_t *const *out, size_t m) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (m == 0) return H2B_OK;
+    if (!in || !out) return fail(H2B_ERR_ARG, "coeff_to_extended_many: null pointer");
+    for (size_t q = 0; q < m; q++)
+        if (!in[q] || !out[q]) return fail(H2B_ERR_ARG, "coeff_to_extended_many: null column");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = g->stream;
+    TRY(enter(s));
+    const size_t n = (size_t)1 << d->k, en = (size_t)1 << d->extended_k;
+    size_t step = std::max<size_t>(1, std::min<size_t>(m, ((size_t)1 << 30) / (en * 32)));
+    for (size_t q0 = 0; q0 < m; q0 += step) {
+        const size_t cnt = std::min(step, m - q0);
+        Fe *din, *dout;
+        TRY(get_buf(BUF_NTT_IN, cnt * n * 32, (void **)&din));
+        TRY(get_buf(BUF_NTT_A, cnt * en * 32, (void **)&dout));
+        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(din + q * n, in[q0 + q], n * 32, cudaMemcpyHostToDevice, s));
+        TRY(dev_coeff_to_extended(d, din, dout, s, (uint32_t)cnt));
+        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(out[q0 + q], dout + q * en, en * 32, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return leave(s, H2B_OK);
+}
+int h2b_dev_lagrange_to_coeff_many(const h2b_domain *d, void *d_a, size_t m, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (m == 0) return H2B_OK;
+    if (!d_a) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: null pointer");
+    if (m > 65535) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: more than 65535 columns");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, dev_lagrange_to_coeff(d, (Fe *)d_a, s, (uint32_t)m));
+}
+int h2b_dev_coeff_to_extended_many(const h2b_domain *d, const void *d_in, void *d_out, size_t m, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (m == 0) return H2B_OK;
+    if (!d_in || !d_out) return fail(H2B_ERR_ARG, "coeff_to_extended_many: null pointer");
+    if (m > 65535) return fail(H2B_ERR_ARG, "coeff_to_extended_many: more than 65535 columns");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    return leave(s, dev_coeff_to_extended(d, (const Fe *)d_in, (Fe *)d_out, s, (uint32_t)m));
 }
 int h2b_dev_extended_to_coeff(const h2b_domain *d, const void *d_in, void *d_out, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);

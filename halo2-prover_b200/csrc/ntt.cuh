@@ -37,6 +37,8 @@ struct NttIo {
     uint32_t epi;    // 1: multiply output i by epi_c[i % 3]
     Fe pro_c[3];
     Fe epi_c[3];
+    // batch: gridDim.y independent transforms; transform b reads in + b * bin, writes out + b * bout (elements)
+    uint32_t bin, bout;
 };
 
 // W[e] = omega^e for e in [0, n): two small tables then one product per entry.
@@ -182,7 +184,9 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, uint32_t log_n,
     uint4 *t_hi = t_lo + (R / 2 > 0 ? R / 2 : 1);
 
     PassArgs pa;
-    pa.in = in; pa.out = out; pa.W = W;
+    pa.in = in + (size_t)blockIdx.y * io.bin;
+    pa.out = out + (size_t)blockIdx.y * io.bout;
+    pa.W = W;
     pa.log_n = log_n; pa.log_ns = log_ns; pa.last = last;
     pa.M = 1u << (log_n - S);           // columns in the whole pass
     pa.q0 = blockIdx.x * C;

@@ -56,19 +56,50 @@ class EvaluationDomain:
         _ffi.check(_ffi.lib().h2b_lagrange_to_coeff(C.byref(self._d), _ffi.u64p(a)))
         return a
 
-    def coeff_to_extended(self, a: np.ndarray) -> np.ndarray:
-        """domain.rs:244 -- 2^k coefficients -> 2^extended_k evaluations on the zeta-coset."""
+    def coeff_to_extended(self, a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """domain.rs:244 -- 2^k coefficients -> 2^extended_k evaluations on the zeta-coset
+        (``out``: optional preallocated (2^extended_k, 4) uint64 result buffer)."""
         a = _ffi.as_u64(a, 4)
         assert a.shape[0] == 1 << self.k, "assert_eq!(a.values.len(), 1 << self.k)"
-        out = np.empty((self.extended_len(), 4), dtype=np.uint64)
+        if out is None:
+            out = np.empty((self.extended_len(), 4), dtype=np.uint64)
+        assert out.shape == (self.extended_len(), 4)
         _ffi.check(_ffi.lib().h2b_coeff_to_extended(C.byref(self._d), _ffi.u64p(a), _ffi.u64p(out)))
         return out
 
-    def extended_to_coeff(self, a: np.ndarray) -> np.ndarray:
+    def lagrange_to_coeff_many(self, cols) -> list:
+        """[lagrange_to_coeff(a) for a in cols] in one call (in place)."""
+        cols = [_ffi.as_u64(a, 4) for a in cols]
+        for a in cols:
+            assert a.shape[0] == 1 << self.k, "assert_eq!(a.values.len(), 1 << self.k)"
+        m = len(cols)
+        if m:
+            ptrs = (C.POINTER(C.c_uint64) * m)(*[_ffi.u64p(a) for a in cols])
+            _ffi.check(_ffi.lib().h2b_lagrange_to_coeff_many(C.byref(self._d), ptrs, C.c_size_t(m)))
+        return cols
+
+    def coeff_to_extended_many(self, cols, outs: list | None = None) -> list:
+        """[coeff_to_extended(a) for a in cols] in one call (``outs``: optional preallocated results)."""
+        cols = [_ffi.as_u64(a, 4) for a in cols]
+        for a in cols:
+            assert a.shape[0] == 1 << self.k, "assert_eq!(a.values.len(), 1 << self.k)"
+        m = len(cols)
+        if outs is None:
+            outs = [np.empty((self.extended_len(), 4), dtype=np.uint64) for _ in range(m)]
+        assert len(outs) == m and all(o.shape == (self.extended_len(), 4) for o in outs)
+        if m:
+            pin = (C.POINTER(C.c_uint64) * m)(*[_ffi.u64p(a) for a in cols])
+            pout = (C.POINTER(C.c_uint64) * m)(*[_ffi.u64p(a) for a in outs])
+            _ffi.check(_ffi.lib().h2b_coeff_to_extended_many(C.byref(self._d), pin, pout, C.c_size_t(m)))
+        return outs
+
+    def extended_to_coeff(self, a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """domain.rs:311 -- 2^extended_k coset evaluations -> n * (j-1) coefficients."""
         a = _ffi.as_u64(a, 4)
         assert a.shape[0] == self.extended_len(), "assert_eq!(a.values.len(), self.extended_len())"
-        out = np.empty((self.n * self.quotient_poly_degree, 4), dtype=np.uint64)
+        if out is None:
+            out = np.empty((self.n * self.quotient_poly_degree, 4), dtype=np.uint64)
+        assert out.shape == (self.n * self.quotient_poly_degree, 4)
         _ffi.check(_ffi.lib().h2b_extended_to_coeff(C.byref(self._d), _ffi.u64p(a), _ffi.u64p(out)))
         return out
 

@@ -115,6 +115,12 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a);
  * to m calls of h2b_commit; the fixed latency of a small MSM is paid once per batch. */
 int h2b_commit_many(uint64_t srs, const uint64_t *const *polys, size_t n, size_t m, uint64_t *out);
 
+/* lagrange_to_coeff / coeff_to_extended over m columns in one call (one kernel launch per pass for
+ * the whole batch).  cols[q] / in[q] / out[q] are host columns of 2^k (resp. 2^extended_k) elements;
+ * results are identical to m single calls. */
+int h2b_lagrange_to_coeff_many(const h2b_domain *d, uint64_t *const *cols, size_t m);
+int h2b_coeff_to_extended_many(const h2b_domain *d, const uint64_t *const *in, uint64_t *const *out, size_t m);
+
 /* ---- device-resident variants (inputs/outputs already in HBM) ---------------------- */
 int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out /* 96 B */, void *stream);
 /* ParamsKZG::commit with the polynomial already in HBM: d_coeffs (n x 32 B) against bases[0..n] of a
@@ -128,6 +134,9 @@ int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *s
 int h2b_dev_lagrange_to_coeff(const h2b_domain *d, void *d_a, void *stream);
 int h2b_dev_coeff_to_extended(const h2b_domain *d, const void *d_in, void *d_out, void *stream);
 int h2b_dev_extended_to_coeff(const h2b_domain *d, const void *d_in, void *d_out, void *stream);
+/* m columns one after the other in HBM: d_a + q * 2^k (in place); d_in + q * 2^k -> d_out + q * 2^extended_k. */
+int h2b_dev_lagrange_to_coeff_many(const h2b_domain *d, void *d_a, size_t m, void *stream);
+int h2b_dev_coeff_to_extended_many(const h2b_domain *d, const void *d_in, void *d_out, size_t m, void *stream);
 int h2b_dev_g1_fold(const void *d_points, size_t count, void *d_out, void *stream);
 /* out[i] = [scalars[i]] * base as G1Affine (n x 64 B): the per-element fixed-base multiplication of
  * ParamsKZG::setup (src/poly/kzg/commitment.rs:68-114); builds synthetic SRS / benchmark bases in HBM. */

@@ -92,6 +92,28 @@ def test_domain_vs_oracle(h2b, spec, href, j, k):
     assert (back == ref).all()
 
 
+@pytest.mark.parametrize("j,k,m", [(3, 1, 3), (4, 5, 5), (6, 9, 7), (4, 12, 3), (6, 14, 4), (3, 21, 2)])
+def test_batched_column_transforms_equal_single_calls(h2b, spec, href, j, k, m):
+    """lagrange_to_coeff_many / coeff_to_extended_many (one launch per pass for all columns) == single calls
+    == the oracle, for one-, two- and three-pass sizes."""
+    d = h2b.EvaluationDomain(j, k)
+    dc = href.domain_new(j, k)
+    cols = [href.random_fr(1 << k, 500 + 7 * k + q) for q in range(m)]
+    cols[-1][:] = 0
+    got = d.lagrange_to_coeff_many([c.copy() for c in cols])
+    ext = d.coeff_to_extended_many(cols)
+    for q in range(m):
+        if k <= 14 or q == 0:
+            assert (got[q] == href.lagrange_to_coeff(dc, cols[q])).all(), q
+            assert (ext[q] == href.coeff_to_extended(dc, cols[q])).all(), q
+        else:
+            assert (got[q] == d.lagrange_to_coeff(cols[q].copy())).all(), q
+            assert (ext[q] == d.coeff_to_extended(cols[q])).all(), q
+    assert d.lagrange_to_coeff_many([]) == [] and d.coeff_to_extended_many([]) == []
+    with pytest.raises(AssertionError):
+        d.coeff_to_extended_many([np.zeros((3, 4), dtype=np.uint64)])
+
+
 def test_domain_length_asserts(h2b, href):
     d = h2b.EvaluationDomain(4, 5)
     with pytest.raises(AssertionError):
