@@ -273,7 +273,7 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     cfg.slice = L;
     size_t max_slices = entries / cfg.slice + 1;
     uint32_t *counts, *cursor, *ne_off, *ne_id, *sorted, *totals, *heavy, *digits;
-    int32_t *tail_j;
+    int32_t *tail_j, *head_j;
     XYZZ *head, *tail;
     uint2 *block_sums;
     TRY(get_buf(BUF_COUNTS, (size_t)cfg.nb * 4, (void **)&counts));
@@ -284,7 +284,8 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     TRY(get_buf(BUF_DIGITS, entries * 4, (void **)&digits));
     TRY(get_buf(BUF_HEAD, max_slices * sizeof(XYZZ), (void **)&head));
     TRY(get_buf(BUF_TAIL, max_slices * sizeof(XYZZ), (void **)&tail));
-    TRY(get_buf(BUF_TAILJ, max_slices * 4, (void **)&tail_j));
+    TRY(get_buf(BUF_TAILJ, 2 * max_slices * 4, (void **)&tail_j));
+    head_j = tail_j + max_slices;
     TRY(get_buf(BUF_BLOCKSUMS, 1024 * sizeof(uint2), (void **)&block_sums));
     TRY(get_buf(BUF_TOTALS, 16, (void **)&totals));
     TRY(get_buf(BUF_HEAVY, (max_slices + 2) * 4, (void **)&heavy));
@@ -299,7 +300,7 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     }
     CU(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * 4, s));
     CU(cudaMemsetAsync(heavy, 0, 4, s));
-    CU(cudaMemsetAsync(tail_j, 0xff, max_slices * 4, s));
+    CU(cudaMemsetAsync(tail_j, 0xff, 2 * max_slices * 4, s));
     uint32_t nblk = (uint32_t)((m * cfg.cols + 255) / 256);
     msm_digits_kernel<<<nblk, 256, 0, s>>>(d_scalars, cfg, counts, digits);
     LAUNCHED();
@@ -316,11 +317,14 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     time_begin(s);
     uint32_t ablocks = (uint32_t)((max_slices + 127) / 128);
     msm_accumulate_kernel<<<ablocks, 128, 0, s>>>(d_bases, sorted, ne_off, ne_id, totals, cfg, target, head, tail,
-                                                  tail_j);
+                                                  tail_j, head_j);
     LAUNCHED();
     time_end(s);
-    msm_fixup_kernel<<<ablocks, 128, 0, s>>>(ne_off, ne_id, totals, cfg, head, tail, tail_j, target, heavy);
-    LAUNCHED();
+    for (uint32_t r = 0; r < kFixupLevels; r++) {
+        msm_fixup_level_kernel<<<ablocks, 128, 0, s>>>(ne_off, ne_id, totals, cfg, head, tail, tail_j, head_j, target,
+                                                       heavy, r);
+        LAUNCHED();
+    }
     msm_fixup_heavy_kernel<<<g->sm_count * 4, 128, 0, s>>>(ne_off, ne_id, cfg, head, tail, tail_j, heavy, target);
     LAUNCHED();
     if (run.chunks_done > 0) {

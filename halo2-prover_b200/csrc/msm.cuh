@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(128)
 msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restrict__ sorted,
                       const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
                       const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *__restrict__ bucket_sums,
-                      XYZZ *__restrict__ head, XYZZ *__restrict__ tail, int32_t *__restrict__ tail_j) {
+                      XYZZ *__restrict__ head, XYZZ *__restrict__ tail, int32_t *__restrict__ tail_j,
+                      int32_t *__restrict__ head_j) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = totals[0], J = totals[1];
     const uint64_t begin64 = (uint64_t)s * cfg.slice;
@@ -242,6 +243,7 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
     uint32_t j = lo;
     uint32_t bend = ne_off[j + 1];
     bool started_before = ne_off[j] < begin;
+    if (started_before) head_j[s] = (int32_t)j;  // this slice holds a middle / last piece of bucket j
 
     XYZZ acc = xyzz_identity();
     uint32_t e = begin;
@@ -283,29 +285,51 @@ msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restri
 }
 
 // Buckets that straddle slices.  The slice holding the first piece (tail) owns the bucket:
-// sum = tail[s] + head[s+1] + ... + head[s_last].  Short spans are folded by the owning thread;
-// long ones (skewed scalars, short top window) are queued and folded by one block each.
+// sum = tail[s0] + head[s0+1] + ... + head[s0+last].  The pieces of one bucket are adjacent slice
+// slots, so they are folded as a pairwise tree, one launch per level r (piece o absorbs piece
+// o + 2^r when o is a multiple of 2^(r+1)): every thread performs at most one addition per role and
+// level, whatever the bucket sizes, instead of one thread walking a whole bucket.  Five levels cover
+// spans of up to 32 slices; longer ones (skewed scalars, short top window) are queued in level 0
+// and folded by one block each (msm_fixup_heavy_kernel).  The last level publishes the sums.
+constexpr uint32_t kFixupLevels = 5;
 __global__ void __launch_bounds__(128)
-msm_fixup_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
-                 const uint32_t *__restrict__ totals, MsmCfg cfg, const XYZZ *__restrict__ head,
-                 const XYZZ *__restrict__ tail, const int32_t *__restrict__ tail_j,
-                 XYZZ *__restrict__ bucket_sums, uint32_t *__restrict__ heavy) {
+msm_fixup_level_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
+                       const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *__restrict__ head,
+                       XYZZ *__restrict__ tail, const int32_t *__restrict__ tail_j,
+                       const int32_t *__restrict__ head_j, XYZZ *__restrict__ bucket_sums,
+                       uint32_t *__restrict__ heavy, uint32_t r) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = totals[0];
     if ((uint64_t)s * cfg.slice >= total) return;
-    const int32_t j = tail_j[s];
-    if (j < 0) return;
-    const uint32_t s_last = (ne_off[j + 1] - 1) / cfg.slice;
-    if (s_last - s > 16) {
-        heavy[1 + atomicAdd(&heavy[0], 1u)] = s;
-        return;
+    const uint32_t step = 1u << r;
+    const int32_t jh = head_j[s];
+    if (jh >= 0) {  // a non-first piece of bucket jh
+        const uint32_t s0 = ne_off[jh] / cfg.slice;
+        const uint32_t last = (ne_off[jh + 1] - 1) / cfg.slice - s0, o = s - s0;
+        if (last < (1u << kFixupLevels) && (o & (2 * step - 1)) == 0 && o + step <= last) {
+            XYZZ a = load_xyzz(&head[s]);
+            XYZZ b = load_xyzz(&head[s + step]);
+            xyzz_add(a, b);
+            store_xyzz(&head[s], a);
+        }
     }
-    XYZZ acc = load_xyzz(&tail[s]);
-    for (uint32_t t = s + 1; t <= s_last; t++) {
-        XYZZ q = load_xyzz(&head[t]);
-        xyzz_add(acc, q);
+    const int32_t jt = tail_j[s];
+    if (jt >= 0) {  // the first piece: this slice owns bucket jt
+        const uint32_t last = (ne_off[jt + 1] - 1) / cfg.slice - s;
+        if (last >= (1u << kFixupLevels)) {
+            if (r == 0) heavy[1 + atomicAdd(&heavy[0], 1u)] = s;
+            return;
+        }
+        const bool fold = step <= last, publish = r + 1 == kFixupLevels;
+        if (!fold && !publish) return;
+        XYZZ a = load_xyzz(&tail[s]);
+        if (fold) {
+            XYZZ b = load_xyzz(&head[s + step]);
+            xyzz_add(a, b);
+            if (!publish) store_xyzz(&tail[s], a);
+        }
+        if (publish) store_xyzz(&bucket_sums[ne_id[jt]], a);
     }
-    store_xyzz(&bucket_sums[ne_id[j]], acc);
 }
 __global__ void __launch_bounds__(128)
 msm_fixup_heavy_kernel(const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id, MsmCfg cfg,
