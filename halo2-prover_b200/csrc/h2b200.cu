@@ -1145,6 +1145,18 @@ int h2b_srs_device_ptr(uint64_t srs, void **d_bases, size_t *n) {
     if (n) *n = it->second.n;
     return H2B_OK;
 }
+int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windows, size_t *table_bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    auto it = g->srs.find(srs);
+    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "srs_info: unknown handle");
+    const Srs &sr = it->second;
+    if (n) *n = sr.n;
+    if (window_bits) *window_bits = sr.table ? sr.c : 0;
+    if (windows) *windows = sr.table ? sr.windows : 0;
+    if (table_bytes) *table_bytes = sr.table ? (size_t)sr.windows * sr.n * sizeof(Affine) : 0;
+    return H2B_OK;
+}
 int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());

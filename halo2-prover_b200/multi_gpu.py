@@ -50,3 +50,23 @@ def sharded_multiexp(coeffs_local, bases_local, group=None, stream=None):
     out = torch.empty(12, dtype=torch.int64, device=dev)
     dev_g1_fold(parts, out, stream=stream)
     return out
+
+
+def sharded_commit(params, coeffs_local, which: str = "g", group=None, stream=None):
+    """ParamsKZG::commit over an SRS sharded by point range: ``params`` holds THIS rank's slice of the bases
+    (registered once, with its precomputed window table), ``coeffs_local`` the matching slice of the
+    polynomial ((m,4) int64 cuda tensor).  Returns the folded (12,) projective sum (same on every rank)."""
+    import torch
+    import torch.distributed as dist
+
+    from .arithmetic import dev_g1_fold
+
+    dev = coeffs_local.device
+    partial = torch.empty(12, dtype=torch.int64, device=dev)
+    params.dev_commit(coeffs_local, partial, which=which, stream=stream)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return partial
+    parts = gather_partials(partial, group)
+    out = torch.empty(12, dtype=torch.int64, device=dev)
+    dev_g1_fold(parts, out, stream=stream)
+    return out

@@ -145,6 +145,10 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
 /* ---- tuning / introspection ------------------------------------------------------- */
 /* Override the MSM window (0 = automatic). */
 int h2b_set_msm_window(uint32_t c);
+/* Geometry of a registered SRS: its length and, when it has a precomputed window table, the window
+ * width, the number of windows (= bucket additions per point of a commit) and the table's size in HBM
+ * (zeros when there is no table). */
+int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windows, size_t *table_bytes);
 /* h2b_srs_register precomputes 2^(c*w) * P_i for the static bases (default on) so that all windows of a
  * commit share one bucket set; `c` overrides that table's window (0 = automatic).  Applies to SRS
  * registered after the call. */
