@@ -1078,8 +1078,43 @@ int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     return leave(g->stream, H2B_OK);
 }
 
+static int srs_register_locked(const void *bases, size_t n, uint64_t *handle);
 int h2b_srs_register(const uint64_t *bases, size_t n, uint64_t *handle) {
     std::lock_guard<std::mutex> lk(g_mu);
+    return srs_register_locked(bases, n, handle);
+}
+// ParamsKZG::read, SerdeFormat::RawBytes (what ParamsKZG::write produces; the reference moves its SRS
+// between setup and prover in this form, /root/reference/circuits/src/wasm.rs:52, :79, :126):
+//   k: u32 LE | g[2^k] x 64 B | g_lagrange[2^k] x 64 B | g2 128 B | s_g2 128 B
+// with every coordinate as its four Montgomery limbs -- the body of the file IS the base array, so both
+// arrays go to HBM straight from the caller's buffer.
+int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k_out, uint64_t *g_handle, uint64_t *g_lagrange_handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!bytes || !g_handle || !g_lagrange_handle) return fail(H2B_ERR_ARG, "params_read: null pointer");
+    if (len < 4) return fail(H2B_ERR_ARG, "params_read: truncated header");
+    const uint32_t k = (uint32_t)bytes[0] | ((uint32_t)bytes[1] << 8) | ((uint32_t)bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
+    if (k > 28) return fail(H2B_ERR_ARG, "params_read: k > 28");
+    const size_t n = (size_t)1 << k;
+    if (len != 4 + 128 * n + 256) return fail(H2B_ERR_ARG, "params_read: length is not 4 + 128 * 2^k + 256");
+    uint64_t hg = 0, hl = 0;
+    TRY(srs_register_locked(bytes + 4, n, &hg));
+    int rc = srs_register_locked(bytes + 4 + 64 * n, n, &hl);
+    if (rc != H2B_OK) {
+        auto it = g->srs.find(hg);
+        if (it != g->srs.end()) {
+            cudaFree(it->second.d);
+            if (it->second.table) cudaFree(it->second.table);
+            g->srs.erase(it);
+        }
+        return rc;
+    }
+    if (k_out) *k_out = k;
+    *g_handle = hg;
+    *g_lagrange_handle = hl;
+    return H2B_OK;
+}
+static int srs_register_locked(const void *bases, size_t n, uint64_t *handle) {
     TRY(ensure_ctx());
     if (!bases || !handle || n == 0) return fail(H2B_ERR_ARG, "srs_register: bad argument");
     CU(cudaSetDevice(g->device));

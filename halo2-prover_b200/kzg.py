@@ -31,6 +31,21 @@ class ParamsKZG:
             _ffi.check(_ffi.lib().h2b_srs_register(_ffi.u64p(arr), C.c_size_t(arr.shape[0]), C.byref(h)))
             self._handles[name] = h.value
 
+    @classmethod
+    def read(cls, data) -> "ParamsKZG":
+        """ParamsKZG::read (SerdeFormat::RawBytes): ``data`` is the byte string ParamsKZG::write produced
+        (k | g | g_lagrange | g2 | s_g2); both base arrays are registered straight from it."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        _ffi.init()
+        k, hg, hl = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _ffi.check(_ffi.lib().h2b_params_read(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(buf.size),
+                                              C.byref(k), C.byref(hg), C.byref(hl)))
+        self = cls.__new__(cls)
+        self.k = k.value
+        self.n = 1 << k.value
+        self._handles = {"g": hg.value, "g_lagrange": hl.value}
+        return self
+
     def _commit(self, which: str, poly: np.ndarray) -> np.ndarray:
         poly = _ffi.as_u64(poly, 4)
         size = poly.shape[0]

@@ -145,6 +145,10 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
 /* ---- tuning / introspection ------------------------------------------------------- */
 /* Override the MSM window (0 = automatic). */
 int h2b_set_msm_window(uint32_t c);
+/* ParamsKZG::read for SerdeFormat::RawBytes (the bytes ParamsKZG::write produces, wasm.rs:52/:79/:126):
+ * k:u32 LE | g[2^k] x 64 B | g_lagrange[2^k] x 64 B | g2 128 B | s_g2 128 B.  Registers both base arrays
+ * straight from the buffer and returns their handles (release each with h2b_srs_release). */
+int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k, uint64_t *g_handle, uint64_t *g_lagrange_handle);
 /* Geometry of a registered SRS: its length and, when it has a precomputed window table, the window
  * width, the number of windows (= bucket additions per point of a commit) and the table's size in HBM
  * (zeros when there is no table). */

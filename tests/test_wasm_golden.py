@@ -114,3 +114,33 @@ def test_cuda_domain_transforms_match_reference_fft_records(h2b, href):
             assert (d.lagrange_to_coeff(a.copy()) == href.fr_mul(np.ascontiguousarray(z[f"fft{i}_out"]), div)).all()
             hit += 1
     assert hit > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+def test_params_read_from_reference_setup_bytes(name, h2b, href):
+    """ParamsKZG::read on the bytes the reference's own `setup(k)` wrote (SerdeFormat::RawBytes), then the
+    recorded commits of the reference's proof through the SRS registered from that buffer -- one by one and
+    as one batch per base array."""
+    ent, z, g, gl = _load(name)
+    params = h2b.ParamsKZG.read(z["params"].tobytes())
+    assert params.k == ent["k"]
+    batch = {"g": [], "g_lagrange": []}
+    for m in ent["msm"]:
+        if m["bases"] not in batch or m["n"] != params.n:
+            continue
+        sc = np.ascontiguousarray(z[f"msm{m['i']}_scalars"])
+        out = params.commit(sc) if m["bases"] == "g" else params.commit_lagrange(sc)
+        assert (href.g1_to_affine(out) == z[f"msm{m['i']}_affine"]).all(), (name, m)
+        batch[m["bases"]].append((sc, z[f"msm{m['i']}_affine"]))
+    assert batch["g"] or batch["g_lagrange"]
+    for which, items in batch.items():
+        if not items:
+            continue
+        outs = params.commit_many([sc for sc, _ in items]) if which == "g" else params.commit_lagrange_many([sc for sc, _ in items])
+        for out, (_, want) in zip(outs, items):
+            assert (href.g1_to_affine(out) == want).all(), (name, which)
+    params.release()
+    for bad in (b"", b"\x04\x00\x00", z["params"].tobytes()[:-1]):
+        with pytest.raises(Exception):
+            h2b.ParamsKZG.read(bad)
