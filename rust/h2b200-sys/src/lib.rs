@@ -50,6 +50,10 @@ extern "C" {
     pub fn h2b_coeff_to_extended(d: *const H2bDomain, input: *const u64, out: *mut u64) -> c_int;
     pub fn h2b_extended_to_coeff(d: *const H2bDomain, input: *const u64, out: *mut u64) -> c_int;
     pub fn h2b_divide_by_vanishing_poly(d: *const H2bDomain, a: *mut u64) -> c_int;
+    pub fn h2b_commit_many(srs: u64, polys: *const *const u64, n: usize, m: usize, out: *mut u64) -> c_int;
+    pub fn h2b_params_read(bytes: *const u8, len: usize, k: *mut u32, g: *mut u64, g_lagrange: *mut u64) -> c_int;
+    pub fn h2b_lagrange_to_coeff_many(d: *const H2bDomain, cols: *const *mut u64, m: usize) -> c_int;
+    pub fn h2b_coeff_to_extended_many(d: *const H2bDomain, input: *const *const u64, out: *const *mut u64, m: usize) -> c_int;
     pub fn h2b_dev_msm(c: *const c_void, b: *const c_void, n: usize, out: *mut c_void, stream: *mut c_void) -> c_int;
 }
 
@@ -105,6 +109,26 @@ impl Srs {
         unsafe { out.assume_init() }
     }
 }
+impl Srs {
+    /// `polys.iter().map(|p| self.commit(p))` in one pass of the kernels: the advice columns, the
+    /// permutation / lookup products or the h pieces of one create_proof phase (plonk/prover.rs).
+    pub fn commit_many(&self, polys: &[&[Fr]]) -> Vec<G1> {
+        let n = polys.first().map_or(0, |p| p.len());
+        assert!(polys.iter().all(|p| p.len() == n));
+        let ptrs: Vec<*const u64> = polys.iter().map(|p| p.as_ptr() as *const u64).collect();
+        let mut out: Vec<G1> = Vec::with_capacity(polys.len());
+        check(unsafe { h2b_commit_many(self.0, ptrs.as_ptr(), n, polys.len(), out.as_mut_ptr() as *mut u64) }, "commit_many");
+        unsafe { out.set_len(polys.len()) };
+        out
+    }
+    /// `ParamsKZG::read` (SerdeFormat::RawBytes): returns (k, g, g_lagrange) registered from the buffer.
+    pub fn read_params(bytes: &[u8]) -> (u32, Srs, Srs) {
+        ensure_init();
+        let (mut k, mut g, mut gl) = (0u32, 0u64, 0u64);
+        check(unsafe { h2b_params_read(bytes.as_ptr(), bytes.len(), &mut k, &mut g, &mut gl) }, "params_read");
+        (k, Srs(g), Srs(gl))
+    }
+}
 impl Drop for Srs {
     fn drop(&mut self) {
         unsafe { h2b_srs_release(self.0) };
@@ -130,6 +154,21 @@ impl Domain {
         let mut out = vec![Fr::zero(); 1 << self.0.extended_k];
         check(unsafe { h2b_coeff_to_extended(&self.0, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) }, "coeff_to_extended");
         out
+    }
+    /// `for a in cols { self.lagrange_to_coeff(a) }` with one kernel launch per pass for all columns.
+    pub fn lagrange_to_coeff_many(&self, cols: &mut [&mut [Fr]]) {
+        assert!(cols.iter().all(|a| a.len() == 1 << self.0.k));
+        let ptrs: Vec<*mut u64> = cols.iter_mut().map(|a| a.as_mut_ptr() as *mut u64).collect();
+        check(unsafe { h2b_lagrange_to_coeff_many(&self.0, ptrs.as_ptr(), ptrs.len()) }, "lagrange_to_coeff_many");
+    }
+    /// `cols.iter().map(|a| self.coeff_to_extended(a))` in one call (evaluate_h extends every column).
+    pub fn coeff_to_extended_many(&self, cols: &[&[Fr]]) -> Vec<Vec<Fr>> {
+        assert!(cols.iter().all(|a| a.len() == 1 << self.0.k));
+        let mut outs: Vec<Vec<Fr>> = cols.iter().map(|_| vec![Fr::zero(); 1 << self.0.extended_k]).collect();
+        let pin: Vec<*const u64> = cols.iter().map(|a| a.as_ptr() as *const u64).collect();
+        let pout: Vec<*mut u64> = outs.iter_mut().map(|a| a.as_mut_ptr() as *mut u64).collect();
+        check(unsafe { h2b_coeff_to_extended_many(&self.0, pin.as_ptr(), pout.as_ptr(), pin.len()) }, "coeff_to_extended_many");
+        outs
     }
     pub fn extended_to_coeff(&self, a: &[Fr]) -> Vec<Fr> {
         assert_eq!(a.len(), 1 << self.0.extended_k);
