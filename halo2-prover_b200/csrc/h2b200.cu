@@ -70,6 +70,7 @@ struct Ctx {
     std::map<uint64_t, h2b_domain> domains;
     uint64_t launches = 0;
     uint32_t msm_window = 0;
+    double e2e_ratio = 0;      // growth of the host-path chunk sizes (0 = automatic)
     uint32_t srs_window = 0;   // 0 = automatic
     int srs_precompute = 1;
     int timing = 0;
@@ -392,10 +393,26 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
     // the copy stream must not overwrite staging that earlier work on `s` may still read
     CU(cudaEventRecord(g->copy_fence, s));
     CU(cudaStreamWaitEvent(g->copy_stream, g->copy_fence, 0));
-    size_t per = (n + chunks - 1) / chunks;
-    per = (per + 255) & ~(size_t)255;
+    // Chunk sizes grow geometrically: the first copy is the only one nothing overlaps, so it is small, and
+    // every later chunk is as large as the accumulation of its predecessor can hide (the ratio is compute
+    // time per point over copy time per point: ~4 with resident bases, ~1.5 when the bases travel too).
+    const double ratio = g->e2e_ratio > 0 ? g->e2e_ratio : (h_bases ? 1.5 : 4.0);
+    double denom = 0, pw = 1;
+    for (uint32_t k = 0; k < chunks; k++) { denom += pw; pw *= ratio; }
     std::vector<size_t> lo, hi;
-    for (size_t a = 0; a < n; a += per) { lo.push_back(a); hi.push_back(a + per < n ? a + per : n); }
+    pw = 1;
+    size_t at = 0;
+    for (uint32_t k = 0; k < chunks && at < n; k++) {
+        size_t m = k + 1 == chunks ? n - at : (size_t)((double)n * pw / denom);
+        m = (m + 255) & ~(size_t)255;
+        if (m == 0) m = 256;
+        if (at + m > n) m = n - at;
+        lo.push_back(at);
+        hi.push_back(at + m);
+        at += m;
+        pw *= ratio;
+    }
+    if (at < n) hi.back() = n;
     while (g->chunk_events.size() < lo.size()) {
         cudaEvent_t e;
         CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -883,6 +900,8 @@ int h2b_init(int device) {
         int v = atoi(sw);
         if (v >= 2 && v <= 24) c->srs_window = (uint32_t)v;
     }
+    const char *er = getenv("H2B_E2E_RATIO");
+    if (er) c->e2e_ratio = atof(er);
     const char *sp = getenv("H2B_SRS_PRECOMPUTE");
     if (sp) c->srs_precompute = atoi(sp) != 0;
     const char *ec = getenv("H2B_E2E_CHUNKS");
