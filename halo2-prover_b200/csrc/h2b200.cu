@@ -70,6 +70,7 @@ struct Ctx {
     std::map<uint64_t, h2b_domain> domains;
     uint64_t launches = 0;
     uint32_t msm_window = 0;
+    uint32_t reduce_lgrp = 0;  // tuning override (H2B_REDUCE_LGRP)
     double e2e_ratio = 0;      // growth of the host-path chunk sizes (0 = automatic)
     uint32_t srs_window = 0;   // 0 = automatic
     int srs_precompute = 1;
@@ -218,6 +219,10 @@ MsmCfg msm_plan(size_t n, const Srs *srs = nullptr, uint32_t cols = 1) {
     // reduction groups of 2^lgrp buckets: 16 per group once a window has >= 4096 buckets
     uint32_t lgrp = 0;
     while (lgrp < 4 && (cfg.bpw >> lgrp) > 256) lgrp++;
+    // very wide windows (shared bucket sets of a window table): larger groups amortise the double-and-add of
+    // the group offset while still leaving >= 2^15 group chains for the GPU
+    while (lgrp < 6 && ((uint64_t)cfg.bpw * cols >> lgrp) > (1u << 15)) lgrp++;
+    if (g->reduce_lgrp) lgrp = g->reduce_lgrp;
     cfg.lgrp = lgrp;
     return cfg;
 }
@@ -225,11 +230,16 @@ MsmCfg msm_plan(size_t n, const Srs *srs = nullptr, uint32_t cols = 1) {
 // Shared-bucket window for a registered SRS of n points (tunable: H2B_SRS_WINDOW).
 uint32_t srs_window_for(size_t n) {
     if (g->srs_window) return g->srs_window;
-    uint32_t lg = ceil_log2(n);
-    uint32_t c = lg > 2 ? lg - 2 : 1;
-    if (c < 6) c = 6;
-    if (c > 24) c = 24;
-    return c;
+    // Measured on B200 (scripts/probe.py, PROBE_COMMIT / PROBE_SRS_C sweeps).  Only widths whose top window
+    // keeps >= 12 of the scalar's 254 bits are used from 2^15 points up (15, 16, 17, 20, 22, 24): a top window
+    // of one or two bits sends every point to the same few buckets (hot atomics, buckets spanning thousands
+    // of slices).  Small SRS are latency-bound: few buckets keep the reduction chains short.
+    const uint32_t lg = ceil_log2(n);
+    if (lg <= 14) return lg >= 11 ? lg - 5 : 6;
+    if (lg <= 16) return 16;
+    if (lg <= 18) return 17;
+    if (lg <= 25) return 20;
+    return 22;
 }
 
 // An MSM is: begin (clear the buckets) -> one or more chunks over contiguous point ranges, each
@@ -900,6 +910,8 @@ int h2b_init(int device) {
         int v = atoi(sw);
         if (v >= 2 && v <= 24) c->srs_window = (uint32_t)v;
     }
+    const char *rl = getenv("H2B_REDUCE_LGRP");
+    if (rl) c->reduce_lgrp = (uint32_t)atoi(rl);
     const char *er = getenv("H2B_E2E_RATIO");
     if (er) c->e2e_ratio = atof(er);
     const char *sp = getenv("H2B_SRS_PRECOMPUTE");
