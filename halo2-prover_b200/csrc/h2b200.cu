@@ -15,9 +15,11 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "curve.cuh"
+#include "hostcopy.h"
 #include "field.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
@@ -84,6 +86,7 @@ struct Ctx {
     std::vector<cudaEvent_t> tev0, tev1;  // timing event pairs
     uint32_t tev_used = 0;
     int sm_count = 148;
+    HostCopier *copier = nullptr;  // pageable host memory <-> HBM through worker threads and a pinned ring
 };
 Ctx *g = nullptr;
 
@@ -116,6 +119,18 @@ int ensure_ctx() {
     return fail(H2B_ERR_STATE, "h2b_init has not been called");
 }
 
+// host <-> device copies of caller buffers (pinned buffers go straight to the DMA engine)
+int copy_in(void *dev, const void *host, size_t bytes, cudaStream_t s) {
+    cudaError_t e = g->copier->h2d(dev, host, bytes, s);
+    if (e != cudaSuccess) return fail(H2B_ERR_CUDA, "host-to-device copy", e);
+    return H2B_OK;
+}
+// ordered after the work on `s`; returns when the host buffer is complete and `s` is idle
+int copy_out(void *host, const void *dev, size_t bytes, cudaStream_t s) {
+    cudaError_t e = g->copier->d2h(host, dev, bytes, s);
+    if (e != cudaSuccess) return fail(H2B_ERR_CUDA, "device-to-host copy", e);
+    return H2B_OK;
+}
 int get_buf(BufId id, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
     if (g->cap[id] < bytes) {
@@ -395,9 +410,41 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
     MsmRun run;
     TRY(msm_begin(n, &run, s, h_bases ? nullptr : srs));
     if (chunks <= 1) {
-        CU(cudaMemcpyAsync(ds, h_scalars, n * sizeof(Fe), cudaMemcpyHostToDevice, s));
-        if (h_bases) CU(cudaMemcpyAsync(db, h_bases, n * sizeof(Affine), cudaMemcpyHostToDevice, s));
+        TRY(copy_in(ds, h_scalars, n * sizeof(Fe), s));
+        if (h_bases) TRY(copy_in(db, h_bases, n * sizeof(Affine), s));
         TRY(msm_chunk(run, ds, bases, n, s));
+        return msm_finish(run, d_out, s);
+    }
+    if (g->copier->stages(h_scalars)) {
+        // pageable scalars: the staged copy of a chunk is host work that overlaps the accumulation of the
+        // previous chunk already running on the GPU
+        std::vector<size_t> clo, chi;
+        {
+            // staged copies run at roughly half the pinned rate: chunks grow by 2 (measured: 44.6 ms for 2^24
+            // pageable scalars against 45.8 ms from pinned memory and 89 ms through the driver's staging)
+            const double ratio = g->e2e_ratio > 0 ? g->e2e_ratio : (h_bases ? 1.25 : 2.0);
+            double denom = 0, pw = 1;
+            for (uint32_t k = 0; k < chunks; k++) { denom += pw; pw *= ratio; }
+            pw = 1;
+            size_t at = 0;
+            for (uint32_t k = 0; k < chunks && at < n; k++) {
+                size_t m = k + 1 == chunks ? n - at : (((size_t)((double)n * pw / denom) + 255) & ~(size_t)255);
+                if (m == 0) m = 256;
+                if (at + m > n) m = n - at;
+                clo.push_back(at);
+                chi.push_back(at + m);
+                at += m;
+                pw *= ratio;
+            }
+            if (at < n) chi.back() = n;
+        }
+        for (size_t k = 0; k < clo.size(); k++) {
+            const size_t m = chi[k] - clo[k];
+            TRY(copy_in(ds + clo[k], h_scalars + 4 * clo[k], m * sizeof(Fe), s));
+            if (h_bases) TRY(copy_in(db + clo[k], h_bases + 8 * clo[k], m * sizeof(Affine), s));
+            if (shared) TRY(msm_chunk(run, ds + clo[k], bases, m, s, clo[k]));
+            else TRY(msm_chunk(run, ds + clo[k], bases + clo[k], m, s));
+        }
         return msm_finish(run, d_out, s);
     }
     // the copy stream must not overwrite staging that earlier work on `s` may still read
@@ -856,8 +903,7 @@ __global__ void imad_wide_bench_kernel(uint64_t *sink, uint32_t iters, uint32_t 
 int stage_in(BufId id, const void *host, size_t bytes, void **dev) {
     TRY(enter(g->stream));
     TRY(get_buf(id, bytes, dev));
-    CU(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, g->stream));
-    return H2B_OK;
+    return copy_in(*dev, host, bytes, g->stream);
 }
 
 }  // namespace
@@ -892,6 +938,12 @@ int h2b_init(int device) {
         cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return fail(H2B_ERR_CUDA, "h2b_init: stream/event creation failed", cudaGetLastError());
+    }
+    {
+        int threads = (int)std::min(6u, std::max(2u, std::thread::hardware_concurrency() / 2));
+        const char *ct = getenv("H2B_COPY_THREADS");  // 0: leave pageable copies to the driver
+        if (ct) threads = atoi(ct);
+        c->copier = new HostCopier(threads);
     }
     const char *mr = getenv("H2B_NTT_MAX_RADIX");
     if (mr) {
@@ -940,6 +992,7 @@ void h2b_shutdown(void) {
     for (auto e : g->tev0) cudaEventDestroy(e);
     for (auto e : g->tev1) cudaEventDestroy(e);
     for (auto e : g->chunk_events) cudaEventDestroy(e);
+    delete g->copier;
     cudaEventDestroy(g->copy_fence);
     cudaStreamDestroy(g->copy_stream);
     cudaEventDestroy(g->last_done);
@@ -1087,11 +1140,14 @@ int h2b_commit_many(uint64_t srs, const uint64_t *const *polys, size_t n, size_t
     void *dout;
     if (n) TRY(get_buf(BUF_SCALARS, m * n * sizeof(Fe), (void **)&ds));
     TRY(get_buf(BUF_OUT, m * sizeof(Projective), &dout));
-    for (size_t q = 0; q < m && n; q++)
-        CU(cudaMemcpyAsync(ds + q * n, polys[q], n * sizeof(Fe), cudaMemcpyHostToDevice, s));
+    if (n) {
+        std::vector<HostCopier::Seg> segs;
+        for (size_t q = 0; q < m; q++) segs.push_back({ds + q * n, const_cast<uint64_t *>(polys[q]), n * sizeof(Fe)});
+        cudaError_t ce = g->copier->h2d(segs, s);
+        if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "host-to-device copy", ce);
+    }
     TRY(commit_many_device(it->second, ds, n, m, (Projective *)dout, s));
-    CU(cudaMemcpyAsync(out, dout, m * sizeof(Projective), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    TRY(copy_out(out, dout, m * sizeof(Projective), s));
     return leave(s, H2B_OK);
 }
 
@@ -1104,8 +1160,7 @@ int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     void *dout;
     TRY(get_buf(BUF_OUT, 96, &dout));
     TRY(msm_run_pipelined(coeffs, bases, nullptr, n, (Projective *)dout));
-    CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(out, dout, 96, g->stream));
     return leave(g->stream, H2B_OK);
 }
 
@@ -1156,7 +1211,8 @@ static int srs_register_locked(const void *bases, size_t n, uint64_t *handle) {
         return fail(H2B_ERR_OOM, "cudaMalloc(srs)", e);
     }
     s.n = n;
-    e = cudaMemcpy(s.d, bases, n * sizeof(Affine), cudaMemcpyHostToDevice);
+    e = g->copier->h2d(s.d, bases, n * sizeof(Affine), g->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
     if (e != cudaSuccess) {
         cudaFree(s.d);
         return fail(H2B_ERR_CUDA, "cudaMemcpy(srs)", e);
@@ -1235,8 +1291,7 @@ int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]
     void *dout;
     TRY(get_buf(BUF_OUT, 96, &dout));
     TRY(msm_run_pipelined(scalars, nullptr, &it->second, n, (Projective *)dout));
-    CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(out, dout, 96, g->stream));
     return leave(g->stream, H2B_OK);
 }
 
@@ -1277,8 +1332,7 @@ int h2b_g1_fold(const uint64_t *points, size_t count, uint64_t out[12]) {
     TRY(get_buf(BUF_OUT, 96, &dout));
     g1_fold_kernel<<<1, 32, 0, g->stream>>>((const Projective *)dp, (uint32_t)count, (Projective *)dout);
     LAUNCHED();
-    CU(cudaMemcpyAsync(out, dout, 96, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(out, dout, 96, g->stream));
     return leave(g->stream, H2B_OK);
 }
 
@@ -1302,8 +1356,7 @@ int h2b_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
     void *da;
     TRY(stage_in(BUF_NTT_A, a, bytes, &da));
     TRY(ntt_run((const Fe *)da, (Fe *)da, log_n, omega, io_plain(log_n), g->stream));
-    CU(cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(a, da, bytes, g->stream));
     return leave(g->stream, H2B_OK);
 }
 
@@ -1335,8 +1388,7 @@ int h2b_lagrange_to_coeff(const h2b_domain *d, uint64_t *a) {
     void *da;
     TRY(stage_in(BUF_NTT_A, a, bytes, &da));
     TRY(dev_lagrange_to_coeff(d, (Fe *)da, g->stream));
-    CU(cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(a, da, bytes, g->stream));
     return leave(g->stream, H2B_OK);
 }
 int h2b_dev_coeff_to_extended(const h2b_domain *d, const void *d_in, void *d_out, void *stream) {
@@ -1360,8 +1412,7 @@ int h2b_coeff_to_extended(const h2b_domain *d, const uint64_t *in, uint64_t *out
     TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din));
     TRY(get_buf(BUF_NTT_A, out_bytes, &dout));
     TRY(dev_coeff_to_extended(d, (const Fe *)din, (Fe *)dout, g->stream));
-    CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(out, dout, out_bytes, g->stream));
     return leave(g->stream, H2B_OK);
 }
 // Batched column transforms (create_proof runs lagrange_to_coeff over every advice / instance / product
@@ -1385,10 +1436,13 @@ int h2b_lagrange_to_coeff_many(const h2b_domain *d, uint64_t *const *cols, size_
         const size_t cnt = std::min(step, m - q0);
         Fe *da;
         TRY(get_buf(BUF_NTT_A, cnt * bytes, (void **)&da));
-        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(da + q * n, cols[q0 + q], bytes, cudaMemcpyHostToDevice, s));
+        std::vector<HostCopier::Seg> segs;
+        for (size_t q = 0; q < cnt; q++) segs.push_back({da + q * n, cols[q0 + q], bytes});
+        cudaError_t ce = g->copier->h2d(segs, s);
+        if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "host-to-device copy", ce);
         TRY(dev_lagrange_to_coeff(d, da, s, (uint32_t)cnt));
-        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(cols[q0 + q], da + q * n, bytes, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        ce = g->copier->d2h(segs, s);
+        if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "device-to-host copy", ce);
     }
     return leave(s, H2B_OK);
 }
@@ -1410,10 +1464,16 @@ int h2b_coeff_to_extended_many(const h2b_domain *d, const uint64_t *const *in, u
         Fe *din, *dout;
         TRY(get_buf(BUF_NTT_IN, cnt * n * 32, (void **)&din));
         TRY(get_buf(BUF_NTT_A, cnt * en * 32, (void **)&dout));
-        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(din + q * n, in[q0 + q], n * 32, cudaMemcpyHostToDevice, s));
+        std::vector<HostCopier::Seg> sin, sout;
+        for (size_t q = 0; q < cnt; q++) {
+            sin.push_back({din + q * n, const_cast<uint64_t *>(in[q0 + q]), n * 32});
+            sout.push_back({dout + q * en, out[q0 + q], en * 32});
+        }
+        cudaError_t ce = g->copier->h2d(sin, s);
+        if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "host-to-device copy", ce);
         TRY(dev_coeff_to_extended(d, din, dout, s, (uint32_t)cnt));
-        for (size_t q = 0; q < cnt; q++) CU(cudaMemcpyAsync(out[q0 + q], dout + q * en, en * 32, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        ce = g->copier->d2h(sout, s);
+        if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "device-to-host copy", ce);
     }
     return leave(s, H2B_OK);
 }
@@ -1463,8 +1523,7 @@ int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out
     TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din));
     TRY(get_buf(BUF_NTT_OUT, out_bytes, &dout));
     TRY(dev_extended_to_coeff(d, (const Fe *)din, (Fe *)dout, g->stream));
-    CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(out, dout, out_bytes, g->stream));
     return leave(g->stream, H2B_OK);
 }
 int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
@@ -1480,8 +1539,7 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
     fr_scale_cyclic_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, g->stream>>>((Fe *)da, (uint32_t)n,
                                                                                (const Fe *)dt, d->n_t);
     LAUNCHED();
-    CU(cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(a, da, n * 32, g->stream));
     return leave(g->stream, H2B_OK);
 }
 
@@ -1501,8 +1559,7 @@ int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, u
     else
         test_field_kernel<Fq><<<blocks, 128, 0, g->stream>>>(op, (Fe *)da, (Fe *)db, (Fe *)dout, (uint32_t)n);
     LAUNCHED();
-    CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(out, dout, n * 32, g->stream));
     return leave(g->stream, H2B_OK);
 }
 int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
@@ -1517,8 +1574,7 @@ int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, 
     test_g1_add_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>((Affine *)da, (Affine *)db,
                                                                            (Projective *)dout, (uint32_t)n);
     LAUNCHED();
-    CU(cudaMemcpyAsync(out, dout, n * 96, cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    TRY(copy_out(out, dout, n * 96, g->stream));
     return leave(g->stream, H2B_OK);
 }
 

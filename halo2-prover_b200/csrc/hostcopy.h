@@ -1,0 +1,240 @@
+// hostcopy.h -- pageable host memory <-> HBM at PCIe speed.
+//
+// The reference's polynomials live in ordinary Rust Vecs (pageable memory).  cudaMemcpy from/to such memory
+// is staged by the driver through one thread and reaches ~12-15 GB/s on this host, a quarter of what the
+// link does from pinned memory, and at k <= 20 those copies cost more than the transforms they feed.
+// Here the staging is done by a few worker threads into a pinned ring, chunk by chunk, with the DMA of a
+// chunk overlapping the memcpy of the next ones.  Pinned caller buffers are detected and copied directly.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace h2b {
+
+class HostCopier {
+  public:
+    static constexpr size_t kChunk = (size_t)512 << 10;  // bytes per staged chunk
+    static constexpr size_t kSlots = 128;                // pinned ring: 64 MiB
+    struct Seg {
+        void *dev;
+        void *host;
+        size_t bytes;
+    };
+    // below this the wake-up of the workers costs more than the driver's own staging loses (measured: 0.5-4 MiB
+    // column copies of a k = 14 proof got slower, the 28 MiB read-back of its extended columns 25 % faster)
+    static constexpr size_t kMinStaged = (size_t)8 << 20;
+
+    explicit HostCopier(int threads) : nthreads_(threads) {}
+    ~HostCopier() { shutdown(); }
+    int threads() const { return nthreads_; }
+    // true when copies from/to `host` go through the pinned ring (pageable memory, staging enabled)
+    bool stages(const void *host) const { return staged(host, 0); }
+
+    // dev <- host for every segment.  On return every DMA has been enqueued and `s` waits for them.
+    cudaError_t h2d(const std::vector<Seg> &segs, cudaStream_t s) {
+        std::vector<Piece> pieces;
+        cudaError_t e = plan(segs, cudaMemcpyHostToDevice, s, pieces);
+        if (e != cudaSuccess || pieces.empty()) return e;
+        if ((e = ensure()) != cudaSuccess) return e;
+        for (size_t base = 0; base < pieces.size(); base += kSlots) {
+            const size_t cnt = std::min(kSlots, pieces.size() - base);
+            if (base && (e = cudaStreamSynchronize(copy_)) != cudaSuccess) return e;  // ring reused: drain its DMAs
+            std::atomic<int> err{0};
+            run(cnt, [&](size_t i) {
+                const Piece &p = pieces[base + i];
+                std::memcpy(ring_ + i * kChunk, p.host, p.len);
+                if (cudaMemcpyAsync(p.dev, ring_ + i * kChunk, p.len, cudaMemcpyHostToDevice, copy_) != cudaSuccess) err = 1;
+            });
+            if (err) return cudaErrorUnknown;
+        }
+        if ((e = cudaEventRecord(done_, copy_)) != cudaSuccess) return e;
+        busy_ = true;
+        return cudaStreamWaitEvent(s, done_, 0);
+    }
+    cudaError_t h2d(void *dev, const void *host, size_t bytes, cudaStream_t s) {
+        return h2d(std::vector<Seg>{{dev, const_cast<void *>(host), bytes}}, s);
+    }
+
+    // host <- dev for every segment, ordered after the work already enqueued on `s`.  Blocks until the host
+    // buffers are complete (and `s` is idle).
+    cudaError_t d2h(const std::vector<Seg> &segs, cudaStream_t s) {
+        std::vector<Piece> pieces;
+        cudaError_t e = plan(segs, cudaMemcpyDeviceToHost, s, pieces);
+        if (e != cudaSuccess) return e;
+        if (pieces.empty()) return cudaStreamSynchronize(s);
+        if ((e = ensure()) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(fence_, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(copy_, fence_, 0)) != cudaSuccess) return e;
+        for (size_t base = 0; base < pieces.size(); base += kSlots) {
+            const size_t cnt = std::min(kSlots, pieces.size() - base);
+            for (size_t i = 0; i < cnt; i++) {
+                const Piece &p = pieces[base + i];
+                if ((e = cudaMemcpyAsync(ring_ + i * kChunk, p.dev, p.len, cudaMemcpyDeviceToHost, copy_)) != cudaSuccess) return e;
+                if ((e = cudaEventRecord(slot_ev_[i], copy_)) != cudaSuccess) return e;
+            }
+            std::atomic<int> err{0};
+            run(cnt, [&](size_t i) {
+                const Piece &p = pieces[base + i];
+                if (cudaEventSynchronize(slot_ev_[i]) != cudaSuccess) err = 1;
+                std::memcpy(p.host, ring_ + i * kChunk, p.len);
+            });
+            if (err) return cudaErrorUnknown;
+        }
+        return cudaStreamSynchronize(s);
+    }
+    cudaError_t d2h(void *host, const void *dev, size_t bytes, cudaStream_t s) {
+        return d2h(std::vector<Seg>{{const_cast<void *>(dev), host, bytes}}, s);
+    }
+
+    // Wait until staged host-to-device copies issued so far have left the pinned ring.
+    cudaError_t drain() {
+        if (!busy_ || !copy_) return cudaSuccess;
+        busy_ = false;
+        return cudaStreamSynchronize(copy_);
+    }
+
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+        workers_.clear();
+        stop_ = false;
+        if (ring_) cudaFreeHost(ring_);
+        ring_ = nullptr;
+        for (auto e : slot_ev_) cudaEventDestroy(e);
+        slot_ev_.clear();
+        if (done_) cudaEventDestroy(done_);
+        if (fence_) cudaEventDestroy(fence_);
+        if (copy_) cudaStreamDestroy(copy_);
+        done_ = fence_ = nullptr;
+        copy_ = nullptr;
+    }
+
+  private:
+    struct Piece {
+        char *dev;
+        char *host;
+        size_t len;
+    };
+    // Segments that are small or pinned are copied directly on `s`; the rest is cut into ring-sized pieces.
+    cudaError_t plan(const std::vector<Seg> &segs, cudaMemcpyKind kind, cudaStream_t s, std::vector<Piece> &pieces) {
+        size_t total = 0;
+        for (const Seg &g : segs) total += g.bytes;
+        for (const Seg &g : segs) {
+            if (g.bytes == 0) continue;
+            if (total < kMinStaged || !staged(g.host, g.bytes)) {
+                cudaError_t e = kind == cudaMemcpyHostToDevice ? cudaMemcpyAsync(g.dev, g.host, g.bytes, kind, s)
+                                                               : cudaMemcpyAsync(g.host, g.dev, g.bytes, kind, s);
+                if (e != cudaSuccess) return e;
+                continue;
+            }
+            for (size_t off = 0; off < g.bytes; off += kChunk)
+                pieces.push_back({(char *)g.dev + off, (char *)g.host + off, std::min(kChunk, g.bytes - off)});
+        }
+        return cudaSuccess;
+    }
+    bool staged(const void *host, size_t bytes) const {
+        (void)bytes;
+        if (nthreads_ <= 0) return false;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return true;
+        }
+        return a.type == cudaMemoryTypeUnregistered;  // pinned / managed memory goes to the DMA engine directly
+    }
+    cudaError_t ensure() {
+        if (ring_) return busy_ ? drain_keep() : cudaSuccess;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        device_ = dev;
+        cudaError_t e = cudaHostAlloc((void **)&ring_, kChunk * kSlots, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&done_, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&fence_, cudaEventDisableTiming)) != cudaSuccess) return e;
+        slot_ev_.resize(kSlots);
+        for (auto &ev : slot_ev_)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        for (int t = 0; t < nthreads_; t++) workers_.emplace_back([this] { loop(); });
+        return cudaSuccess;
+    }
+    // the ring still holds chunks of an earlier h2d whose DMAs may be in flight
+    cudaError_t drain_keep() {
+        busy_ = false;
+        return cudaStreamSynchronize(copy_);
+    }
+    // run fn(0..count-1) on the workers (and the calling thread) and wait
+    void run(size_t count, const std::function<void(size_t)> &fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &fn;
+            next_ = 0;
+            count_ = count;
+            pending_ = count;
+            epoch_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+    void work() {
+        for (;;) {
+            size_t i;
+            const std::function<void(size_t)> *fn;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!job_ || next_ >= count_) return;
+                i = next_++;
+                fn = job_;
+            }
+            (*fn)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        cudaSetDevice(device_);
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && job_ && next_ < count_); });
+                if (stop_) return;
+                seen = epoch_;
+            }
+            work();
+        }
+    }
+
+    int nthreads_;
+    int device_ = 0;
+    char *ring_ = nullptr;
+    cudaStream_t copy_ = nullptr;
+    cudaEvent_t done_ = nullptr, fence_ = nullptr;
+    std::vector<cudaEvent_t> slot_ev_;
+    bool busy_ = false;
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(size_t)> *job_ = nullptr;
+    size_t next_ = 0, count_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace h2b
