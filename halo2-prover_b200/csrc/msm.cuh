@@ -223,7 +223,7 @@ msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t
 //   piece kinds: DIRECT (bucket begins and ends inside the slice) -> bucket_sums[id]
 //                HEAD   (bucket began in an earlier slice)         -> head[s]
 //                TAIL   (bucket begins here, continues past the slice end) -> tail[s], tail_j[s] = j
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)  // 4 blocks per SM: the register budget is 128 (ncu: 3 blocks at 130 registers)
 msm_accumulate_kernel(const Affine *__restrict__ bases, const uint32_t *__restrict__ sorted,
                       const uint32_t *__restrict__ ne_off, const uint32_t *__restrict__ ne_id,
                       const uint32_t *__restrict__ totals, MsmCfg cfg, XYZZ *__restrict__ bucket_sums,
