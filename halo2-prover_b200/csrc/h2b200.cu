@@ -250,7 +250,7 @@ uint32_t srs_window_for(size_t n) {
     // of one or two bits sends every point to the same few buckets (hot atomics, buckets spanning thousands
     // of slices).  Small SRS are latency-bound: few buckets keep the reduction chains short.
     const uint32_t lg = ceil_log2(n);
-    if (lg <= 14) return lg >= 11 ? lg - 5 : 6;
+    if (lg <= 14) return lg >= 8 ? lg - 2 : 6;  // single commits are flat in c here (latency chains); batches want lg - 2
     if (lg <= 16) return 16;
     if (lg <= 18) return 17;
     if (lg <= 25) return 20;
