@@ -1164,10 +1164,14 @@ int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     return leave(g->stream, H2B_OK);
 }
 
-static int srs_register_locked(const void *bases, size_t n, uint64_t *handle);
+static int srs_register_locked(const void *bases, size_t n, uint64_t *handle, bool on_device = false);
 int h2b_srs_register(const uint64_t *bases, size_t n, uint64_t *handle) {
     std::lock_guard<std::mutex> lk(g_mu);
     return srs_register_locked(bases, n, handle);
+}
+int h2b_dev_srs_register(const void *d_bases, size_t n, uint64_t *handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return srs_register_locked(d_bases, n, handle, /*on_device=*/true);
 }
 // ParamsKZG::read, SerdeFormat::RawBytes (what ParamsKZG::write produces; the reference moves its SRS
 // between setup and prover in this form, /root/reference/circuits/src/wasm.rs:52, :79, :126):
@@ -1200,7 +1204,7 @@ int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k_out, uint64_t 
     *g_lagrange_handle = hl;
     return H2B_OK;
 }
-static int srs_register_locked(const void *bases, size_t n, uint64_t *handle) {
+static int srs_register_locked(const void *bases, size_t n, uint64_t *handle, bool on_device) {
     TRY(ensure_ctx());
     if (!bases || !handle || n == 0) return fail(H2B_ERR_ARG, "srs_register: bad argument");
     CU(cudaSetDevice(g->device));
@@ -1211,7 +1215,12 @@ static int srs_register_locked(const void *bases, size_t n, uint64_t *handle) {
         return fail(H2B_ERR_OOM, "cudaMalloc(srs)", e);
     }
     s.n = n;
-    e = g->copier->h2d(s.d, bases, n * sizeof(Affine), g->stream);
+    if (on_device) {
+        e = cudaDeviceSynchronize();  // the caller's producer of d_bases may run on any stream
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.d, bases, n * sizeof(Affine), cudaMemcpyDeviceToDevice, g->stream);
+    } else {
+        e = g->copier->h2d(s.d, bases, n * sizeof(Affine), g->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
     if (e != cudaSuccess) {
         cudaFree(s.d);

@@ -32,6 +32,23 @@ class ParamsKZG:
             self._handles[name] = h.value
 
     @classmethod
+    def from_device(cls, k: int, g_t, g_lagrange_t=None) -> "ParamsKZG":
+        """Bases already in HBM ((>= 2^k, 8) int64 cuda tensors): h2b_dev_srs_register."""
+        _ffi.init(g_t.device.index)
+        self = cls.__new__(cls)
+        self.k = k
+        self.n = 1 << k
+        self._handles = {}
+        for name, t in (("g", g_t), ("g_lagrange", g_lagrange_t)):
+            if t is None:
+                continue
+            assert t.shape[0] >= self.n
+            h = C.c_uint64(0)
+            _ffi.check(_ffi.lib().h2b_dev_srs_register(C.c_void_p(t.data_ptr()), C.c_size_t(t.shape[0]), C.byref(h)))
+            self._handles[name] = h.value
+        return self
+
+    @classmethod
     def read(cls, data) -> "ParamsKZG":
         """ParamsKZG::read (SerdeFormat::RawBytes): ``data`` is the byte string ParamsKZG::write produced
         (k | g | g_lagrange | g2 | s_g2); both base arrays are registered straight from it."""

@@ -122,6 +122,9 @@ int h2b_lagrange_to_coeff_many(const h2b_domain *d, uint64_t *const *cols, size_
 int h2b_coeff_to_extended_many(const h2b_domain *d, const uint64_t *const *in, uint64_t *const *out, size_t m);
 
 /* ---- device-resident variants (inputs/outputs already in HBM) ---------------------- */
+/* h2b_srs_register for bases that are already in HBM (n x 64 B on the library's device); the library keeps
+ * its own copy, the caller's buffer may be freed afterwards. */
+int h2b_dev_srs_register(const void *d_bases, size_t n, uint64_t *handle);
 int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out /* 96 B */, void *stream);
 /* ParamsKZG::commit with the polynomial already in HBM: d_coeffs (n x 32 B) against bases[0..n] of a
  * registered SRS (commitment.rs:319, :363); uses the SRS's precomputed window table when it has one. */

@@ -320,7 +320,19 @@ def test_max_size_msm_2p26_linearity(h2b, spec, href):
         arithmetic.dev_msm(b[: n // 2], bases[: n // 2], outs[3], stream=s)
         arithmetic.dev_msm(b[n // 2:], bases[n // 2:], outs[4], stream=s)
         s.synchronize()
+        # the same MSM as ParamsKZG::commit issues it: bases registered (from HBM), 2^26-point window table
+        from halo2_prover_b200 import kzg
+        s.synchronize()
+        params = kzg.ParamsKZG.from_device(26, bases)
+        outc = torch.empty((2, 12), dtype=torch.int64, device="cuda")
+        params.dev_commit(ab, outc[0], stream=s)
+        params.dev_commit(b[: n // 2], outc[1], stream=s)
+        s.synchronize()
+        params.release()
     o = outs.cpu().numpy().view(np.uint64)
+    oc = outc.cpu().numpy().view(np.uint64)
+    assert (href.g1_to_affine(oc[0]) == href.g1_to_affine(o[2])).all()
+    assert (href.g1_to_affine(oc[1]) == href.g1_to_affine(o[3])).all()
     assert (href.g1_to_affine(href.g1_add(o[0], o[1])) == href.g1_to_affine(o[2])).all()
     assert (href.g1_to_affine(href.g1_add(o[3], o[4])) == href.g1_to_affine(o[1])).all()
     assert spec.g1_is_on_curve(spec.projective_array_to_affine(o[2]))
