@@ -45,6 +45,16 @@ def g1_fold(points: np.ndarray) -> np.ndarray:
     return out
 
 
+def g1_to_bytes(points: np.ndarray) -> bytes:
+    """G1Affine::to_bytes of each projective point ((m,12) uint64): the 32-byte transcript encoding."""
+    points = _ffi.as_u64(points, 12)
+    _ffi.init()
+    out = np.zeros(points.shape[0] * 32, dtype=np.uint8)
+    _ffi.check(_ffi.lib().h2b_g1_to_bytes(_ffi.u64p(points), C.c_size_t(points.shape[0]),
+                                          out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out.tobytes()
+
+
 # ---- device-resident variants (torch tensors as raw 64-bit containers) ------------------------------
 def _ptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())

@@ -827,6 +827,25 @@ int dev_extended_to_coeff(const h2b_domain *d, const Fe *in, Fe *out, cudaStream
     return ntt_run(in, out, d->extended_k, d->extended_omega_inv, io, s, /*dst_full=*/false);
 }
 
+// G1Affine::to_bytes of halo2curves 0.3.2 (the 32-byte form the transcript writes for every commitment):
+// x as a canonical little-endian integer, bit 6 of byte 31 = y mod 2, the identity = 32 zero bytes
+// (format confirmed on the reference's own proof bytes, tests/test_wasm_golden.py).
+__global__ void g1_to_bytes_kernel(const Projective *__restrict__ pts, uint32_t m, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const Fe X = load_fe(&pts[i].x), Y = load_fe(&pts[i].y), Z = load_fe(&pts[i].z);
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!Fq::is_zero(Z)) {
+        const Fe zi = Fq::inv(Z);
+        const Fe x = Fq::from_mont(Fq::mul(X, zi)), y = Fq::from_mont(Fq::mul(Y, zi));
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = x.l[k];
+        w[7] |= (y.l[0] & 1u) << 30;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[(size_t)i * 8 + k] = w[k];
+}
+
 // ------------------------------------------------------------------------------ test kernels
 template <class F>
 __global__ void test_field_kernel(int op, const Fe *a, const Fe *b, Fe *o, uint32_t n) {
@@ -1330,6 +1349,20 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
                                                                          (Affine *)d_out);
     LAUNCHED();
     return leave(s, H2B_OK);
+}
+int h2b_g1_to_bytes(const uint64_t *points, size_t m, uint8_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (m == 0) return H2B_OK;
+    if (!points || !out) return fail(H2B_ERR_ARG, "g1_to_bytes: null pointer");
+    CU(cudaSetDevice(g->device));
+    void *dp = nullptr, *dout;
+    TRY(stage_in(BUF_TEST_A, points, m * 96, &dp));
+    TRY(get_buf(BUF_TEST_O, m * 32, &dout));
+    g1_to_bytes_kernel<<<(uint32_t)((m + 63) / 64), 64, 0, g->stream>>>((const Projective *)dp, (uint32_t)m, (uint32_t *)dout);
+    LAUNCHED();
+    TRY(copy_out(out, dout, m * 32, g->stream));
+    return leave(g->stream, H2B_OK);
 }
 int h2b_g1_fold(const uint64_t *points, size_t count, uint64_t out[12]) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -108,6 +108,11 @@ int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out
 /* EvaluationDomain::divide_by_vanishing_poly: a[i] *= t_evaluations[i % n_t], 2^extended_k, in place. */
 int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a);
 
+/* G1Affine::to_bytes (halo2curves 0.3.2) of m projective results: normalise, x as 32 little-endian canonical
+ * bytes with bit 6 of byte 31 = y mod 2, identity = zeros -- the bytes create_proof's transcript writes for a
+ * commitment (`transcript.write_point`).  points: m x 12 u64, out: m x 32 bytes. */
+int h2b_g1_to_bytes(const uint64_t *points, size_t m, uint8_t *out);
+
 /* m polynomials of n scalars each committed against bases[0..n] of ONE registered SRS in a single pass
  * (the A advice columns, the permutation products or the h pieces of create_proof, which upstream
  * commits one by one: plonk/prover.rs advice `.map(|poly| params.commit_lagrange(poly, blind))`).

@@ -144,3 +144,56 @@ def test_params_read_from_reference_setup_bytes(name, h2b, href):
     for bad in (b"", b"\x04\x00\x00", z["params"].tobytes()[:-1]):
         with pytest.raises(Exception):
             h2b.ParamsKZG.read(bad)
+
+
+def _compress(spec, aff8):
+    """G1Affine::to_bytes restated: x little-endian, bit 6 of byte 31 = y & 1, identity = zeros."""
+    p = spec.array_to_affine(np.asarray(aff8).reshape(1, 8))[0]
+    if p is None:
+        return bytes(32)
+    b = bytearray(p[0].to_bytes(32, "little"))
+    b[31] |= (p[1] & 1) << 6
+    return bytes(b)
+
+
+# (circuit, first MSM record, number of records, first 32-byte chunk of the proof they fill): the commitments
+# create_proof writes before the evaluations, and the opening-proof points after them
+PROOF_POINT_RUNS = [("arithmetic", 9, 10, 0), ("arithmetic", 19, 3, 34), ("poseidon", 16, 12, 0), ("poseidon", 28, 4, 44)]
+
+
+@pytest.mark.parametrize("name,first,count,chunk", PROOF_POINT_RUNS)
+def test_reference_proof_bytes_are_the_recorded_commitments(name, first, count, chunk, spec):
+    """Every group element in the reference's proof is the compression of a recorded best_multiexp result, in
+    call order: the proof bytes are determined by this path's outputs (plus field evaluations)."""
+    ent, z, g, gl = _load(name)
+    proof = z["proof"].tobytes()
+    want = proof[32 * chunk: 32 * (chunk + count)]
+    got = b"".join(_compress(spec, z[f"msm{i}_affine"]) for i in range(first, first + count))
+    assert got == want
+    if name == "arithmetic":  # 13 points + 24 scalars = the whole 1184-byte proof
+        assert len(proof) == 32 * 37
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,first,count,chunk", PROOF_POINT_RUNS)
+def test_cuda_reproduces_reference_proof_bytes(name, first, count, chunk, h2b, href):
+    """The same bytes from the CUDA path: SRS read from the reference's params bytes, the recorded scalars
+    committed on the GPU (one batch per base array), results encoded by h2b_g1_to_bytes."""
+    ent, z, g, gl = _load(name)
+    params = h2b.ParamsKZG.read(z["params"].tobytes())
+    recs = {m["i"]: m for m in ent["msm"]}
+    proof = z["proof"].tobytes()
+    out = {}
+    by_kind = {}
+    for i in range(first, first + count):
+        by_kind.setdefault((recs[i]["bases"], recs[i]["n"]), []).append(i)
+    for (kind, n), idxs in by_kind.items():
+        cols = [np.ascontiguousarray(z[f"msm{i}_scalars"]) for i in idxs]
+        pts = params.commit_many(cols) if kind == "g" else params.commit_lagrange_many(cols)
+        enc = h2b.g1_to_bytes(pts)
+        for j, i in enumerate(idxs):
+            out[i] = enc[32 * j: 32 * j + 32]
+    got = b"".join(out[i] for i in range(first, first + count))
+    assert got == proof[32 * chunk: 32 * (chunk + count)]
+    assert h2b.g1_to_bytes(np.array([[0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0]], dtype=np.uint64)) == bytes(32)  # identity
+    params.release()
