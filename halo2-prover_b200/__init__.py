@@ -17,8 +17,8 @@ G1Affine: 8 limbs; G1: 12 limbs homogeneous projective).  There is no CPU fallba
 works anywhere, computing requires the CUDA library and a GPU and raises otherwise.
 """
 from . import _ffi  # noqa: F401
-from .arithmetic import best_fft, best_multiexp, g1_fold, g1_to_bytes  # noqa: F401
+from .arithmetic import best_fft, best_multiexp, g1_fold, g1_to_bytes, g_to_lagrange  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
 from .kzg import ParamsKZG  # noqa: F401
 
-__all__ = ["best_multiexp", "best_fft", "g1_fold", "g1_to_bytes", "EvaluationDomain", "ParamsKZG"]
+__all__ = ["best_multiexp", "best_fft", "g1_fold", "g1_to_bytes", "g_to_lagrange", "EvaluationDomain", "ParamsKZG"]

@@ -45,6 +45,16 @@ def g1_fold(points: np.ndarray) -> np.ndarray:
     return out
 
 
+def g_to_lagrange(g: np.ndarray, k: int) -> np.ndarray:
+    """arithmetic::g_to_lagrange: the Lagrange-basis SRS ((2^k, 8) uint64 affine) from the monomial one."""
+    g = _ffi.as_u64(g, 8)
+    assert g.shape[0] == 1 << k, "assert_eq!(g.len(), 1 << k)"
+    _ffi.init()
+    out = np.zeros_like(g)
+    _ffi.check(_ffi.lib().h2b_g_to_lagrange(_ffi.u64p(g), C.c_uint32(k), _ffi.u64p(out)))
+    return out
+
+
 def g1_to_bytes(points: np.ndarray) -> bytes:
     """G1Affine::to_bytes of each projective point ((m,12) uint64): the 32-byte transcript encoding."""
     points = _ffi.as_u64(points, 12)

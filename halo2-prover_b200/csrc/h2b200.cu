@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "curve.cuh"
+#include "ecntt.cuh"
 #include "hostcopy.h"
 #include "field.cuh"
 #include "msm.cuh"
@@ -38,7 +39,7 @@ std::mutex g_mu;
 
 enum BufId {
     BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_CURSOR, BUF_NEOFF, BUF_NEID, BUF_SORTED, BUF_DIGITS, BUF_HEAD, BUF_TAIL,
-    BUF_TAILJ, BUF_TOTALS,
+    BUF_TAILJ, BUF_TOTALS, BUF_ECNTT,
     BUF_BUCKETS, BUF_BUCKETS2, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
     BUF_NTT_OUT, BUF_MISC,
     BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
@@ -1348,6 +1349,39 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
     g1_fixed_base_mul_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>((const Fe *)d_scalars, (uint32_t)n, b,
                                                                          (Affine *)d_out);
     LAUNCHED();
+    return leave(s, H2B_OK);
+}
+int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!g_bases || !out) return fail(H2B_ERR_ARG, "g_to_lagrange: null pointer");
+    if (k > 26) return fail(H2B_ERR_ARG, "g_to_lagrange: k > 26");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = g->stream;
+    TRY(enter(s));
+    const size_t n = (size_t)1 << k;
+    h2b_domain d;
+    TRY(domain_build(3, k, &d));  // omega_inv and 1/2^k do not depend on j
+    void *din;
+    XYZZ *work;
+    Affine *dout;
+    TRY(stage_in(BUF_BASES, g_bases, n * sizeof(Affine), &din));
+    TRY(get_buf(BUF_ECNTT, n * sizeof(XYZZ), (void **)&work));
+    TRY(get_buf(BUF_TEST_O, n * sizeof(Affine), (void **)&dout));
+    const Fe *W = nullptr;
+    if (k > 0) TRY(get_twiddles(d.omega_inv, k, s, &W));
+    const uint32_t blocks = (uint32_t)((n + 127) / 128);
+    ec_ntt_load_kernel<<<blocks, 128, 0, s>>>((const Affine *)din, k, work);
+    LAUNCHED();
+    for (uint32_t st = 0; st < k; st++) {
+        ec_ntt_stage_kernel<<<(uint32_t)((n / 2 + 127) / 128), 128, 0, s>>>(work, k, st, W);
+        LAUNCHED();
+    }
+    Fe scale;
+    memcpy(&scale, d.ifft_divisor, 32);
+    ec_ntt_finish_kernel<<<blocks, 128, 0, s>>>(work, (uint32_t)n, scale, dout);
+    LAUNCHED();
+    TRY(copy_out(out, dout, n * sizeof(Affine), s));
     return leave(s, H2B_OK);
 }
 int h2b_g1_to_bytes(const uint64_t *points, size_t m, uint8_t *out) {

@@ -108,6 +108,10 @@ int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out
 /* EvaluationDomain::divide_by_vanishing_poly: a[i] *= t_evaluations[i % n_t], 2^extended_k, in place. */
 int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a);
 
+/* g_to_lagrange (halo2_proofs arithmetic.rs; the G = G1 instantiation of best_fft with omega_inv, the
+ * 1/2^k scaling and the normalisation): g_lagrange from g, as ParamsKZG::{setup, from_parts} need it
+ * (kzg/commitment.rs:68-114).  g_bases and out: 2^k x 8 u64 affine points. */
+int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out);
 /* G1Affine::to_bytes (halo2curves 0.3.2) of m projective results: normalise, x as 32 little-endian canonical
  * bytes with bit 6 of byte 31 = y mod 2, identity = zeros -- the bytes create_proof's transcript writes for a
  * commitment (`transcript.write_point`).  points: m x 12 u64, out: m x 32 bytes. */

@@ -336,3 +336,18 @@ def test_max_size_msm_2p26_linearity(h2b, spec, href):
     assert (href.g1_to_affine(href.g1_add(o[0], o[1])) == href.g1_to_affine(o[2])).all()
     assert (href.g1_to_affine(href.g1_add(o[3], o[4])) == href.g1_to_affine(o[1])).all()
     assert spec.g1_is_on_curve(spec.projective_array_to_affine(o[2]))
+
+
+@pytest.mark.parametrize("k", [0, 1, 3, 8])
+def test_g_to_lagrange_vs_oracle_msm(h2b, spec, href, k):
+    """g_lagrange[i] = sum_j [omega^(-ij) / n] g[j] on random bases (with an identity among them)."""
+    n = 1 << k
+    g = href.random_g1(n, 700 + k)
+    if n > 4:
+        g[2] = 0
+    got = h2b.g_to_lagrange(g, k)
+    w_inv = pow(pow(spec.ROOT_OF_UNITY, 1 << (28 - k), spec.R_MOD), -1, spec.R_MOD)
+    n_inv = pow(n, -1, spec.R_MOD)
+    for i in sorted({0, 1 % n, (n // 2 + 1) % n, n - 1}):
+        sc = spec.fr_array([pow(w_inv, i * j, spec.R_MOD) * n_inv % spec.R_MOD for j in range(n)])
+        assert (_affine(href, href.best_multiexp(sc, g)) == got[i]).all(), i

@@ -197,3 +197,25 @@ def test_cuda_reproduces_reference_proof_bytes(name, first, count, chunk, h2b, h
     assert got == proof[32 * chunk: 32 * (chunk + count)]
     assert h2b.g1_to_bytes(np.array([[0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0]], dtype=np.uint64)) == bytes(32)  # identity
     params.release()
+
+
+def test_reference_g_lagrange_is_the_group_ifft_of_g(href, spec):
+    """In the reference's setup() bytes, g_lagrange[i] = sum_j [omega^(-ij) / n] g[j] (checked for a few i with the
+    oracle's MSM): the relation g_to_lagrange computes."""
+    ent, z, g, gl = _load("arithmetic")
+    k = ent["k"]
+    n = 1 << k
+    w_inv = pow(pow(spec.ROOT_OF_UNITY, 1 << (28 - k), spec.R_MOD), -1, spec.R_MOD)
+    n_inv = pow(n, -1, spec.R_MOD)
+    for i in (0, 1, 5, n - 1):
+        sc = spec.fr_array([pow(w_inv, i * j, spec.R_MOD) * n_inv % spec.R_MOD for j in range(n)])
+        assert (href.g1_to_affine(href.best_multiexp(sc, g)) == gl[i]).all(), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+def test_cuda_g_to_lagrange_reproduces_reference_params(name, h2b):
+    """h2b_g_to_lagrange on the g of the reference's params bytes == the g_lagrange in the same bytes
+    (k = 4, 7 and 10), limb for limb."""
+    ent, z, g, gl = _load(name)
+    assert (h2b.g_to_lagrange(g, ent["k"]) == gl).all()
