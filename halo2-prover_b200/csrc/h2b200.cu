@@ -297,6 +297,16 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     size_t entries = m * cfg.cols * cfg.windows;
     uint32_t L = 512;  // slice: enough slices to fill the GPU several times over, at most 512 entries
     while (L > 16 && entries / L < (size_t)g->sm_count * 2048) L >>= 1;
+    if (L == 512) {
+        // every slice is the same amount of work and 4 blocks of 128 slices are resident per SM, so the
+        // launch runs in lockstep waves: size the slices so that the last wave is full
+        // (2^24 x 13 entries: 3329 blocks = 5.6 waves at L = 512, 3550 blocks = 6.0 waves at L = 480)
+        const size_t per_wave = (size_t)g->sm_count * 4 * 128;
+        size_t waves = entries / (per_wave * 512);            // round down if the slices stay <= 640 entries
+        if (waves == 0 || (entries + waves * per_wave - 1) / (waves * per_wave) > 640) waves++;
+        const size_t fit = (entries + waves * per_wave - 1) / (waves * per_wave);
+        if (fit >= 64 && fit <= 640) L = (uint32_t)fit;
+    }
     cfg.slice = L;
     size_t max_slices = entries / cfg.slice + 1;
     uint32_t *counts, *cursor, *ne_off, *ne_id, *sorted, *totals, *heavy, *digits;
