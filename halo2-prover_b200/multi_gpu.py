@@ -70,3 +70,40 @@ def sharded_commit(params, coeffs_local, which: str = "g", group=None, stream=No
     out = torch.empty(12, dtype=torch.int64, device=dev)
     dev_g1_fold(parts, out, stream=stream)
     return out
+
+
+def column_owner(q: int, world: int) -> int:
+    """Rank that commits / transforms column ``q`` when independent columns are spread over GPUs."""
+    return q % world
+
+
+def commit_columns(commit_many_fn, cols, group=None, device=None):
+    """Independent per-column commitments scheduled across ranks (north_star: small MSMs do not shard, whole
+    columns are dealt round-robin instead).  ``commit_many_fn(list_of_columns) -> (m, 12) uint64 array`` is this
+    rank's batched commit (``ParamsKZG.commit_many`` with the full SRS registered on every rank); every rank
+    returns all ``len(cols)`` results in column order.  The only exchange is one all_gather of the padded
+    per-rank results."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    m = len(cols)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = [q for q in range(m) if column_owner(q, world) == rank]
+    out_local = np.asarray(commit_many_fn([cols[q] for q in mine]), dtype=np.uint64).reshape(len(mine), 12)
+    if world == 1:
+        return out_local
+    per = (m + world - 1) // world
+    pad = np.zeros((per, 12), dtype=np.uint64)
+    pad[: len(mine)] = out_local
+    t = torch.from_numpy(pad.view(np.int64))
+    if device is not None:
+        t = t.to(device)
+    gathered = torch.empty((world, per, 12), dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(gathered.view(-1), t.contiguous().view(-1), group=group)
+    g = gathered.cpu().numpy().view(np.uint64)
+    res = np.zeros((m, 12), dtype=np.uint64)
+    for q in range(m):
+        res[q] = g[column_owner(q, world), q // world]
+    return res

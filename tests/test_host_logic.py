@@ -67,3 +67,44 @@ def test_sharded_msm_gather_gloo_world2():
     sc, pts = h2ref.random_fr(n, 11), h2ref.random_g1(n, 12)
     want = h2ref.g1_to_affine(h2ref.best_multiexp(sc, pts, 1)).tolist()
     assert res[0] == want and res[1] == want
+
+
+def _col_worker(rank, world, port, m, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "oracle")]
+    import torch.distributed as dist
+    import h2ref
+    from halo2_prover_b200.multi_gpu import commit_columns
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 32
+    pts = h2ref.random_g1(n, 21)
+    cols = [h2ref.random_fr(n, 30 + c) for c in range(m)]
+    # the per-rank batched commit is the GPU's job; the checker stands in so the scheduling is tested on CPU
+    fn = lambda cs: np.stack([h2ref.best_multiexp(c, pts, 1) for c in cs]) if cs else np.zeros((0, 12), dtype=np.uint64)
+    res = commit_columns(fn, cols)
+    q.put((rank, [h2ref.g1_to_affine(r).tolist() for r in res]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m", [1, 5])
+def test_columns_round_robin_gloo_world2(m):
+    """Independent columns dealt round-robin over two ranks: every rank ends with every commitment, in order."""
+    import torch.multiprocessing as mp
+    import h2ref
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_col_worker, args=(r, world, port, m, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pts = h2ref.random_g1(32, 21)
+    want = [h2ref.g1_to_affine(h2ref.best_multiexp(h2ref.random_fr(32, 30 + c), pts, 1)).tolist() for c in range(m)]
+    assert res[0] == want and res[1] == want
