@@ -149,6 +149,36 @@ def test_commit_precomputed_window_table(h2b, spec, href, srs_c):
         _ffi.check(_ffi.lib().h2b_set_srs_precompute(1, 0))
 
 
+def test_commit_table_collisions_and_odd_srs_length(h2b, spec, href):
+    """Table path with an SRS whose length is not a power of two, duplicated bases (P + P inside a bucket),
+    a base and its negative under equal scalars (P - P), and scalars that differ only in sign."""
+    import ctypes as C
+    from halo2_prover_b200 import _ffi
+    n = 777
+    g = href.random_g1(n, 401)
+    g[11] = g[10]
+    neg = spec.array_to_affine(g[13:14])[0]
+    g[12] = spec.affine_to_array([(neg[0], spec.Q_MOD - neg[1])])[0]
+    sc = href.random_fr(n, 402)
+    sc[11] = sc[10]
+    sc[12] = sc[13]
+    r_minus = lambda a: spec.fr_array([(spec.R_MOD - v) % spec.R_MOD for v in spec.fr_ints(a.reshape(1, 4))])[0]
+    sc[20] = r_minus(sc[21])
+    g[20] = g[21]                      # s * P + (-s) * P
+    h = C.c_uint64(0)
+    _ffi.check(_ffi.lib().h2b_srs_register(_ffi.u64p(g), C.c_size_t(n), C.byref(h)))
+    try:
+        for m in (n, 500, 1):
+            out = np.zeros(12, dtype=np.uint64)
+            _ffi.check(_ffi.lib().h2b_commit(h, _ffi.u64p(np.ascontiguousarray(sc[:m])), C.c_size_t(m), _ffi.u64p(out)))
+            assert (_affine(href, out) == _affine(href, href.best_multiexp(sc[:m].copy(), g[:m].copy()))).all(), m
+        out = np.zeros(12, dtype=np.uint64)
+        rc = _ffi.lib().h2b_commit(h, _ffi.u64p(np.ascontiguousarray(href.random_fr(n + 1, 5))), C.c_size_t(n + 1), _ffi.u64p(out))
+        assert rc != 0  # bases.len() < size
+    finally:
+        _ffi.check(_ffi.lib().h2b_srs_release(h))
+
+
 def test_dev_commit_matches_best_multiexp_2p18(h2b, spec, href):
     """Device-resident commit (h2b_dev_commit) over a 2^18-point SRS == the oracle's best_multiexp."""
     import ctypes as C
