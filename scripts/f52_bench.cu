@@ -6,6 +6,7 @@
 #include <vector>
 #include "../halo2-prover_b200/csrc/field.cuh"
 #include "../halo2-prover_b200/csrc/field52.cuh"
+#include "karatsuba_experiment.cuh"
 using namespace h2b;
 
 #define CHAINS 4
@@ -19,6 +20,22 @@ __global__ void __launch_bounds__(128) k_mul_i(const Fe *in, Fe *out, int iters)
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int c = 0; c < CHAINS; c++) x[c] = Fq::mul(x[c], y);
+    }
+    Fe r = x[0];
+#pragma unroll
+    for (int c = 1; c < CHAINS; c++) r = Fq::add(r, x[c]);
+    store_fe(&out[t], r);
+}
+
+__global__ void __launch_bounds__(128) k_mul_k(const Fe *in, Fe *out, int iters) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    Fe x[CHAINS], y = load_fe(&in[t]);
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) x[c] = load_fe(&in[t + 1 + c]);
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; c++) x[c] = mul_karatsuba<FqP>(x[c], y);
     }
     Fe r = x[0];
 #pragma unroll
@@ -109,6 +126,24 @@ int main(int argc, char **argv) {
         cudaEventRecord(e1);
         cudaDeviceSynchronize();
         cudaEventElapsedTime(&ms_i, e0, e1);
+        {
+            float ms_k;
+            std::vector<Fe> ri(threads), rk(threads);
+            cudaMemcpy(ri.data(), doi, threads * sizeof(Fe), cudaMemcpyDeviceToHost);
+            k_mul_k<<<blocks, 128>>>(di, doi, 10);
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0);
+            k_mul_k<<<blocks, 128>>>(di, doi, iters);
+            cudaEventRecord(e1);
+            cudaDeviceSynchronize();
+            cudaEventElapsedTime(&ms_k, e0, e1);
+            cudaMemcpy(rk.data(), doi, threads * sizeof(Fe), cudaMemcpyDeviceToHost);
+            int bad = 0;
+            for (int t = 0; t < threads; t++)
+                for (int i = 0; i < 8; i++) bad += ri[t].l[i] != rk[t].l[i];
+            printf("%d blocks/SM: Karatsuba form %.3f ms (%.1f G modmul/s), ratio to IMAD form %.3f, results %s\n", bpsm, ms_k,
+                   (double)threads * CHAINS * iters / ms_k * 1e-6, ms_i / ms_k, bad ? "DIFFER" : "identical");
+        }
         cudaEventRecord(e0);
         k_mulonly_f<<<blocks, 128>>>(df, dof, iters);
         cudaEventRecord(e1);
