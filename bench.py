@@ -57,7 +57,10 @@ def rand_fr_np(n: int, seed: int) -> np.ndarray:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The process is started before the warm-up
+    steps (it takes a few hundred ms to deliver its first row) and only the rows that arrive between
+    mark_begin() and stop() -- the timed region -- are reported; if the region is shorter than the sampling
+    allows, the rows taken under the warm-up load stand in and the report says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -67,7 +70,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -76,7 +79,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self) -> dict:
         if not self.proc:
@@ -86,9 +92,16 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        t_end = time.perf_counter()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_begin = getattr(self, "t_begin", 0.0)
+        timed = [r for t, r in self.rows if t_begin <= t <= t_end + 0.05]
+        window = "timed region"
+        if not timed:
+            timed = [r for _, r in self.rows][-8:]
+            window = "warm-up and timed region (timed region shorter than the sampling interval)"
+        for r in timed:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -98,7 +111,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def measured_peaks() -> dict:
@@ -210,12 +223,14 @@ def run_b200(args) -> None:
         imad, imad_w, _mhz = C.c_double(), C.c_double(), C.c_double()
         _ffi.check(L.h2b_imad_peak(C.byref(imad), C.byref(imad_w), C.byref(_mhz)))
 
+        sampler = ClockSampler(local) if rank == 0 else None
         for _ in range(max(args.warmup, 3)):
             step()
         stream.synchronize()
         if world > 1:
             dist.barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.mark_begin()
         _ffi.check(L.h2b_set_kernel_timing(1))
         launches0 = L.h2b_kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -343,10 +358,10 @@ def run_b200(args) -> None:
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TIMAD/s", "frac": (achieved / peak) if achieved and peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 / 13 windows from the
-                         # committed capture profiles/r01_ncu_full_commit_accumulate_v4.md (ncu cannot run inside the
+                         # committed capture profiles/r01_ncu_full_commit_accumulate_v6.md (ncu cannot run inside the
                          # timed bench); only quoted for the configuration it was captured on
-                         "traffic": 29.22e9 if (args.log_n == 24 and srs_w.value == 13) else None,
-                         "traffic_source": "profiles/r01_ncu_full_commit_accumulate_v4.md (ncu --set full, per launch)",
+                         "traffic": 29.40e9 if (args.log_n == 24 and srs_w.value == 13) else None,
+                         "traffic_source": "profiles/r01_ncu_full_commit_accumulate_v6.md (ncu --set full, per launch)",
                          "launch_ms": acc_ms,
                          "algorithmic": "43,520 IMAD-class/point (160 modmul x 272) x 2^%d points per launch" % args.log_n,
                          "executed": {"achieved": executed, "frac": (executed / peak) if executed and peak else None,
