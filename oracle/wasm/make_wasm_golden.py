@@ -32,7 +32,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 # (name, circuit index in wasm.rs:82-119, k, input JSON, RNG seed, keep-all?)
 # Collatz needs k = 10 (NotEnoughRowsAvailable below that; the web demo uses setup(10),
 # src/components/Circuits.tsx:90); its 7 MB of records are all CHECKED here but only a sample is
-# committed (first three MSMs of each size, first two FFTs of each log_n) to keep fixtures small.
+# committed (every MSM against the SRS, first three MSMs of each size with their own bases, first two
+# FFTs of each log_n) to keep fixtures small.
 RUNS = [
     ("arithmetic", 1, 4, '{"x": 6, "y": 9, "constant": 7, "z": 2923}', 12345, True),
     ("poseidon", 2, 7, '{"x": [1, 2]@SIMULATE@}', 4242, True),
@@ -102,15 +103,18 @@ def main():
                     sp = spec.msm_naive(spec.fr_ints(sc), spec.array_to_affine(bs))
                     assert (spec.affine_to_array([sp])[0] == want_aff).all(), "big-integer spec disagrees"
                 seen_msm[m] = seen_msm.get(m, 0) + 1
-                if not keep_all and seen_msm[m] > 3:
-                    n_msm += 1
-                    continue
                 if m <= n and (bs == g[:m]).all():
                     src = "g"
                 elif m <= n and (bs == gl[:m]).all():
                     src = "g_lagrange"
                 else:
                     src = "explicit"
+                # records against the SRS cost only their scalars: keep them all (the proof-byte tests need every
+                # commitment); records with their own bases are sampled when the run is large
+                if not keep_all and src == "explicit" and seen_msm[m] > 3:
+                    n_msm += 1
+                    continue
+                if src == "explicit":
                     arrays[f"msm{n_msm}_bases"] = bs
                 arrays[f"msm{n_msm}_scalars"] = sc
                 arrays[f"msm{n_msm}_affine"] = want_aff

@@ -158,7 +158,8 @@ def _compress(spec, aff8):
 
 # (circuit, first MSM record, number of records, first 32-byte chunk of the proof they fill): the commitments
 # create_proof writes before the evaluations, and the opening-proof points after them
-PROOF_POINT_RUNS = [("arithmetic", 9, 10, 0), ("arithmetic", 19, 3, 34), ("poseidon", 16, 12, 0), ("poseidon", 28, 4, 44)]
+PROOF_POINT_RUNS = [("arithmetic", 9, 10, 0), ("arithmetic", 19, 3, 34), ("poseidon", 16, 12, 0), ("poseidon", 28, 4, 44),
+                    ("collatz", 3, 8, 0), ("collatz", 11, 2, 18)]  # collatz: SHPLONK, 10 points + 10 scalars = 640 bytes
 
 
 @pytest.mark.parametrize("name,first,count,chunk", PROOF_POINT_RUNS)
@@ -172,6 +173,8 @@ def test_reference_proof_bytes_are_the_recorded_commitments(name, first, count, 
     assert got == want
     if name == "arithmetic":  # 13 points + 24 scalars = the whole 1184-byte proof
         assert len(proof) == 32 * 37
+    if name == "collatz":
+        assert len(proof) == 32 * 20
 
 
 @pytest.mark.gpu
