@@ -23,6 +23,7 @@
 #include "hostcopy.h"
 #include "field.cuh"
 #include "msm.cuh"
+#include "msm_comb.cuh"
 #include "ntt.cuh"
 
 using namespace h2b;
@@ -59,6 +60,9 @@ struct Srs {
     size_t n = 0;
     Affine *table = nullptr;  // precomputed windows: table[w * n + i] = 2^(c*w) * d[i], or null
     uint32_t c = 0, windows = 0;
+    // small SRS: every multiple d * 2^(comb_c * w) * d[i], d <= 2^(comb_c - 1) (msm_comb.cuh), or null
+    Affine *comb = nullptr;
+    uint32_t comb_c = 0, comb_w = 0;
 };
 
 struct Ctx {
@@ -74,6 +78,8 @@ struct Ctx {
     uint64_t launches = 0;
     uint32_t msm_window = 0;
     uint32_t reduce_lgrp = 0;  // tuning override (H2B_REDUCE_LGRP)
+    size_t comb_max_n = (size_t)1 << 14;  // registered SRS up to this length get the bucket-free table
+    uint32_t comb_c = 8;
     double e2e_ratio = 0;      // growth of the host-path chunk sizes (0 = automatic)
     uint32_t srs_window = 0;   // 0 = automatic
     int srs_precompute = 1;
@@ -997,7 +1003,7 @@ int h2b_init(int device) {
     const char *er = getenv("H2B_E2E_RATIO");
     if (er) c->e2e_ratio = atof(er);
     const char *sp = getenv("H2B_SRS_PRECOMPUTE");
-    if (sp) c->srs_precompute = atoi(sp) != 0;
+    if (sp) c->srs_precompute = atoi(sp);
     const char *ec = getenv("H2B_E2E_CHUNKS");
     if (ec) {
         int v = atoi(ec);
@@ -1017,6 +1023,7 @@ void h2b_shutdown(void) {
     for (auto &kv : g->srs) {
         cudaFree(kv.second.d);
         if (kv.second.table) cudaFree(kv.second.table);
+        if (kv.second.comb) cudaFree(kv.second.comb);
     }
     for (auto &kv : g->twiddles) cudaFree(kv.second);
     for (auto e : g->tev0) cudaEventDestroy(e);
@@ -1042,7 +1049,7 @@ int h2b_set_srs_precompute(int enabled, uint32_t c) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
     if (c != 0 && (c < 2 || c > 24)) return fail(H2B_ERR_ARG, "srs window must be 0 or in [2, 24]");
-    g->srs_precompute = enabled != 0;
+    g->srs_precompute = enabled;  // 0: none, 1: automatic (bucket-free table up to 2^14 points), 2: window table only
     g->srs_window = c;
     return H2B_OK;
 }
@@ -1093,6 +1100,7 @@ int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out
     return leave(s, msm_run((const Fe *)d_coeffs, (const Affine *)d_bases, n, (Projective *)d_out, s));
 }
 
+int commit_many_device(const Srs &sr, const Fe *d_scalars, size_t n, size_t m, Projective *d_out, cudaStream_t s);
 int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
@@ -1105,11 +1113,67 @@ int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out, vo
     TRY(enter(s));
     if (n == 0) return leave(s, msm_identity_out((Projective *)d_out, s));
     const Srs &sr = it->second;
+    if (sr.comb) return leave(s, commit_many_device(sr, (const Fe *)d_coeffs, n, 1, (Projective *)d_out, s));
     MsmRun run;
     int rc = msm_begin(n, &run, s, &sr);
     if (rc == H2B_OK) rc = msm_chunk(run, (const Fe *)d_coeffs, sr.table ? sr.table : sr.d, n, s, 0);
     if (rc == H2B_OK) rc = msm_finish(run, (Projective *)d_out, s);
     return leave(s, rc);
+}
+
+// Bucket-free commit of `cols` columns against a small SRS (msm_comb.cuh): digits -> table indices, slice sums,
+// a binary tree over the slice sums.
+int comb_commit(const Srs &sr, const Fe *d_scalars, size_t n, size_t cols, Projective *d_out, cudaStream_t s) {
+    MsmCfg cfg{};
+    cfg.n = (uint32_t)n;
+    cfg.cols = (uint32_t)cols;
+    cfg.c = sr.comb_c;
+    cfg.windows = sr.comb_w;
+    cfg.bpw = 1u << (sr.comb_c - 1);
+    cfg.stride = (uint32_t)sr.n;
+    for (uint32_t w = 0; w + 1 < cfg.windows; w++) {
+        const uint32_t bit = cfg.c * w + cfg.c - 1;
+        cfg.half[bit >> 5] |= 1u << (bit & 31);
+    }
+    const size_t per_col = n * cfg.windows, total = per_col * cols;
+    uint32_t *entries;
+    TRY(get_buf(BUF_SORTED, total * 4, (void **)&entries));
+    msm_comb_digits_kernel<<<(uint32_t)((n * cols + 255) / 256), 256, 0, s>>>(d_scalars, cfg, entries);
+    LAUNCHED();
+    // ~2^17 slice sums in flight: short enough chains, few enough tree levels
+    size_t L = (total + (1u << 17) - 1) >> 17;
+    if (L < 2) L = 2;
+    if (L > 64) L = 64;
+    const size_t slices = (per_col + L - 1) / L;
+    XYZZ *pa, *pb;
+    TRY(get_buf(BUF_HEAD, cols * slices * sizeof(XYZZ), (void **)&pa));
+    time_begin(s);
+    msm_comb_sum_kernel<<<dim3((uint32_t)((slices + 127) / 128), (uint32_t)cols), 128, 0, s>>>(
+        sr.comb, entries, (uint32_t)per_col, (uint32_t)L, (uint32_t)slices, pa);
+    LAUNCHED();
+    time_end(s);
+    size_t count = slices;
+    TRY(get_buf(BUF_TAIL, cols * ((count + 255) / 256 + 1) * sizeof(XYZZ), (void **)&pb));
+    XYZZ *src = pa, *dst = pb;
+    while (count > 1) {
+        uint32_t nt = 256, pt = 1;
+        size_t blocks;
+        if (count <= 256) {
+            nt = 32;
+            while (nt < count) nt <<= 1;
+            blocks = 1;
+        } else {
+            pt = (uint32_t)((count + 65535) / 65536);  // at most 256 blocks remain after this level group
+            blocks = (count + (size_t)nt * pt - 1) / ((size_t)nt * pt);
+        }
+        msm_comb_tree_kernel<<<dim3((uint32_t)blocks, (uint32_t)cols), nt, nt * sizeof(XYZZ), s>>>(src, (uint32_t)count, pt, dst);
+        LAUNCHED();
+        count = blocks;
+        std::swap(src, dst);
+    }
+    msm_batch_out_kernel<<<(uint32_t)((cols + 31) / 32), 32, 0, s>>>(src, (uint32_t)cols, d_out);
+    LAUNCHED();
+    return H2B_OK;
 }
 
 // m polynomials of n scalars each (device, one after the other) against bases[0..n] of one SRS.  With a window
@@ -1119,6 +1183,14 @@ int commit_many_device(const Srs &sr, const Fe *d_scalars, size_t n, size_t m, P
     if (m == 0) return H2B_OK;
     if (n == 0) {
         for (size_t q = 0; q < m; q++) TRY(msm_identity_out(d_out + q, s));
+        return H2B_OK;
+    }
+    if (sr.comb) {
+        const size_t per_col = n * sr.comb_w;
+        size_t step = m;
+        while (step > 1 && step * per_col > ((size_t)1 << 27)) step = (step + 1) / 2;
+        for (size_t q0 = 0; q0 < m; q0 += step)
+            TRY(comb_commit(sr, d_scalars + q0 * n, n, std::min(step, m - q0), d_out + q0, s));
         return H2B_OK;
     }
     if (!sr.table) {  // no table: one MSM per column
@@ -1225,6 +1297,7 @@ int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k_out, uint64_t 
         if (it != g->srs.end()) {
             cudaFree(it->second.d);
             if (it->second.table) cudaFree(it->second.table);
+            if (it->second.comb) cudaFree(it->second.comb);
             g->srs.erase(it);
         }
         return rc;
@@ -1258,7 +1331,34 @@ static int srs_register_locked(const void *bases, size_t n, uint64_t *handle, bo
     }
     // Static bases: precompute 2^(c*w) * P_i once so that every window of a commit feeds ONE bucket set
     // (fewer, wider windows; no Horner).  Skipped when the table would not fit comfortably.
-    if (g->srs_precompute && n >= 2) {
+    if (g->srs_precompute == 1 && g->srs_window == 0 && n <= g->comb_max_n) {
+        // small SRS (the reference's circuits: k <= 14): bucket-free table of all window multiples
+        const uint32_t c = g->comb_c, W = msm_windows_for(c), M = 1u << (c - 1);
+        const size_t count = (size_t)W * M * n + 1, bytes = count * sizeof(Affine);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes <= free_b / 3 && count < (1u << 31)) {
+            e = cudaMalloc(&s.comb, bytes);
+            if (e == cudaSuccess) {
+                e = cudaMemsetAsync(s.comb + (count - 1), 0, sizeof(Affine), g->stream);  // the identity entry
+                msm_comb_build_kernel<<<(uint32_t)((n * W + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, s.comb);
+                g->launches++;
+                if (e == cudaSuccess) e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+                if (e != cudaSuccess) {
+                    cudaFree(s.comb);
+                    cudaFree(s.d);
+                    return fail(H2B_ERR_CUDA, "srs comb table", e);
+                }
+                s.comb_c = c;
+                s.comb_w = W;
+            } else {
+                (void)cudaGetLastError();
+                s.comb = nullptr;
+            }
+        }
+    }
+    if (!s.comb && g->srs_precompute && n >= 2) {
         uint32_t c = srs_window_for(n), W = msm_windows_for(c);
         size_t bytes = (size_t)W * n * sizeof(Affine), free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -1294,6 +1394,7 @@ int h2b_srs_release(uint64_t handle) {
     CU(cudaStreamSynchronize(g->stream));
     cudaFree(it->second.d);
     if (it->second.table) cudaFree(it->second.table);
+    if (it->second.comb) cudaFree(it->second.comb);
     g->srs.erase(it);
     return H2B_OK;
 }
@@ -1313,9 +1414,11 @@ int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windo
     if (it == g->srs.end()) return fail(H2B_ERR_STATE, "srs_info: unknown handle");
     const Srs &sr = it->second;
     if (n) *n = sr.n;
-    if (window_bits) *window_bits = sr.table ? sr.c : 0;
-    if (windows) *windows = sr.table ? sr.windows : 0;
-    if (table_bytes) *table_bytes = sr.table ? (size_t)sr.windows * sr.n * sizeof(Affine) : 0;
+    if (window_bits) *window_bits = sr.comb ? sr.comb_c : (sr.table ? sr.c : 0);
+    if (windows) *windows = sr.comb ? sr.comb_w : (sr.table ? sr.windows : 0);
+    if (table_bytes)
+        *table_bytes = sr.comb ? ((size_t)sr.comb_w * (1u << (sr.comb_c - 1)) * sr.n + 1) * sizeof(Affine)
+                               : (sr.table ? (size_t)sr.windows * sr.n * sizeof(Affine) : 0);
     return H2B_OK;
 }
 int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]) {
@@ -1329,7 +1432,14 @@ int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]
     TRY(enter(g->stream));
     void *dout;
     TRY(get_buf(BUF_OUT, 96, &dout));
-    TRY(msm_run_pipelined(scalars, nullptr, &it->second, n, (Projective *)dout));
+    if (it->second.comb && n) {
+        Fe *ds;
+        TRY(get_buf(BUF_SCALARS, n * sizeof(Fe), (void **)&ds));
+        TRY(copy_in(ds, scalars, n * sizeof(Fe), g->stream));
+        TRY(commit_many_device(it->second, ds, n, 1, (Projective *)dout, g->stream));
+    } else {
+        TRY(msm_run_pipelined(scalars, nullptr, &it->second, n, (Projective *)dout));
+    }
     TRY(copy_out(out, dout, 96, g->stream));
     return leave(g->stream, H2B_OK);
 }

@@ -1,0 +1,149 @@
+// msm_comb.cuh -- commits against a SMALL registered SRS without buckets.
+//
+// The reference's own circuits prove at k = 4 ... 14 (arithmetic k = 4, Poseidon k = 7, Collatz
+// k = 10).  At those sizes a Pippenger MSM is a latency chain, not a throughput problem: the bucket reduction
+// is 20-40 SERIAL group additions of ~6 us each (a lone warp needs ~840 cycles per Montgomery product), and
+// sorting, fix-up and reduction cost 4-5x the accumulation itself.  With the bases static and HBM at 180 GB
+// the buckets can be removed altogether: for every point, window and digit magnitude the multiple
+//      comb[(w * M + (d - 1)) * n + i] = d * 2^(c*w) * P_i          d = 1 .. M = 2^(c-1)
+// is precomputed once (c = 8: 32 windows x 128 multiples = 256 KiB per point, 4 GiB at n = 2^14), and a commit
+// is the plain SUM of n * W table entries: digits -> entry indices (no sort, no histogram), slice sums with
+// mixed additions, a binary tree over the slice sums.  Depth: L + log2(n * W / L) additions.
+#pragma once
+#include "msm.cuh"
+
+namespace h2b {
+
+// One thread per (point, window): the 2^(c-1) multiples of 2^(c*w) * P_i, each normalised to affine.
+__global__ void __launch_bounds__(128)
+msm_comb_build_kernel(const Affine *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W, Affine *__restrict__ comb) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * W) return;
+    const uint32_t i = t % n, w = t / n, M = 1u << (c - 1);
+    const Affine p = load_affine(&bases[i]);
+    Affine *dst = comb + (size_t)w * M * n + i;
+    if (affine_is_identity(p)) {
+        for (uint32_t d = 0; d < M; d++) {
+            store_fe(&dst[(size_t)d * n].x, Fq::zero());
+            store_fe(&dst[(size_t)d * n].y, Fq::zero());
+        }
+        return;
+    }
+    // base = 2^(c*w) * P_i
+    XYZZ acc = xyzz_from_affine(p);
+#pragma unroll 1
+    for (uint32_t k = 0; k < c * w; k++) acc = xyzz_dbl_ni(acc);
+    Affine base;
+    {
+        const Fe inv = Fq::inv(Fq::mul(acc.zz, acc.zzz));
+        base.x = Fq::mul(Fq::mul(acc.x, inv), acc.zzz);
+        base.y = Fq::mul(Fq::mul(acc.y, inv), acc.zz);
+    }
+    store_fe(&dst[0].x, base.x);
+    store_fe(&dst[0].y, base.y);
+    acc = xyzz_from_affine(base);
+#pragma unroll 1
+    for (uint32_t d = 1; d < M; d++) {
+        xyzz_madd_ni(acc, base);  // (d + 1) * base; never the identity: the group order is a 254-bit prime
+        const Fe inv = Fq::inv(Fq::mul(acc.zz, acc.zzz));
+        store_fe(&dst[(size_t)d * n].x, Fq::mul(Fq::mul(acc.x, inv), acc.zzz));
+        store_fe(&dst[(size_t)d * n].y, Fq::mul(Fq::mul(acc.y, inv), acc.zz));
+    }
+}
+
+// Scalars -> table indices.  entries[(col * W + w) * n + i] = index | sign << 31; a zero digit points at the
+// identity entry that closes the table (index W * M * stride).
+__global__ void __launch_bounds__(256)
+msm_comb_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg, uint32_t *__restrict__ entries) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cfg.n * cfg.cols) return;
+    const uint32_t col = t / cfg.n, i = t - col * cfg.n;
+    Fe s = Fr::from_mont(load_fe_ro(&scalars[t]));
+    uint32_t l[9];
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]), "=r"(l[4]), "=r"(l[5]), "=r"(l[6]), "=r"(l[7])
+        : "r"(s.l[0]), "r"(s.l[1]), "r"(s.l[2]), "r"(s.l[3]), "r"(s.l[4]), "r"(s.l[5]), "r"(s.l[6]),
+          "r"(s.l[7]), "r"(cfg.half[0]), "r"(cfg.half[1]), "r"(cfg.half[2]), "r"(cfg.half[3]),
+          "r"(cfg.half[4]), "r"(cfg.half[5]), "r"(cfg.half[6]), "r"(cfg.half[7]));
+    l[8] = 0;
+    const uint32_t ident = cfg.windows * cfg.bpw * cfg.stride;
+    uint32_t *dst = entries + (size_t)col * cfg.windows * cfg.n + i;
+    for (uint32_t w = 0; w < cfg.windows; w++) {
+        const int32_t d = digit_at(l, w, cfg);
+        uint32_t e = ident;
+        if (d != 0) {
+            const uint32_t neg = d < 0;
+            const uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+            e = ((w * cfg.bpw + mag - 1) * cfg.stride + i) | (neg << 31);
+        }
+        dst[(size_t)w * cfg.n] = e;
+    }
+}
+
+// Slice sums: thread (col, s) adds entries [s * L, (s + 1) * L) of its column.
+__global__ void __launch_bounds__(128)
+msm_comb_sum_kernel(const Affine *__restrict__ comb, const uint32_t *__restrict__ entries, uint32_t per_col, uint32_t L,
+                    uint32_t slices, XYZZ *__restrict__ partial) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (s >= slices) return;
+    const uint32_t *e = entries + (size_t)col * per_col;
+    const uint32_t begin = s * L, end = min(begin + L, per_col);
+    XYZZ acc = xyzz_identity();
+    uint32_t v = e[begin];
+    Affine p = load_affine(&comb[v & 0x7fffffffu]);
+    for (uint32_t k = begin; k < end; k++) {
+        uint32_t vn = 0;
+        Affine pn;
+        const bool more = k + 1 < end;
+        if (more) {
+            vn = e[k + 1];
+            pn = load_affine(&comb[vn & 0x7fffffffu]);
+        }
+        if (!affine_is_identity(p)) {
+            if (v >> 31) p.y = Fq::neg(p.y);
+            xyzz_madd(acc, p);
+        }
+        v = vn;
+        p = pn;
+    }
+    store_xyzz(&partial[(size_t)col * slices + s], acc);
+}
+
+// One level group of the tree: block b of column `col` folds in[col][b * span, (b + 1) * span) into
+// out[col][b]  (span = blockDim.x * per_thread; per_thread sequential additions, then a shared-memory tree).
+__global__ void __launch_bounds__(256)
+msm_comb_tree_kernel(const XYZZ *__restrict__ in, uint32_t count, uint32_t per_thread, XYZZ *__restrict__ out) {
+    extern __shared__ uint4 tree_smem[];
+    XYZZ *sh = reinterpret_cast<XYZZ *>(tree_smem);
+    const uint32_t col = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+    const XYZZ *src = in + (size_t)col * count;
+    const uint32_t base = (blockIdx.x * nt + tid) * per_thread;
+    XYZZ acc = xyzz_identity();
+    for (uint32_t k = 0; k < per_thread; k++) {
+        if (base + k < count) {
+            XYZZ q = load_xyzz(&src[base + k]);
+            xyzz_add(acc, q);
+        }
+    }
+    store_xyzz(&sh[tid], acc);
+    __syncthreads();
+    for (uint32_t stride = nt >> 1; stride > 0; stride >>= 1) {
+        if (tid < stride) {
+            XYZZ a = load_xyzz(&sh[tid]);
+            XYZZ b = load_xyzz(&sh[tid + stride]);
+            xyzz_add(a, b);
+            store_xyzz(&sh[tid], a);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_xyzz(&out[(size_t)col * gridDim.x + blockIdx.x], load_xyzz(&sh[0]));
+}
+
+}  // namespace h2b

@@ -165,9 +165,11 @@ int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k, uint64_t *g_h
  * width, the number of windows (= bucket additions per point of a commit) and the table's size in HBM
  * (zeros when there is no table). */
 int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windows, size_t *table_bytes);
-/* h2b_srs_register precomputes 2^(c*w) * P_i for the static bases (default on) so that all windows of a
- * commit share one bucket set; `c` overrides that table's window (0 = automatic).  Applies to SRS
- * registered after the call. */
+/* What h2b_srs_register precomputes for the static bases.  enabled = 1 (default): SRS of up to 2^14 points get
+ * every window multiple d * 2^(8w) * P_i (commits become bucket-free sums, msm_comb.cuh), larger ones the window
+ * table 2^(c*w) * P_i (all windows of a commit share one bucket set); 2: the window table at every size;
+ * 0: nothing.  `c` overrides the window table's width (0 = automatic) and implies the window table.
+ * Applies to SRS registered after the call. */
 int h2b_set_srs_precompute(int enabled, uint32_t c);
 /* Host-buffer MSM entry points (h2b_best_multiexp, h2b_commit) split inputs of at least `min_n`
  * points into `chunks` contiguous pieces so the H2D copy of a piece overlaps the bucket accumulation

@@ -118,11 +118,12 @@ def test_commit_against_registered_srs(h2b, spec, href):
     params.release()
 
 
-@pytest.mark.parametrize("srs_c", [0, 7, 13, 16])
-def test_commit_precomputed_window_table(h2b, spec, href, srs_c):
-    """Registered bases get a table 2^(c*w) * P_i so all windows of a commit share one bucket set; the result
-    must equal best_multiexp on the plain bases for every table window, with identity bases, repeated
-    scalars, r-1 / 0 / 1 scalars, for a prefix of the SRS, and with the table disabled."""
+@pytest.mark.parametrize("mode,srs_c", [(1, 0), (2, 0), (1, 7), (1, 13), (1, 16)])
+def test_commit_precomputed_window_table(h2b, spec, href, mode, srs_c):
+    """Registered bases get a precomputed table: mode 1 / c = 0 the bucket-free table of all window multiples
+    (small SRS), mode 2 or an explicit c the window table 2^(c*w) * P_i whose windows share one bucket set.
+    The result must equal best_multiexp on the plain bases in every mode, with identity bases, repeated
+    scalars, r-1 / 0 / 1 scalars, for a prefix of the SRS, and with the tables disabled."""
     import ctypes as C
     from halo2_prover_b200 import _ffi
     n = 1 << 12
@@ -136,10 +137,14 @@ def test_commit_precomputed_window_table(h2b, spec, href, srs_c):
     want = _affine(href, href.best_multiexp(poly, g))
     want_short = _affine(href, href.best_multiexp(poly[:1500].copy(), g[:1500].copy()))
     try:
-        _ffi.check(_ffi.lib().h2b_set_srs_precompute(1, srs_c))
+        _ffi.check(_ffi.lib().h2b_set_srs_precompute(mode, srs_c))
         params = h2b.ParamsKZG(12, g)
         assert (_affine(href, params.commit(poly)) == want).all()
         assert (_affine(href, params.commit(poly[:1500].copy())) == want_short).all()
+        many = params.commit_many([poly, poly[::-1].copy(), np.zeros_like(poly)])
+        assert (_affine(href, many[0]) == want).all()
+        assert (_affine(href, many[1]) == _affine(href, href.best_multiexp(poly[::-1].copy(), g))).all()
+        assert (_affine(href, many[2]) == 0).all()
         params.release()
         _ffi.check(_ffi.lib().h2b_set_srs_precompute(0, 0))
         params = h2b.ParamsKZG(12, g)
