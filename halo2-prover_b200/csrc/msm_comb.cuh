@@ -116,6 +116,52 @@ msm_comb_sum_kernel(const Affine *__restrict__ comb, const uint32_t *__restrict_
     store_xyzz(&partial[(size_t)col * slices + s], acc);
 }
 
+// A group addition shared by a team of 4 adjacent lanes.  A lone warp needs ~840 cycles per Montgomery product
+// (its carry chains serialise), so a 14-product addition is ~6 us for one thread; the tree below has few
+// active nodes and idle lanes, so four lanes take one product each per round and exchange the results by
+// shuffles: 4 rounds instead of 14 products (add-2008-s: {U1,U2,S1,S2}, {PP,RR,ZZ1*ZZ2,ZZZ1*ZZZ2},
+// {PPP,Q,ZZ3}, {R(Q-X3),S1*PPP,ZZZ3}).  a and b are replicated in the 4 lanes, and so is the result.  The
+// shuffles run unconditionally (mask = the lanes of all teams doing an addition in this step); identities
+// and equal / opposite x-coordinates are patched afterwards without communication.
+H2B_DI Fe fe_team(const Fe &v, int src, uint32_t mask) {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(mask, v.l[i], src, 4);
+    return r;
+}
+H2B_DI XYZZ xyzz_add_team4(const XYZZ &a, const XYZZ &b, uint32_t lane4, uint32_t mask) {
+    const bool l0 = lane4 == 0, l1 = lane4 == 1, l2 = lane4 == 2;
+    // round 1
+    Fe r = Fq::mul(fe_sel(l0, a.x, fe_sel(l1, b.x, fe_sel(l2, a.y, b.y))),
+                   fe_sel(l0, b.zz, fe_sel(l1, a.zz, fe_sel(l2, b.zzz, a.zzz))));
+    const Fe u1 = fe_team(r, 0, mask), u2 = fe_team(r, 1, mask), s1 = fe_team(r, 2, mask), s2 = fe_team(r, 3, mask);
+    const Fe p = Fq::sub(u2, u1), rr_ = Fq::sub(s2, s1);
+    // round 2
+    r = Fq::mul(fe_sel(l0, p, fe_sel(l1, rr_, fe_sel(l2, a.zz, a.zzz))), fe_sel(l0, p, fe_sel(l1, rr_, fe_sel(l2, b.zz, b.zzz))));
+    const Fe pp = fe_team(r, 0, mask), r2 = fe_team(r, 1, mask), zm = fe_team(r, 2, mask), zn = fe_team(r, 3, mask);
+    // round 3
+    r = Fq::mul(fe_sel(l0, p, fe_sel(l1, u1, zm)), pp);
+    const Fe ppp = fe_team(r, 0, mask), q = fe_team(r, 1, mask), zz3 = fe_team(r, 2, mask);
+    const Fe x3 = Fq::sub(Fq::sub(Fq::sub(r2, ppp), q), q);
+    // round 4
+    r = Fq::mul(fe_sel(l0, rr_, fe_sel(l1, s1, zn)), fe_sel(l0, Fq::sub(q, x3), ppp));
+    const Fe t0 = fe_team(r, 0, mask), t1 = fe_team(r, 1, mask), zzz3 = fe_team(r, 2, mask);
+    XYZZ out;
+    out.x = x3;
+    out.y = Fq::sub(t0, t1);
+    out.zz = zz3;
+    out.zzz = zzz3;
+    // patches (uniform inside a team, no communication)
+    if (xyzz_is_identity(a)) return b;
+    if (xyzz_is_identity(b)) return a;
+    if (Fq::is_zero(p)) {  // same x: doubling or P + (-P)
+        XYZZ t = a;
+        xyzz_add(t, b);
+        return t;
+    }
+    return out;
+}
+
 // One level group of the tree: block b of column `col` folds in[col][b * span, (b + 1) * span) into
 // out[col][b]  (span = blockDim.x * per_thread; per_thread sequential additions, then a shared-memory tree).
 __global__ void __launch_bounds__(256)
@@ -135,7 +181,19 @@ msm_comb_tree_kernel(const XYZZ *__restrict__ in, uint32_t count, uint32_t per_t
     store_xyzz(&sh[tid], acc);
     __syncthreads();
     for (uint32_t stride = nt >> 1; stride > 0; stride >>= 1) {
-        if (tid < stride) {
+        if (stride * 4 <= nt) {
+            // enough idle lanes: node t of this level is added by the team of lanes 4t .. 4t+3
+            const uint32_t team = tid >> 2;
+            const bool active = team < stride;
+            const uint32_t mask = __ballot_sync(0xffffffffu, active);
+            if (active) {
+                const XYZZ a = load_xyzz(&sh[team]);
+                const XYZZ b = load_xyzz(&sh[team + stride]);
+                const XYZZ c = xyzz_add_team4(a, b, tid & 3, mask);
+                __syncwarp(mask);
+                if ((tid & 3) == 0) store_xyzz(&sh[team], c);
+            }
+        } else if (tid < stride) {
             XYZZ a = load_xyzz(&sh[tid]);
             XYZZ b = load_xyzz(&sh[tid + stride]);
             xyzz_add(a, b);
