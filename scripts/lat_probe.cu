@@ -2,6 +2,7 @@
 #include <cstdio>
 #include "../halo2-prover_b200/csrc/field.cuh"
 #include "../halo2-prover_b200/csrc/curve.cuh"
+#include "../halo2-prover_b200/csrc/msm_comb.cuh"
 using namespace h2b;
 
 template <int MODE>
@@ -22,6 +23,8 @@ __global__ void __launch_bounds__(32) k(const Fe *in, Fe *out, int iters, long l
             x0 = Fq::mul_portable(x0, b); x0 = Fq::mul_portable(x0, b); x0 = Fq::mul_portable(x0, b); x0 = Fq::mul_portable(x0, b);
         } else if (MODE == 5) {  // 4 independent products, 64-bit C arithmetic
             x0 = Fq::mul_portable(x0, b); x1 = Fq::mul_portable(x1, b); x2 = Fq::mul_portable(x2, b); x3 = Fq::mul_portable(x3, b);
+        } else if (MODE == 6) {  // addition shared by teams of 4 lanes
+            p = xyzz_add_team4(p, q, threadIdx.x & 3, 0xffffffffu);
         } else if (MODE == 2) {  // xyzz_add (noinline, 12M + 2S)
             xyzz_add(p, q);
         } else if (MODE == 3) {  // xyzz_dbl_ni
@@ -42,8 +45,8 @@ int main() {
     cudaMalloc(&cyc, 8);
     cudaMemset(in, 0x11, 64 * sizeof(Fe));
     const int iters = 200;
-    const char *names[] = {"4 dependent modmul", "4 independent modmul", "xyzz_add (14 modmul)", "xyzz_dbl (9 modmul)", "4 dependent portable", "4 independent portable"};
-    for (int m = 0; m < 6; m++) {
+    const char *names[] = {"4 dependent modmul", "4 independent modmul", "xyzz_add (14 modmul)", "xyzz_dbl (9 modmul)", "4 dependent portable", "4 independent portable", "xyzz_add_team4"};
+    for (int m = 0; m < 7; m++) {
         for (int rep = 0; rep < 2; rep++) {
             if (m == 0) k<0><<<148, 32>>>(in, out, iters, cyc);
             if (m == 1) k<1><<<148, 32>>>(in, out, iters, cyc);
@@ -51,6 +54,7 @@ int main() {
             if (m == 3) k<3><<<148, 32>>>(in, out, iters, cyc);
             if (m == 4) k<4><<<148, 32>>>(in, out, iters, cyc);
             if (m == 5) k<5><<<148, 32>>>(in, out, iters, cyc);
+            if (m == 6) k<6><<<148, 32>>>(in, out, iters, cyc);
             cudaDeviceSynchronize();
         }
         cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
