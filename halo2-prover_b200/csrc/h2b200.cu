@@ -20,6 +20,7 @@
 
 #include "curve.cuh"
 #include "ecntt.cuh"
+#include "evalh.cuh"
 #include "hostcopy.h"
 #include "field.cuh"
 #include "msm.cuh"
@@ -40,7 +41,7 @@ std::mutex g_mu;
 
 enum BufId {
     BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_CURSOR, BUF_NEOFF, BUF_NEID, BUF_SORTED, BUF_DIGITS, BUF_HEAD, BUF_TAIL,
-    BUF_TAILJ, BUF_TOTALS, BUF_ECNTT,
+    BUF_TAILJ, BUF_TOTALS, BUF_ECNTT, BUF_EVALH, BUF_EVALH_SCRATCH,
     BUF_BUCKETS, BUF_BUCKETS2, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
     BUF_NTT_OUT, BUF_MISC,
     BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
@@ -698,8 +699,11 @@ NttIo io_plain(uint32_t log_n) {
 // ------------------------------------------------------------------------------ domain constants
 __device__ const uint32_t kRootOfUnityMont[8] = {0xb639feb8u, 0x9632c7c5u, 0x0d0ff299u, 0x985ce340u,
                                                  0x01b0ecd8u, 0xb2dd8800u, 0x6d98ce29u, 0x1d69070du};
-__device__ const uint32_t kZetaMont[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu,
-                                          0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};
+// Fr::ZETA = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd in Montgomery form.  (SURVEY.md quotes the other
+// primitive cube root, ZETA^2 = g_coset_inv; the reference's recorded coeff_to_extended calls decide: coefficient
+// 1 is multiplied by this value.)
+__device__ const uint32_t kZetaMont[8] = {0x4a0329b3u, 0x93e7cedeu, 0x7a96c167u, 0x7d4fdca7u,
+                                          0xb19a750au, 0x8be4ba08u, 0xa5661c25u, 0x1cbd5653u};
 
 struct DomainDev {
     Fe omega, omega_inv, ext_omega, ext_omega_inv, g_coset, g_coset_inv, ifft_div, ext_ifft_div;
@@ -1471,6 +1475,136 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
     LAUNCHED();
     return leave(s, H2B_OK);
 }
+// ---- evaluate_h
+static bool evalh_source_ok(uint64_t src, const h2b_eval_h *a) {
+    const uint32_t kind = (uint32_t)(src & 0xff), x = (uint32_t)((src >> 8) & 0xfffffff), b = (uint32_t)(src >> 36);
+    switch (kind) {
+        case VS_CONSTANT: return x < a->num_constants;
+        case VS_INTERMEDIATE: return x < a->num_intermediates;
+        case VS_FIXED: return x < a->num_fixed && b < a->num_rotations;
+        case VS_ADVICE: return x < a->num_advice && b < a->num_rotations;
+        case VS_INSTANCE: return x < a->num_instance && b < a->num_rotations;
+        case VS_CHALLENGE: return x < a->num_challenges;
+        default: return kind <= VS_PREVIOUS;
+    }
+}
+int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!a || !d_values) return fail(H2B_ERR_ARG, "evaluate_h: null pointer");
+    if (a->num_rotations > kMaxRotations) return fail(H2B_ERR_ARG, "evaluate_h: more than 32 distinct rotations");
+    if ((a->num_fixed && !a->fixed) || (a->num_advice && !a->advice) || (a->num_instance && !a->instance) ||
+        (a->num_challenges && !a->challenges) || (a->num_constants && !a->constants) || (a->num_rotations && !a->rotations) ||
+        (a->num_calcs && !a->calcs))
+        return fail(H2B_ERR_ARG, "evaluate_h: null array");
+    // validate the serialised graph before it is trusted with device pointers
+    {
+        size_t w = 0;
+        for (uint32_t c = 0; c < a->num_calcs; c++) {
+            if (w >= a->calc_words) return fail(H2B_ERR_ARG, "evaluate_h: truncated calculation list");
+            const uint64_t hdr = a->calcs[w++];
+            const uint32_t op = (uint32_t)(hdr & 0xff), target = (uint32_t)((hdr >> 8) & 0xffffffffu), nparts = (uint32_t)(hdr >> 40);
+            if (op > CALC_STORE || target >= a->num_intermediates) return fail(H2B_ERR_ARG, "evaluate_h: bad calculation");
+            const size_t nsrc = op == CALC_HORNER ? 2 + (size_t)nparts : (op <= CALC_MUL ? 2 : 1);
+            if (w + nsrc > a->calc_words) return fail(H2B_ERR_ARG, "evaluate_h: truncated calculation list");
+            for (size_t k = 0; k < nsrc; k++)
+                if (!evalh_source_ok(a->calcs[w + k], a)) return fail(H2B_ERR_ARG, "evaluate_h: value source out of range");
+            w += nsrc;
+        }
+        if (w != a->calc_words) return fail(H2B_ERR_ARG, "evaluate_h: calc_words does not match the calculation list");
+    }
+    const uint32_t P = a->num_perm_columns;
+    uint32_t sets = 0;
+    if (P) {
+        if (a->chunk_len == 0) return fail(H2B_ERR_ARG, "evaluate_h: chunk_len = 0");
+        sets = (P + a->chunk_len - 1) / a->chunk_len;
+        if (!a->perm_kind || !a->perm_index || !a->sigma_cosets || !a->z_cosets || !a->l0 || !a->l_last || !a->l_active_row)
+            return fail(H2B_ERR_ARG, "evaluate_h: null permutation data");
+        for (uint32_t c = 0; c < P; c++) {
+            const uint32_t lim = a->perm_kind[c] == 0 ? a->num_advice : (a->perm_kind[c] == 1 ? a->num_fixed : a->num_instance);
+            if (a->perm_kind[c] > 2 || a->perm_index[c] >= lim) return fail(H2B_ERR_ARG, "evaluate_h: permutation column out of range");
+        }
+    }
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    const uint32_t size = 1u << d->extended_k;
+    // one staging blob: pointer tables, scalars, graph
+    std::vector<uint64_t> blob;
+    auto put = [&](const void *src, size_t bytes) {
+        if (blob.size() & 1) blob.push_back(0);  // field elements are read with 128-bit loads
+        const size_t off = blob.size();
+        blob.resize(off + (bytes + 7) / 8);
+        if (bytes) memcpy(&blob[off], src, bytes);
+        return off;
+    };
+    const size_t o_fixed = put(a->fixed, a->num_fixed * sizeof(void *)), o_adv = put(a->advice, a->num_advice * sizeof(void *));
+    const size_t o_inst = put(a->instance, a->num_instance * sizeof(void *));
+    const size_t o_chal = put(a->challenges, (size_t)a->num_challenges * 32), o_const = put(a->constants, (size_t)a->num_constants * 32);
+    const size_t o_rot = put(a->rotations, a->num_rotations * sizeof(int32_t)), o_calc = put(a->calcs, a->calc_words * 8);
+    std::vector<const void *> cols(P);
+    for (uint32_t c = 0; c < P; c++)
+        cols[c] = a->perm_kind[c] == 0 ? a->advice[a->perm_index[c]] : (a->perm_kind[c] == 1 ? a->fixed[a->perm_index[c]] : a->instance[a->perm_index[c]]);
+    const size_t o_cols = put(cols.data(), P * sizeof(void *)), o_sig = put(a->sigma_cosets, P * sizeof(void *));
+    const size_t o_z = put(a->z_cosets, sets * sizeof(void *));
+    uint64_t *dblob;
+    TRY(get_buf(BUF_EVALH, blob.size() * 8 + 8, (void **)&dblob));
+    if (!blob.empty()) CU(cudaMemcpyAsync(dblob, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice, s));
+    Fe *scratch;
+    TRY(get_buf(BUF_EVALH_SCRATCH, (size_t)std::max(a->num_intermediates, 1u) * size * sizeof(Fe), (void **)&scratch));
+    CU(cudaMemsetAsync(d_values, 0, (size_t)size * sizeof(Fe), s));
+    EvalGates eg;
+    eg.fixed = (const Fe *const *)(dblob + o_fixed);
+    eg.advice = (const Fe *const *)(dblob + o_adv);
+    eg.instance = (const Fe *const *)(dblob + o_inst);
+    eg.challenges = (const Fe *)(dblob + o_chal);
+    eg.constants = (const Fe *)(dblob + o_const);
+    eg.rotations = (const int32_t *)(dblob + o_rot);
+    eg.calcs = dblob + o_calc;
+    eg.scratch = scratch;
+    eg.num_rotations = a->num_rotations;
+    eg.num_calcs = a->num_calcs;
+    eg.size = size;
+    eg.rot_scale = 1u << (d->extended_k - d->k);
+    memcpy(&eg.beta, a->beta, 32);
+    memcpy(&eg.gamma, a->gamma, 32);
+    memcpy(&eg.theta, a->theta, 32);
+    memcpy(&eg.y, a->y, 32);
+    const uint32_t blocks = (size + 127) / 128;
+    evalh_gates_kernel<<<blocks, 128, 0, s>>>(eg, (Fe *)d_values);
+    LAUNCHED();
+    if (P) {
+        static const uint32_t kDeltaMont[8] = {0xefd78855u, 0x9a0c322bu, 0x249b563cu, 0x46e82d14u,
+                                               0xe0b0b7a7u, 0x5983a663u, 0xaaa111adu, 0x22ab452bu};  // Fr::DELTA = 7^(2^28)
+        EvalPerm ep;
+        ep.columns = (const Fe *const *)(dblob + o_cols);
+        ep.sigma = (const Fe *const *)(dblob + o_sig);
+        ep.z = (const Fe *const *)(dblob + o_z);
+        ep.l0 = (const Fe *)a->l0;
+        ep.l_last = (const Fe *)a->l_last;
+        ep.l_active = (const Fe *)a->l_active_row;
+        ep.num_columns = P;
+        ep.chunk_len = a->chunk_len;
+        ep.num_sets = sets;
+        ep.size = size;
+        ep.rot_scale = eg.rot_scale;
+        ep.last_rotation = a->last_rotation;
+        ep.beta = eg.beta;
+        ep.gamma = eg.gamma;
+        ep.y = eg.y;
+        memcpy(&ep.zeta, d->g_coset, 32);
+        memcpy(&ep.ext_omega, d->extended_omega, 32);
+        memcpy(&ep.delta, kDeltaMont, 32);
+        evalh_permutation_kernel<<<blocks, 128, 0, s>>>(ep, (Fe *)d_values);
+        LAUNCHED();
+    }
+    // the staging blob lives on this frame: the copy above has consumed it once the stream reaches the kernels;
+    // wait so that a pageable-source copy cannot outlive the vector
+    CU(cudaStreamSynchronize(s));
+    return leave(s, H2B_OK);
+}
+
 int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());

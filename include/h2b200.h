@@ -154,6 +154,40 @@ int h2b_dev_g1_fold(const void *d_points, size_t count, void *d_out, void *strea
  * ParamsKZG::setup (src/poly/kzg/commitment.rs:68-114); builds synthetic SRS / benchmark bases in HBM. */
 int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[8], void *d_out, void *stream);
 
+/* ---- quotient numerator ---------------------------------------- */
+/* Evaluator::evaluate_h (halo2_proofs@6b43b6b src/plonk/evaluation.rs) for circuits without lookups, with
+ * every column already on the extended coset in HBM (the outputs of h2b_dev_coeff_to_extended(_many)): the
+ * custom gates as upstream's compiled GraphEvaluator, then the permutation argument folded in with y.
+ *
+ * ValueSource (one u64): kind | a << 8 | b << 36 with kind 0 Constant(a) 1 Intermediate(a) 2 Fixed(column a,
+ * rotation index b) 3 Advice(a, b) 4 Instance(a, b) 5 Challenge(a) 6 Beta 7 Gamma 8 Theta 9 Y 10 PreviousValue.
+ * Calculation: header u64 = op | target << 8 | nparts << 40 followed by its ValueSources, op 0 Add(a, b)
+ * 1 Sub(a, b) 2 Mul(a, b) 3 Square(a) 4 Double(a) 5 Negate(a) 6 Horner(start, factor, parts[nparts])
+ * 7 Store(a); `target` is the intermediate it writes.  The value of a row is that of the last calculation. */
+typedef struct h2b_eval_h {
+    uint32_t num_fixed, num_advice, num_instance, num_challenges;
+    const void *const *fixed;    /* host arrays of DEVICE pointers, each column 2^extended_k x 32 B */
+    const void *const *advice;
+    const void *const *instance;
+    const uint64_t *challenges;  /* host, num_challenges x 4 */
+    uint64_t beta[4], gamma[4], theta[4], y[4];
+    uint32_t num_constants, num_rotations, num_calcs, num_intermediates;
+    const uint64_t *constants;   /* host, num_constants x 4 */
+    const int32_t *rotations;    /* host, num_rotations (<= 32) */
+    const uint64_t *calcs;       /* host, calc_words u64 */
+    size_t calc_words;
+    /* permutation argument; num_perm_columns = 0 when the circuit has none */
+    uint32_t num_perm_columns, chunk_len; /* chunk_len = cs.degree() - 2 */
+    int32_t last_rotation;                /* -(cs.blinding_factors() + 1) */
+    const uint8_t *perm_kind;             /* per column of cs.permutation: 0 advice, 1 fixed, 2 instance */
+    const uint32_t *perm_index;
+    const void *const *sigma_cosets;      /* DEVICE pointers: pk.permutation.cosets */
+    const void *const *z_cosets;          /* DEVICE pointers: permutation_product_coset of every chunk */
+    const void *l0, *l_last, *l_active_row; /* DEVICE pointers */
+} h2b_eval_h;
+/* d_values: 2^extended_k x 32 B in HBM, overwritten (upstream starts from domain.empty_extended()). */
+int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values, void *stream);
+
 /* ---- tuning / introspection ------------------------------------------------------- */
 /* Override the MSM window (0 = automatic). */
 int h2b_set_msm_window(uint32_t c);

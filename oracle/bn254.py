@@ -39,7 +39,11 @@ MONT_R = 1 << 256
 FR_S = 28
 FR_GENERATOR = 7
 ROOT_OF_UNITY = 0x03DDB9F5166D18B798865EA93DD31F743215CF6DD39329C8D34F1ED960C37C9C
-ZETA = 0x30644E72E131A029048B6E193FD84104CC37A73FEC2BC5E9B8CA0B2D36636F23
+# Fr::ZETA of halo2curves 0.3.2 (the coset generator of EvaluationDomain).  SURVEY.md quotes its SQUARE
+# (0x30644e72...36636f23, found as an immediate in EvaluationDomain::new: that is g_coset_inv); the reference's
+# recorded coeff_to_extended calls multiply coefficient 1 by THIS value (tests/test_wasm_golden.py,
+# tests/test_evaluate_h.py), which settles it.
+ZETA = 0xB3C4D79D41A917585BFC41088D8DAAA78B17EA66B99C90DD
 INV_R = 0xC2E1F593EFFFFFFF  # -r^{-1} mod 2^64
 INV_Q = 0x87D20782E4866389  # -q^{-1} mod 2^64
 CURVE_B = 3

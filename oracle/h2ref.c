@@ -549,7 +549,8 @@ typedef struct {
 } h2ref_domain;
 
 static const fe FR_ROOT_OF_UNITY_CANON = {{0xd34f1ed960c37c9cULL, 0x3215cf6dd39329c8ULL, 0x98865ea93dd31f74ULL, 0x03ddb9f5166d18b7ULL}};
-static const fe FR_ZETA_CANON = {{0xb8ca0b2d36636f23ULL, 0xcc37a73fec2bc5e9ULL, 0x048b6e193fd84104ULL, 0x30644e72e131a029ULL}};
+/* Fr::ZETA (halo2curves 0.3.2); SURVEY.md quotes its square, the reference's recorded coeff_to_extended calls use this one */
+static const fe FR_ZETA_CANON = {{0x8b17ea66b99c90ddULL, 0x5bfc41088d8daaa7ULL, 0xb3c4d79d41a91758ULL, 0x0ULL}};
 #define FR_S 28
 
 int h2ref_domain_new(uint32_t j, uint32_t k, h2ref_domain *d) {

@@ -1,0 +1,226 @@
+"""evaluate_h: the oracle's restatement pinned against the reference's execution, and
+the CUDA path against both.
+
+In the recorded arithmetic-circuit proof (k = 4, extended_k = 5) the recorded best_fft calls of keygen_pk and
+create_proof are, in order: 0-4 fixed lagrange_to_coeff (sm, sl, sr, so, sc), 5-9 their coeff_to_extended,
+10-13 / 14-17 the four permutation polynomials, 18-23 l0, l_blind, l_last (each lagrange_to_coeff then
+coeff_to_extended), 24 instance, 25-32 the four permutation products z_i (lagrange_to_coeff, coeff_to_extended),
+33-35 advice l, r, o, 36-39 coeff_to_extended of advice and instance inside evaluate_h, 40 extended_to_coeff of
+the quotient.  So every input of evaluate_h is a recorded output, and its result is input 40 divided by the
+t_evaluations."""
+import json
+
+import numpy as np
+import pytest
+
+from util import GOLDEN
+
+MANIFEST = json.load(open(f"{GOLDEN}/wasm_manifest.json"))
+K, EXT_K = 4, 5
+N, EN = 1 << K, 1 << EXT_K
+
+
+def _fixture(spec):
+    ent = MANIFEST["arithmetic"]
+    z = np.load(f"{GOLDEN}/{ent['file']}")
+    R = spec.R_MOD
+    out = lambda i: spec.fr_ints(z[f"fft{i}_out"])
+    inp = lambda i: spec.fr_ints(z[f"fft{i}_in"])
+    ext_omega = pow(spec.ROOT_OF_UNITY, 1 << (28 - EXT_K), R)
+    # the coset generator: recorded coset evaluations are p(zeta * omega^i); check it on l0 = L_0
+    zeta = spec.fr_ints(z["fft36_in"][1:2])[0] * pow(spec.fr_ints(z["fft33_out"][1:2])[0] * pow(N, -1, R), -1, R) % R
+    d = {
+        "fixed": [out(i) for i in range(5, 10)], "sigma": [out(i) for i in range(14, 18)],
+        "l0": out(19), "l_blind": out(21), "l_last": out(23), "z": [out(i) for i in (26, 28, 30, 32)],
+        "advice": [out(i) for i in (36, 37, 38)], "instance": [out(39)], "ext_omega": ext_omega, "zeta": zeta,
+    }
+    d["l_active"] = [(1 - a - b) % R for a, b in zip(d["l_last"], d["l_blind"])]
+    tev = [pow((pow(zeta * pow(ext_omega, i, R) % R, N, R) - 1) % R, -1, R) for i in range(EN // N)]
+    d["values"] = [v * pow(tev[i % len(tev)], -1, R) % R for i, v in enumerate(inp(40))]   # undo divide_by_vanishing_poly
+    return d
+
+
+def _gate_graph(ev, spec):
+    """The compiled "plonk" gate of circuits/src/arithmetic_circuit.rs:205-217:
+    l*sl + r*sr + l*r*sm + (o*so*(-1)) + sc with fixed columns created in the order sm, sl, sr, so, sc (:196-200)."""
+    g = ev.Graph()
+    r0 = g.add_rotation(0)
+    l, r, o = (ev.ADVICE, 0, r0), (ev.ADVICE, 1, r0), (ev.ADVICE, 2, r0)
+    sm, sl, sr, so, sc = [(ev.FIXED, i, r0) for i in range(5)]
+    t = g.add_calc(ev.ADD, g.add_calc(ev.MUL, l, sl), g.add_calc(ev.MUL, r, sr))
+    t = g.add_calc(ev.ADD, t, g.add_calc(ev.MUL, g.add_calc(ev.MUL, l, r), sm))
+    t = g.add_calc(ev.ADD, t, g.add_calc(ev.MUL, g.add_calc(ev.MUL, o, so), g.add_constant(spec.R_MOD - 1)))
+    t = g.add_calc(ev.ADD, t, sc)
+    g.add_calc(ev.HORNER, (ev.PREVIOUS, 0, 0), [t], (ev.Y, 0, 0))
+    return g
+
+
+def _solve(A, b, R):
+    m, nv = len(A), len(A[0])
+    A = [row[:] + [bb] for row, bb in zip(A, b)]
+    piv, rr = [], 0
+    for c in range(nv):
+        p = next((i for i in range(rr, m) if A[i][c] % R), None)
+        if p is None:
+            piv.append(None)
+            continue
+        A[rr], A[p] = A[p], A[rr]
+        inv = pow(A[rr][c], -1, R)
+        A[rr] = [v * inv % R for v in A[rr]]
+        for i in range(m):
+            if i != rr and A[i][c] % R:
+                f = A[i][c]
+                A[i] = [(v - f * w) % R for v, w in zip(A[i], A[rr])]
+        piv.append(rr)
+        rr += 1
+    residual = sum(1 for i in range(rr, m) if A[i][nv] % R)
+    return [A[p][nv] if p is not None else None for p in piv], rr, residual
+
+
+def _recover_challenges(d, spec):
+    """values[idx] is linear in the 17 monomials y^9..y, beta*y^3..beta, gamma*y^3..gamma (10 Horner terms, the last
+    four are A + beta*B + gamma*C): solve the 32 x 17 system and insist on zero residual and on monomials that are
+    powers / products of one (y, beta, gamma)."""
+    import evaluate_h as ev
+    R = spec.R_MOD
+    sm, sl, sr, so, sc = d["fixed"]
+    adv, z, sig = d["advice"], d["z"], d["sigma"]
+    cols = adv + d["instance"]
+    rows, rhs = [], []
+    for idx in range(EN):
+        l, r, o = adv[0][idx], adv[1][idx], adv[2][idx]
+        gate = (l * sl[idx] + r * sr[idx] + l * r * sm[idx] - o * so[idx] + sc[idx]) % R
+        r_next, r_last = (idx + 2) % EN, (idx - 12) % EN
+        terms = [gate, (1 - z[0][idx]) * d["l0"][idx], (z[3][idx] ** 2 - z[3][idx]) * d["l_last"][idx]]
+        terms += [(z[i][idx] - z[i - 1][r_last]) * d["l0"][idx] for i in (1, 2, 3)]
+        X = d["zeta"] * pow(d["ext_omega"], idx, R) % R
+        row, const = [t % R for t in terms] + [0] * 11, 0
+        for i in range(4):
+            zn, zz, c, la = z[i][r_next], z[i][idx], cols[i][idx], d["l_active"][idx]
+            A, B, Cc = (zn - zz) * c * la, (zn * sig[i][idx] - zz * pow(ev.DELTA, i, R) * X) * la, (zn - zz) * la
+            if i < 3:
+                row[6 + i] = (row[6 + i] + A) % R      # y^(3-i) sits at index 9 - (3 - i)
+            else:
+                const = A % R
+            row[9 + i], row[13 + i] = B % R, Cc % R
+        rows.append(row)
+        rhs.append((d["values"][idx] - const) % R)
+    sol, rank, residual = _solve(rows, rhs, R)
+    return sol, rank, residual
+
+
+def test_oracle_evaluate_h_is_pinned_by_the_reference_execution(spec):
+    import evaluate_h as ev
+    R = spec.R_MOD
+    d = _fixture(spec)
+    # the labelling itself: l0 is L_0 on the coset zeta * <extended_omega>, the gate vanishes on H
+    for idx in range(EN):
+        X = d["zeta"] * pow(d["ext_omega"], idx, R) % R
+        assert d["l0"][idx] == (pow(X, N, R) - 1) * pow(N * (X - 1) % R, -1, R) % R
+    assert pow(d["zeta"], 3, R) == 1 and d["zeta"] != 1
+    sol, rank, residual = _recover_challenges(d, spec)
+    assert rank == 17 and residual == 0, "the recorded quotient is not consistent with this restatement"
+    y, beta, gamma = sol[8], sol[12], sol[16]
+    assert all(sol[9 - p] == pow(y, p, R) for p in range(1, 10))
+    assert all(sol[9 + i] == beta * pow(y, 3 - i, R) % R and sol[13 + i] == gamma * pow(y, 3 - i, R) % R for i in range(4))
+    perm = ev.Permutation(columns=[(ev.ADVICE, 0), (ev.ADVICE, 1), (ev.ADVICE, 2), (ev.INSTANCE, 0)], sigma_cosets=d["sigma"],
+                          z_cosets=d["z"], chunk_len=1, last_rotation=-6, l0=d["l0"], l_last=d["l_last"], l_active_row=d["l_active"])
+    sc = ev.Scalars(challenges=[], beta=beta, gamma=gamma, theta=0, y=y)
+    got = ev.evaluate_h(_gate_graph(ev, spec), d["fixed"], d["advice"], d["instance"], sc, perm, K, EXT_K, d["ext_omega"], d["zeta"])
+    assert got == d["values"]
+    # and only this restatement: another rotation of z_{i-1} or no coset generator in delta leaves a residual
+    perm_bad = ev.Permutation(**{**perm.__dict__, "last_rotation": -5})
+    assert ev.evaluate_h(_gate_graph(ev, spec), d["fixed"], d["advice"], d["instance"], sc, perm_bad, K, EXT_K, d["ext_omega"],
+                         d["zeta"]) != d["values"]
+
+
+def _to_product_graph(g, spec, evaluation):
+    return evaluation.GraphEvaluator(constants=spec.fr_array(g.constants) if g.constants else np.zeros((0, 4), dtype=np.uint64),
+                                     rotations=list(g.rotations), calculations=list(g.calcs), num_intermediates=g.num_intermediates)
+
+
+def _run_gpu(h2b, spec, evaluation, g, fixed, advice, instance, sc, perm, k, j):
+    import torch
+    up = lambda col: torch.from_numpy(spec.fr_array(col).view(np.int64)).cuda()
+    dom = h2b.EvaluationDomain(j, k)
+    f_t, a_t, i_t = [up(c) for c in fixed], [up(c) for c in advice], [up(c) for c in instance]
+    pd = None
+    if perm is not None:
+        pd = evaluation.PermutationData(columns=perm.columns, sigma_cosets=[up(c) for c in perm.sigma_cosets],
+                                        z_cosets=[up(c) for c in perm.z_cosets], chunk_len=perm.chunk_len,
+                                        last_rotation=perm.last_rotation, l0=up(perm.l0), l_last=up(perm.l_last),
+                                        l_active_row=up(perm.l_active_row))
+    values = torch.empty((1 << dom.extended_k, 4), dtype=torch.int64, device="cuda")
+    fr1 = lambda v: spec.fr_array([v])[0]
+    ch = spec.fr_array(list(sc.challenges)) if len(sc.challenges) else np.zeros((0, 4), dtype=np.uint64)
+    evaluation.dev_evaluate_h(dom, _to_product_graph(g, spec, evaluation), f_t, a_t, i_t, ch, fr1(sc.beta), fr1(sc.gamma),
+                              fr1(sc.theta), fr1(sc.y), pd, values)
+    torch.cuda.synchronize()
+    return spec.fr_ints(values.cpu().numpy().view(np.uint64)), dom
+
+
+@pytest.mark.gpu
+def test_cuda_evaluate_h_reproduces_the_reference_quotient(h2b, spec):
+    """h2b_dev_evaluate_h on the recorded cosets, with the challenges recovered from the record, gives the recorded
+    quotient numerator row for row; dividing by the vanishing polynomial and extended_to_coeff on the device then
+    reproduces the recorded best_fft input / output of the reference's own extended_to_coeff call."""
+    import evaluate_h as ev
+    from halo2_prover_b200 import evaluation
+    d = _fixture(spec)
+    sol, rank, residual = _recover_challenges(d, spec)
+    assert residual == 0
+    sc = ev.Scalars(challenges=[], beta=sol[12], gamma=sol[16], theta=0, y=sol[8])
+    perm = ev.Permutation(columns=[(ev.ADVICE, 0), (ev.ADVICE, 1), (ev.ADVICE, 2), (ev.INSTANCE, 0)], sigma_cosets=d["sigma"],
+                          z_cosets=d["z"], chunk_len=1, last_rotation=-6, l0=d["l0"], l_last=d["l_last"], l_active_row=d["l_active"])
+    got, dom = _run_gpu(h2b, spec, evaluation, _gate_graph(ev, spec), d["fixed"], d["advice"], d["instance"], sc, perm, K, 3)
+    assert dom.extended_k == EXT_K
+    assert got == d["values"]
+    z = np.load(f"{GOLDEN}/{MANIFEST['arithmetic']['file']}")
+    h = dom.divide_by_vanishing_poly(spec.fr_array(got))
+    assert (h == z["fft40_in"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2])
+def test_cuda_evaluate_h_random_graph_vs_oracle(h2b, spec, seed):
+    """Random expression graphs over every ValueSource and Calculation kind, random columns, rotations in both
+    directions, two permutation chunks of unequal length: CUDA == oracle."""
+    import random
+    import evaluate_h as ev
+    from halo2_prover_b200 import evaluation
+    rng = random.Random(seed)
+    R = spec.R_MOD
+    k, j = 5, 4
+    ext_k, en = 7, 128
+    rnd_col = lambda: [rng.randrange(R) for _ in range(en)]
+    fixed, advice, instance = [rnd_col() for _ in range(3)], [rnd_col() for _ in range(4)], [rnd_col() for _ in range(2)]
+    g = ev.Graph()
+    rots = [g.add_rotation(r) for r in (0, 1, -1, 3, -7)]
+    leaves = [g.add_constant(rng.randrange(R)) for _ in range(3)]
+    leaves += [(ev.FIXED, c, rng.choice(rots)) for c in range(3)] + [(ev.ADVICE, c, rng.choice(rots)) for c in range(4)]
+    leaves += [(ev.INSTANCE, c, rng.choice(rots)) for c in range(2)]
+    leaves += [(ev.CHALLENGE, 0, 0), (ev.CHALLENGE, 1, 0), (ev.BETA, 0, 0), (ev.GAMMA, 0, 0), (ev.THETA, 0, 0), (ev.Y, 0, 0)]
+    nodes = list(leaves)
+    for _ in range(40):
+        kind = rng.choice([ev.ADD, ev.SUB, ev.MUL, ev.SQUARE, ev.DOUBLE, ev.NEGATE, ev.STORE, ev.HORNER])
+        if kind in (ev.ADD, ev.SUB, ev.MUL):
+            nodes.append(g.add_calc(kind, rng.choice(nodes), rng.choice(nodes)))
+        elif kind == ev.HORNER:
+            nodes.append(g.add_calc(kind, rng.choice(nodes), [rng.choice(nodes) for _ in range(rng.randrange(0, 4))], rng.choice(nodes)))
+        else:
+            nodes.append(g.add_calc(kind, rng.choice(nodes)))
+    g.add_calc(ev.HORNER, (ev.PREVIOUS, 0, 0), nodes[-3:], (ev.Y, 0, 0))
+    sc = ev.Scalars(challenges=[rng.randrange(R), rng.randrange(R)], beta=rng.randrange(R), gamma=rng.randrange(R),
+                    theta=rng.randrange(R), y=rng.randrange(R))
+    perm = ev.Permutation(columns=[(ev.ADVICE, 1), (ev.FIXED, 2), (ev.INSTANCE, 0), (ev.ADVICE, 3), (ev.ADVICE, 0)],
+                          sigma_cosets=[rnd_col() for _ in range(5)], z_cosets=[rnd_col() for _ in range(3)], chunk_len=2,
+                          last_rotation=-6, l0=rnd_col(), l_last=rnd_col(), l_active_row=rnd_col())
+    dom_probe = h2b.EvaluationDomain(j, k)
+    assert dom_probe.extended_k == ext_k
+    ext_omega = spec.fr_ints(dom_probe.get_extended_omega().reshape(1, 4))[0]
+    zeta = spec.fr_ints(dom_probe.g_coset.reshape(1, 4))[0]
+    want = ev.evaluate_h(g, fixed, advice, instance, sc, perm, k, ext_k, ext_omega, zeta)
+    got, _ = _run_gpu(h2b, spec, evaluation, g, fixed, advice, instance, sc, perm, k, j)
+    assert got == want
+    # no permutation argument, empty graph
+    assert _run_gpu(h2b, spec, evaluation, ev.Graph(), fixed, advice, instance, sc, None, k, j)[0] == [0] * en

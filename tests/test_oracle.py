@@ -17,7 +17,9 @@ def test_constants(spec):
     # Montgomery forms quoted in SURVEY.md section 8 (recovered from the reference binary)
     assert hex(o.to_mont(o.ROOT_OF_UNITY, o.R_MOD)).startswith("0x1d69070d")
     assert hex(o.to_mont(o.ROOT_OF_UNITY, o.R_MOD)).endswith("b639feb8")
-    assert hex(o.to_mont(o.ZETA, o.R_MOD)).startswith("0x59c805d")
+    # the immediate 0x059c805d... found in the reference binary's EvaluationDomain::new is ZETA^2 (g_coset_inv)
+    assert hex(o.to_mont(o.ZETA * o.ZETA % o.R_MOD, o.R_MOD)).startswith("0x59c805d")
+    assert o.ZETA == 0xB3C4D79D41A917585BFC41088D8DAAA78B17EA66B99C90DD
 
 
 def test_random_streams_agree(spec, href):

@@ -222,3 +222,57 @@ def test_cuda_g_to_lagrange_reproduces_reference_params(name, h2b):
     (k = 4, 7 and 10), limb for limb."""
     ent, z, g, gl = _load(name)
     assert (h2b.g_to_lagrange(g, ent["k"]) == gl).all()
+
+
+# (circuit, j = cs.degree(), [(lagrange_to_coeff record, coeff_to_extended record)], extended_to_coeff record)
+# The reference reaches best_fft through EvaluationDomain: a coeff_to_extended call shows up as a best_fft record
+# whose INPUT is the scaled, zero-padded coefficient vector; the coefficients themselves are the (1/n-scaled)
+# output of the column's earlier lagrange_to_coeff record.
+DOMAIN_RUNS = [("arithmetic", 3, [(33, 36), (34, 37), (35, 38), (24, 39), (25, 26), (31, 32)], 40)]
+
+
+def _domain_case(spec, name, j, pairs, e2c):
+    ent, z, g, gl = _load(name)
+    k = ent["k"]
+    n_inv = pow(1 << k, -1, spec.R_MOD)
+    cases = []
+    for l2c, c2e in pairs:
+        coeffs = spec.fr_array([v * n_inv % spec.R_MOD for v in spec.fr_ints(z[f"fft{l2c}_out"])])
+        cases.append((coeffs, np.ascontiguousarray(z[f"fft{c2e}_in"]), np.ascontiguousarray(z[f"fft{c2e}_out"])))
+    return k, cases, np.ascontiguousarray(z[f"fft{e2c}_in"]), np.ascontiguousarray(z[f"fft{e2c}_out"])
+
+
+@pytest.mark.parametrize("name,j,pairs,e2c", DOMAIN_RUNS)
+def test_oracle_coset_transforms_match_reference_execution(name, j, pairs, e2c, href, spec):
+    """coeff_to_extended / extended_to_coeff of the oracle on the reference's own polynomials == what the reference
+    computed (this is the check that fixes the coset generator: Fr::ZETA, not its square)."""
+    k, cases, e_in, e_out = _domain_case(spec, name, j, pairs, e2c)
+    dc = href.domain_new(j, k)
+    d = spec.EvaluationDomain(j, k)
+    for coeffs, ref_in, ref_out in cases:
+        assert (href.coeff_to_extended(dc, coeffs) == ref_out).all()
+        assert spec.fr_array(d.coeff_to_extended(spec.fr_ints(coeffs))).tolist() == ref_out.tolist()
+        # the recorded input is the coefficient vector after distribute_powers_zeta, zero-padded
+        zeta = d.g_coset
+        want_in = [c * pow(zeta, i % 3, spec.R_MOD) % spec.R_MOD for i, c in enumerate(spec.fr_ints(coeffs))]
+        assert spec.fr_ints(ref_in)[: len(want_in)] == want_in and not ref_in[len(want_in):].any()
+    # extended_to_coeff = recorded best_fft output * 1/2^ext_k * {1, zeta^-1, zeta^-2}[i % 3], truncated to n (j - 1)
+    ext_n = e_in.shape[0]
+    div = pow(ext_n, -1, spec.R_MOD)
+    zi = pow(d.g_coset, -1, spec.R_MOD)
+    want = [v * div % spec.R_MOD * pow(zi, i % 3, spec.R_MOD) % spec.R_MOD for i, v in enumerate(spec.fr_ints(e_out))]
+    want = spec.fr_array(want[: (1 << k) * (j - 1)])
+    assert (href.extended_to_coeff(dc, e_in) == want).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,j,pairs,e2c", DOMAIN_RUNS)
+def test_cuda_coset_transforms_match_reference_execution(name, j, pairs, e2c, h2b, href, spec):
+    k, cases, e_in, e_out = _domain_case(spec, name, j, pairs, e2c)
+    d = h2b.EvaluationDomain(j, k)
+    for coeffs, _, ref_out in cases:
+        assert (d.coeff_to_extended(coeffs) == ref_out).all()
+    outs = d.coeff_to_extended_many([c for c, _, _ in cases])
+    assert all((o == ref_out).all() for o, (_, _, ref_out) in zip(outs, cases))
+    dc = href.domain_new(j, k)
+    assert (d.extended_to_coeff(e_in) == href.extended_to_coeff(dc, e_in)).all()
