@@ -327,8 +327,10 @@ def run_b200(args) -> None:
                          "best_multiexp (not the Rust binary); result equal to the GPU's on the same sample"}
 
     replay = None
+    evalh = None
     if rank == 0 and world == 1 and not args.no_cpu:
         replay = bench_proof_replay(args, h2b, _ffi)
+        evalh = bench_evaluate_h(args, torch, h2b)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -377,6 +379,7 @@ def run_b200(args) -> None:
             "cpu_baseline": cpu,
             "ntt": ntt,
             "proof_replay": replay,
+            "evaluate_h": evalh,
         }
         print(json.dumps(line))
     if world > 1:
@@ -477,6 +480,43 @@ def bench_proof_replay(args, h2b, _ffi) -> dict:
                                                             "extended_to_coeff": 1},
             "gpu_ms": gpu_ms, "gpu_ms_by_call": by_call, "gpu_batched_ms": gpu_batched_ms,
             "gpu_batched_ms_by_call": by_call_batched, "batched_equals_single": bool(same_b), "cpu_ms": cpu_ms, "cpu_threads": threads, "commitments_equal": bool(same)}
+
+
+def bench_evaluate_h(args, torch, h2b) -> dict:
+    """Device time of the quotient numerator (h2b_dev_evaluate_h) for a circuit shaped like the reference's
+    arithmetic circuit (one degree-3 gate over 3 advice + 5 fixed columns, 4 permutation columns in 4 chunks) at
+    2^proof_k rows, extended columns resident in HBM."""
+    from halo2_prover_b200 import evaluation as ev
+    k = args.proof_k
+    d = h2b.EvaluationDomain(3, k)
+    en = 1 << d.extended_k
+    col = lambda seed: torch.from_numpy(rand_fr_np(en, seed).view(np.int64)).cuda()
+    fixed, advice, instance = [col(500 + i) for i in range(5)], [col(510 + i) for i in range(3)], [col(520)]
+    g = ev.GraphEvaluator(constants=rand_fr_np(1, 530), rotations=[0], num_intermediates=9, calculations=[
+        (ev.MUL, 0, (ev.ADVICE, 0, 0), (ev.FIXED, 1, 0)), (ev.MUL, 1, (ev.ADVICE, 1, 0), (ev.FIXED, 2, 0)),
+        (ev.ADD, 2, (ev.INTERMEDIATE, 0, 0), (ev.INTERMEDIATE, 1, 0)), (ev.MUL, 3, (ev.ADVICE, 0, 0), (ev.ADVICE, 1, 0)),
+        (ev.MUL, 4, (ev.INTERMEDIATE, 3, 0), (ev.FIXED, 0, 0)), (ev.ADD, 5, (ev.INTERMEDIATE, 2, 0), (ev.INTERMEDIATE, 4, 0)),
+        (ev.MUL, 6, (ev.ADVICE, 2, 0), (ev.FIXED, 3, 0)), (ev.SUB, 7, (ev.INTERMEDIATE, 5, 0), (ev.INTERMEDIATE, 6, 0)),
+        (ev.HORNER, 8, (ev.PREVIOUS, 0, 0), [(ev.INTERMEDIATE, 7, 0)], (ev.Y, 0, 0))])
+    perm = ev.PermutationData(columns=[(ev.ADVICE, 0), (ev.ADVICE, 1), (ev.ADVICE, 2), (ev.INSTANCE, 0)],
+                              sigma_cosets=[col(540 + i) for i in range(4)], z_cosets=[col(550 + i) for i in range(4)],
+                              chunk_len=1, last_rotation=-6, l0=col(560), l_last=col(561), l_active_row=col(562))
+    sc = rand_fr_np(4, 570)
+    values = torch.empty((en, 4), dtype=torch.int64, device="cuda")
+    s = torch.cuda.Stream()
+    run = lambda: ev.dev_evaluate_h(d, g, fixed, advice, instance, np.zeros((0, 4), dtype=np.uint64), sc[0], sc[1], sc[2], sc[3],
+                                    perm, values, stream=s)
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(10):
+        run()
+    e1.record(s)
+    s.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    return {"what": "h2b_dev_evaluate_h, arithmetic-circuit shape, resident extended columns", "k": k, "extended_k": int(d.extended_k),
+            "ms": ms, "rows_per_s": en / (ms * 1e-3)}
 
 
 def bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, imad_gops) -> dict:

@@ -263,6 +263,15 @@ def test_oracle_coset_transforms_match_reference_execution(name, j, pairs, e2c, 
     want = [v * div % spec.R_MOD * pow(zi, i % 3, spec.R_MOD) % spec.R_MOD for i, v in enumerate(spec.fr_ints(e_out))]
     want = spec.fr_array(want[: (1 << k) * (j - 1)])
     assert (href.extended_to_coeff(dc, e_in) == want).all()
+    # divide_by_vanishing_poly: the recorded extended_to_coeff input is h / (X^n - 1); multiplying the numerator
+    # back (values = input / t_evaluations) and dividing again must return it, and t_evaluations must be
+    # 1 / ((zeta omega_ext^i)^n - 1) for the reference's zeta
+    tev = spec.fr_ints(np.array(list(dc.t_evaluations), dtype=np.uint64)[: 4 * dc.n_t].reshape(-1, 4))
+    ext_omega = pow(spec.ROOT_OF_UNITY, 1 << (28 - dc.extended_k), spec.R_MOD)
+    assert tev == [pow((pow(d.g_coset * pow(ext_omega, i, spec.R_MOD) % spec.R_MOD, 1 << k, spec.R_MOD) - 1) % spec.R_MOD, -1,
+                       spec.R_MOD) for i in range(dc.n_t)]
+    numer = spec.fr_array([v * pow(tev[i % dc.n_t], -1, spec.R_MOD) % spec.R_MOD for i, v in enumerate(spec.fr_ints(e_in))])
+    assert (href.divide_by_vanishing_poly(dc, numer) == e_in).all()
 
 
 @pytest.mark.gpu
