@@ -1873,6 +1873,23 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
     return leave(g->stream, H2B_OK);
 }
 
+int h2b_dev_divide_by_vanishing_poly(const h2b_domain *d, void *d_a, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (!d_a) return fail(H2B_ERR_ARG, "divide_by_vanishing_poly: null pointer");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    TRY(enter(s));
+    const size_t n = (size_t)1 << d->extended_k;
+    void *dt;
+    TRY(get_buf(BUF_MISC, (size_t)d->n_t * 32, &dt));
+    CU(cudaMemcpyAsync(dt, d->t_evaluations, (size_t)d->n_t * 32, cudaMemcpyHostToDevice, s));
+    fr_scale_cyclic_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>((Fe *)d_a, (uint32_t)n, (const Fe *)dt, d->n_t);
+    LAUNCHED();
+    return leave(s, H2B_OK);
+}
+
 // ---- test hooks
 int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -118,6 +118,21 @@ class EvaluationDomain:
         from .arithmetic import _ptr, _stream_ptr
         _ffi.check(_ffi.lib().h2b_dev_coeff_to_extended(C.byref(self._d), _ptr(in_t), _ptr(out_t), _stream_ptr(stream)))
 
+    def dev_divide_by_vanishing_poly(self, a_t, stream=None) -> None:
+        from .arithmetic import _ptr, _stream_ptr
+        _ffi.check(_ffi.lib().h2b_dev_divide_by_vanishing_poly(C.byref(self._d), _ptr(a_t), _stream_ptr(stream)))
+
+    def dev_lagrange_to_coeff_many(self, a_t, m: int, stream=None) -> None:
+        """m columns one after the other in ``a_t`` ((m * 2^k, 4)), in place."""
+        from .arithmetic import _ptr, _stream_ptr
+        _ffi.check(_ffi.lib().h2b_dev_lagrange_to_coeff_many(C.byref(self._d), _ptr(a_t), C.c_size_t(m), _stream_ptr(stream)))
+
+    def dev_coeff_to_extended_many(self, in_t, out_t, m: int, stream=None) -> None:
+        """m columns: in_t (m * 2^k, 4) -> out_t (m * 2^extended_k, 4)."""
+        from .arithmetic import _ptr, _stream_ptr
+        _ffi.check(_ffi.lib().h2b_dev_coeff_to_extended_many(C.byref(self._d), _ptr(in_t), _ptr(out_t), C.c_size_t(m),
+                                                            _stream_ptr(stream)))
+
     def dev_extended_to_coeff(self, in_t, out_t, stream=None) -> None:
         from .arithmetic import _ptr, _stream_ptr
         _ffi.check(_ffi.lib().h2b_dev_extended_to_coeff(C.byref(self._d), _ptr(in_t), _ptr(out_t), _stream_ptr(stream)))

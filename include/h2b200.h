@@ -146,6 +146,7 @@ int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *s
 int h2b_dev_lagrange_to_coeff(const h2b_domain *d, void *d_a, void *stream);
 int h2b_dev_coeff_to_extended(const h2b_domain *d, const void *d_in, void *d_out, void *stream);
 int h2b_dev_extended_to_coeff(const h2b_domain *d, const void *d_in, void *d_out, void *stream);
+int h2b_dev_divide_by_vanishing_poly(const h2b_domain *d, void *d_a /* 2^extended_k, in place */, void *stream);
 /* m columns one after the other in HBM: d_a + q * 2^k (in place); d_in + q * 2^k -> d_out + q * 2^extended_k. */
 int h2b_dev_lagrange_to_coeff_many(const h2b_domain *d, void *d_a, size_t m, void *stream);
 int h2b_dev_coeff_to_extended_many(const h2b_domain *d, const void *d_in, void *d_out, size_t m, void *stream);

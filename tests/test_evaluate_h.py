@@ -224,3 +224,56 @@ def test_cuda_evaluate_h_random_graph_vs_oracle(h2b, spec, seed):
     assert got == want
     # no permutation argument, empty graph
     assert _run_gpu(h2b, spec, evaluation, ev.Graph(), fixed, advice, instance, sc, None, k, j)[0] == [0] * en
+
+
+@pytest.mark.gpu
+def test_cuda_resident_quotient_pipeline_reproduces_the_h_commitments(h2b, spec, href):
+    """The whole quotient step with nothing leaving HBM: coefficient polynomials of the recorded proof ->
+    coeff_to_extended (batched) -> evaluate_h -> divide_by_vanishing_poly -> extended_to_coeff -> commit of the h
+    pieces.  The h pieces equal the scalars of the reference's two h commitments (MSM records 17, 18) and the
+    commitments are the bytes at words 8 and 9 of the reference's proof."""
+    import torch
+    import evaluate_h as ev
+    from halo2_prover_b200 import evaluation
+    d = _fixture(spec)
+    sol, _, residual = _recover_challenges(d, spec)
+    assert residual == 0
+    z = np.load(f"{GOLDEN}/{MANIFEST['arithmetic']['file']}")
+    R = spec.R_MOD
+    n_inv = pow(N, -1, R)
+    up = lambda col: torch.from_numpy(spec.fr_array(col).view(np.int64)).cuda()
+    dom = h2b.EvaluationDomain(3, K)
+    # advice l, r, o and the instance column in coefficient form (recorded lagrange_to_coeff outputs / n), one after the other
+    coeffs = np.concatenate([spec.fr_array([v * n_inv % R for v in spec.fr_ints(z[f"fft{i}_out"])]) for i in (33, 34, 35, 24)])
+    c_t = torch.from_numpy(coeffs.view(np.int64)).cuda()
+    ext_t = torch.empty((4 * EN, 4), dtype=torch.int64, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    dom.dev_coeff_to_extended_many(c_t, ext_t, 4, stream=s)
+    cols = [ext_t[i * EN:(i + 1) * EN] for i in range(4)]
+    g = _to_product_graph(_gate_graph(ev, spec), spec, evaluation)
+    fixed_t = [up(c) for c in d["fixed"]]
+    pd = evaluation.PermutationData(columns=[(ev.ADVICE, 0), (ev.ADVICE, 1), (ev.ADVICE, 2), (ev.INSTANCE, 0)],
+                                    sigma_cosets=[up(c) for c in d["sigma"]], z_cosets=[up(c) for c in d["z"]], chunk_len=1,
+                                    last_rotation=-6, l0=up(d["l0"]), l_last=up(d["l_last"]), l_active_row=up(d["l_active"]))
+    torch.cuda.synchronize()
+    values = torch.empty((EN, 4), dtype=torch.int64, device="cuda")
+    fr1 = lambda v: spec.fr_array([v])[0]
+    evaluation.dev_evaluate_h(dom, g, fixed_t, cols[:3], cols[3:], np.zeros((0, 4), dtype=np.uint64), fr1(sol[12]), fr1(sol[16]),
+                              fr1(0), fr1(sol[8]), pd, values, stream=s)
+    dom.dev_divide_by_vanishing_poly(values, stream=s)
+    h_t = torch.empty((N * 2, 4), dtype=torch.int64, device="cuda")
+    dom.dev_extended_to_coeff(values, h_t, stream=s)
+    params = h2b.ParamsKZG.read(z["params"].tobytes())
+    out_t = torch.empty((2, 12), dtype=torch.int64, device="cuda")
+    from halo2_prover_b200 import _ffi
+    import ctypes as C
+    _ffi.check(_ffi.lib().h2b_dev_commit_many(C.c_uint64(params._handles["g"]), C.c_void_p(h_t.data_ptr()), C.c_size_t(N),
+                                              C.c_size_t(2), C.c_void_p(out_t.data_ptr()), C.c_void_p(s.cuda_stream)))
+    s.synchronize()
+    h = h_t.cpu().numpy().view(np.uint64)
+    assert (h[:N] == z["msm17_scalars"]).all() and (h[N:] == z["msm18_scalars"]).all()
+    enc = h2b.g1_to_bytes(out_t.cpu().numpy().view(np.uint64))
+    proof = z["proof"].tobytes()
+    assert enc == proof[32 * 8: 32 * 10]
+    params.release()
