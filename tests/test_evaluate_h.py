@@ -277,3 +277,97 @@ def test_cuda_resident_quotient_pipeline_reproduces_the_h_commitments(h2b, spec,
     proof = z["proof"].tobytes()
     assert enc == proof[32 * 8: 32 * 10]
     params.release()
+
+
+# ---------------------------------------------------------------------------------------------- Collatz (k = 10)
+# Second pin: four gates (Horner over several gate polynomials), Rotation::next inside the gates with
+# rot_scale = 4, selectors turned into fixed columns, one permutation column in a chunk of length 2.
+# Fixture: tests/golden/wasm_collatz_k10_evalh.npz (oracle/wasm/make_evalh_golden.py).
+CK, CEXT = 10, 12
+CN, CEN = 1 << CK, 1 << CEXT
+
+
+def _collatz_fixture(spec):
+    z = np.load(f"{GOLDEN}/wasm_collatz_k10_evalh.npz")
+    R = spec.R_MOD
+    A = lambda name: spec.fr_ints(z[name])
+    d = {"fixed": [A("fixed0"), A("fixed1")], "sigma": [A("sigma0")], "l0": A("l0"), "l_blind": A("l_blind"), "l_last": A("l_last"),
+         "z": [A("z0")], "advice": [A("advice0"), A("advice1"), A("advice2")], "instance": []}
+    d["ext_omega"] = pow(spec.ROOT_OF_UNITY, 1 << (28 - CEXT), R)
+    # coset generator read off the record: coefficient 1 of the witness column is multiplied by it
+    d["zeta"] = spec.fr_ints(z["advice0_ext_in"][1:2])[0] * pow(spec.fr_ints(z["advice0_coeff_fft"][1:2])[0] * pow(CN, -1, R), -1, R) % R
+    d["l_active"] = [(1 - a - b) % R for a, b in zip(d["l_last"], d["l_blind"])]
+    tev = [pow((pow(d["zeta"] * pow(d["ext_omega"], i, R) % R, CN, R) - 1) % R, -1, R) for i in range(CEN // CN)]
+    d["values"] = [v * pow(tev[i % len(tev)], -1, R) % R for i, v in enumerate(A("quotient_in"))]
+    d["quotient_in"] = z["quotient_in"]
+    return d
+
+
+def _collatz_graph(ev, spec):
+    """circuits/src/collatz.rs:36-82: is_even, is_odd, is_one, final_element, in that order; the selectors become the
+    fixed columns 1 (`selector`) and 0 (`final_entry`) (the only assignment consistent with the record)."""
+    g = ev.Graph()
+    cur, nxt = g.add_rotation(0), g.add_rotation(1)
+    x, y = (ev.ADVICE, 0, cur), (ev.ADVICE, 0, nxt)
+    is_odd, is_one = (ev.ADVICE, 1, cur), (ev.ADVICE, 2, cur)
+    sel, fin = (ev.FIXED, 1, cur), (ev.FIXED, 0, cur)
+    one, two, three = g.add_constant(1), g.add_constant(2), g.add_constant(3)
+    c = g.add_calc
+    g1 = c(ev.MUL, sel, c(ev.MUL, c(ev.SUB, one, is_odd), c(ev.SUB, x, c(ev.MUL, two, y))))
+    g2 = c(ev.MUL, c(ev.MUL, sel, c(ev.SUB, one, is_one)), c(ev.MUL, is_odd, c(ev.SUB, c(ev.ADD, c(ev.MUL, three, x), one), y)))
+    g3 = c(ev.MUL, c(ev.MUL, sel, is_one), c(ev.ADD, c(ev.SUB, x, y), c(ev.SUB, x, one)))
+    g4 = c(ev.MUL, fin, c(ev.SUB, one, x))
+    c(ev.HORNER, (ev.PREVIOUS, 0, 0), [g1, g2, g3, g4], (ev.Y, 0, 0))
+    return g
+
+
+def _collatz_challenges(d, spec):
+    """7 Horner terms (4 gates, l0 (1 - z), l_last (z^2 - z), the product term A + beta B + gamma C): 8 unknown monomials
+    y^6..y, beta, gamma; 96 sampled rows."""
+    import random
+    R = spec.R_MOD
+    adv, fx, zc, sig = d["advice"], d["fixed"], d["z"][0], d["sigma"][0]
+    rows, rhs = [], []
+    for idx in random.Random(3).sample(range(CEN), 96):
+        nx = (idx + 4) % CEN
+        x, y, odd, one = adv[0][idx], adv[0][nx], adv[1][idx], adv[2][idx]
+        sel, fin = fx[1][idx], fx[0][idx]
+        terms = [sel * (1 - odd) * (x - 2 * y), sel * (1 - one) * odd * (3 * x + 1 - y), sel * one * ((x - y) + (x - 1)), fin * (1 - x),
+                 (1 - zc[idx]) * d["l0"][idx], (zc[idx] ** 2 - zc[idx]) * d["l_last"][idx]]
+        X = d["zeta"] * pow(d["ext_omega"], idx, R) % R
+        zn, zz, cval, la = zc[nx], zc[idx], adv[0][idx], d["l_active"][idx]
+        rows.append([t % R for t in terms] + [(zn * sig[idx] - zz * X) * la % R, (zn - zz) * la % R])
+        rhs.append((d["values"][idx] - (zn - zz) * cval * la) % R)
+    return _solve(rows, rhs, R)
+
+
+def test_oracle_evaluate_h_collatz_pin(spec):
+    import evaluate_h as ev
+    R = spec.R_MOD
+    d = _collatz_fixture(spec)
+    assert d["zeta"] == spec.ZETA
+    sol, rank, residual = _collatz_challenges(d, spec)
+    assert rank == 8 and residual == 0
+    y, beta, gamma = sol[5], sol[6], sol[7]
+    assert all(sol[6 - p] == pow(y, p, R) for p in range(1, 7))
+    perm = ev.Permutation(columns=[(ev.ADVICE, 0)], sigma_cosets=d["sigma"], z_cosets=d["z"], chunk_len=2, last_rotation=-6,
+                          l0=d["l0"], l_last=d["l_last"], l_active_row=d["l_active"])
+    sc = ev.Scalars(challenges=[], beta=beta, gamma=gamma, theta=0, y=y)
+    got = ev.evaluate_h(_collatz_graph(ev, spec), d["fixed"], d["advice"], [], sc, perm, CK, CEXT, d["ext_omega"], d["zeta"])
+    assert got == d["values"]   # all 4096 rows, 8 of them used up by the unknowns
+
+
+@pytest.mark.gpu
+def test_cuda_evaluate_h_collatz_reproduces_the_reference_quotient(h2b, spec):
+    import evaluate_h as ev
+    from halo2_prover_b200 import evaluation
+    d = _collatz_fixture(spec)
+    sol, rank, residual = _collatz_challenges(d, spec)
+    assert residual == 0
+    perm = ev.Permutation(columns=[(ev.ADVICE, 0)], sigma_cosets=d["sigma"], z_cosets=d["z"], chunk_len=2, last_rotation=-6,
+                          l0=d["l0"], l_last=d["l_last"], l_active_row=d["l_active"])
+    sc = ev.Scalars(challenges=[], beta=sol[6], gamma=sol[7], theta=0, y=sol[5])
+    got, dom = _run_gpu(h2b, spec, evaluation, _collatz_graph(ev, spec), d["fixed"], d["advice"], [], sc, perm, CK, 4)
+    assert dom.extended_k == CEXT
+    assert got == d["values"]
+    assert (dom.divide_by_vanishing_poly(spec.fr_array(got)) == d["quotient_in"]).all()
