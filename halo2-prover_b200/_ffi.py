@@ -20,7 +20,7 @@ ERR_NAMES = {-1: "H2B_ERR_ARG", -2: "H2B_ERR_CUDA", -3: "H2B_ERR_OOM", -4: "H2B_
 # every symbol include/h2b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "h2b_init", "h2b_shutdown", "h2b_last_error", "h2b_abi_version",
-    "h2b_best_multiexp", "h2b_srs_register", "h2b_srs_release", "h2b_commit", "h2b_g1_fold", "h2b_g1_to_bytes", "h2b_g_to_lagrange", "h2b_dev_evaluate_h",
+    "h2b_best_multiexp", "h2b_srs_register", "h2b_srs_release", "h2b_commit", "h2b_g1_fold", "h2b_g1_to_bytes", "h2b_g_to_lagrange", "h2b_dev_evaluate_h", "h2b_dev_evaluate_h_lookup",
     "h2b_best_fft", "h2b_domain_new", "h2b_lagrange_to_coeff", "h2b_coeff_to_extended",
     "h2b_extended_to_coeff", "h2b_divide_by_vanishing_poly", "h2b_lagrange_to_coeff_many", "h2b_coeff_to_extended_many",
     "h2b_dev_lagrange_to_coeff_many", "h2b_dev_coeff_to_extended_many", "h2b_dev_divide_by_vanishing_poly",

@@ -54,14 +54,10 @@ H2B_DI Fe eval_source(uint64_t src, const EvalGates &g, const uint32_t *rot_idx,
     }
 }
 
-// values[idx] = custom_gates.evaluate(previous = values[idx]) : one thread per row of the extended domain
-__global__ void __launch_bounds__(128)
-evalh_gates_kernel(EvalGates g, Fe *__restrict__ values) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.size) return;
+// GraphEvaluator::evaluate at row idx (the value of the last calculation; zero for an empty graph, as upstream)
+H2B_DI Fe eval_graph(const EvalGates &g, uint32_t idx, const Fe &prev) {
     uint32_t rot_idx[kMaxRotations];
     for (uint32_t r = 0; r < g.num_rotations; r++) rot_idx[r] = rotation_idx(idx, g.rotations[r], g.rot_scale, g.size);
-    const Fe prev = load_fe(&values[idx]);
     Fe last = Fr::zero();
     const uint64_t *pc = g.calcs;
     for (uint32_t c = 0; c < g.num_calcs; c++) {
@@ -85,7 +81,42 @@ evalh_gates_kernel(EvalGates g, Fe *__restrict__ values) {
         store_fe(&g.scratch[(size_t)target * g.size + idx], v);
         last = v;
     }
-    store_fe(&values[idx], last);  // an empty graph evaluates to zero, as upstream
+    return last;
+}
+
+// values[idx] = custom_gates.evaluate(previous = values[idx]) : one thread per row of the extended domain
+__global__ void __launch_bounds__(128)
+evalh_gates_kernel(EvalGates g, Fe *__restrict__ values) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.size) return;
+    store_fe(&values[idx], eval_graph(g, idx, load_fe(&values[idx])));
+}
+
+// One lookup argument folded into values (evaluation.rs, "Lookup constraints").  g is that lookup's graph:
+// (compressed input + beta) * (compressed table + gamma).
+struct EvalLookup {
+    const Fe *product, *permuted_input, *permuted_table, *l0, *l_last, *l_active;
+};
+__global__ void __launch_bounds__(128)
+evalh_lookup_kernel(EvalGates g, EvalLookup lk, Fe *__restrict__ values) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.size) return;
+    const Fe table_value = eval_graph(g, idx, Fr::zero());
+    const uint32_t r_next = rotation_idx(idx, 1, g.rot_scale, g.size), r_prev = rotation_idx(idx, -1, g.rot_scale, g.size);
+    const Fe one = Fr::one();
+    const Fe l0 = load_fe_ro(&lk.l0[idx]), l_last = load_fe_ro(&lk.l_last[idx]), l_active = load_fe_ro(&lk.l_active[idx]);
+    const Fe z = load_fe_ro(&lk.product[idx]), a = load_fe_ro(&lk.permuted_input[idx]), s = load_fe_ro(&lk.permuted_table[idx]);
+    const Fe a_minus_s = Fr::sub(a, s);
+    Fe v = load_fe(&values[idx]);
+    v = Fr::add(Fr::mul(v, g.y), Fr::mul(Fr::sub(one, z), l0));
+    v = Fr::add(Fr::mul(v, g.y), Fr::mul(Fr::sub(Fr::sqr(z), z), l_last));
+    {
+        const Fe left = Fr::mul(Fr::mul(load_fe_ro(&lk.product[r_next]), Fr::add(a, g.beta)), Fr::add(s, g.gamma));
+        v = Fr::add(Fr::mul(v, g.y), Fr::mul(Fr::sub(left, Fr::mul(z, table_value)), l_active));
+    }
+    v = Fr::add(Fr::mul(v, g.y), Fr::mul(a_minus_s, l0));
+    v = Fr::add(Fr::mul(v, g.y), Fr::mul(Fr::mul(a_minus_s, Fr::sub(a, load_fe_ro(&lk.permuted_input[r_prev]))), l_active));
+    store_fe(&values[idx], v);
 }
 
 struct EvalPerm {

@@ -849,8 +849,9 @@ int dev_extended_to_coeff(const h2b_domain *d, const Fe *in, Fe *out, cudaStream
 }
 
 // G1Affine::to_bytes of halo2curves 0.3.2 (the 32-byte form the transcript writes for every commitment):
-// x as a canonical little-endian integer, bit 6 of byte 31 = y mod 2, the identity = 32 zero bytes
-// (format confirmed on the reference's own proof bytes, tests/test_wasm_golden.py).
+// x as a canonical little-endian integer, bit 6 of byte 31 = y mod 2 (confirmed on the reference's own proof
+// bytes, tests/test_wasm_golden.py); the identity is written as 32 zero bytes (no identity occurs in those
+// proofs, so that case rests on the upstream source as remembered, not on a recorded byte).
 __global__ void g1_to_bytes_kernel(const Projective *__restrict__ pts, uint32_t m, uint32_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
@@ -1488,8 +1489,23 @@ static bool evalh_source_ok(uint64_t src, const h2b_eval_h *a) {
         default: return kind <= VS_PREVIOUS;
     }
 }
+struct EvalhLookupPtrs {
+    const void *product, *permuted_input, *permuted_table;
+};
+static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookupPtrs *lookup, void *d_values, void *stream);
 int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
+    return evalh_run(d, a, nullptr, d_values, stream);
+}
+int h2b_dev_evaluate_h_lookup(const h2b_domain *d, const h2b_eval_h *a, const void *d_product, const void *d_permuted_input,
+                              const void *d_permuted_table, void *d_values, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!d_product || !d_permuted_input || !d_permuted_table) return fail(H2B_ERR_ARG, "evaluate_h_lookup: null pointer");
+    if (a && (!a->l0 || !a->l_last || !a->l_active_row)) return fail(H2B_ERR_ARG, "evaluate_h_lookup: null l0 / l_last / l_active_row");
+    const EvalhLookupPtrs lp{d_product, d_permuted_input, d_permuted_table};
+    return evalh_run(d, a, &lp, d_values, stream);
+}
+static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookupPtrs *lookup, void *d_values, void *stream) {
     TRY(ensure_ctx());
     TRY(check_domain(d));
     if (!a || !d_values) return fail(H2B_ERR_ARG, "evaluate_h: null pointer");
@@ -1514,7 +1530,7 @@ int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values,
         }
         if (w != a->calc_words) return fail(H2B_ERR_ARG, "evaluate_h: calc_words does not match the calculation list");
     }
-    const uint32_t P = a->num_perm_columns;
+    const uint32_t P = lookup ? 0 : a->num_perm_columns;
     uint32_t sets = 0;
     if (P) {
         if (a->chunk_len == 0) return fail(H2B_ERR_ARG, "evaluate_h: chunk_len = 0");
@@ -1553,7 +1569,7 @@ int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values,
     if (!blob.empty()) CU(cudaMemcpyAsync(dblob, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice, s));
     Fe *scratch;
     TRY(get_buf(BUF_EVALH_SCRATCH, (size_t)std::max(a->num_intermediates, 1u) * size * sizeof(Fe), (void **)&scratch));
-    CU(cudaMemsetAsync(d_values, 0, (size_t)size * sizeof(Fe), s));
+    if (!lookup) CU(cudaMemsetAsync(d_values, 0, (size_t)size * sizeof(Fe), s));
     EvalGates eg;
     eg.fixed = (const Fe *const *)(dblob + o_fixed);
     eg.advice = (const Fe *const *)(dblob + o_adv);
@@ -1572,6 +1588,19 @@ int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values,
     memcpy(&eg.theta, a->theta, 32);
     memcpy(&eg.y, a->y, 32);
     const uint32_t blocks = (size + 127) / 128;
+    if (lookup) {
+        EvalLookup el;
+        el.product = (const Fe *)lookup->product;
+        el.permuted_input = (const Fe *)lookup->permuted_input;
+        el.permuted_table = (const Fe *)lookup->permuted_table;
+        el.l0 = (const Fe *)a->l0;
+        el.l_last = (const Fe *)a->l_last;
+        el.l_active = (const Fe *)a->l_active_row;
+        evalh_lookup_kernel<<<blocks, 128, 0, s>>>(eg, el, (Fe *)d_values);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(s));
+        return leave(s, H2B_OK);
+    }
     evalh_gates_kernel<<<blocks, 128, 0, s>>>(eg, (Fe *)d_values);
     LAUNCHED();
     if (P) {

@@ -80,11 +80,7 @@ def _ptrs(tensors) -> C.Array:
     return arr
 
 
-def dev_evaluate_h(domain, graph: GraphEvaluator, fixed, advice, instance, challenges: np.ndarray, beta, gamma, theta, y,
-                   perm: PermutationData | None, values_t, stream=None) -> None:
-    """Evaluator::evaluate_h into ``values_t`` ((2^extended_k, 4) int64 cuda tensor).  Columns are cuda tensors
-    holding extended cosets; scalars are (4,) uint64 Montgomery limbs."""
-    from .arithmetic import _stream_ptr
+def _make_args(graph: GraphEvaluator, fixed, advice, instance, challenges, beta, gamma, theta, y, perm):
     a = _EvalH()
     keep = []
     a.num_fixed, a.num_advice, a.num_instance = len(fixed), len(advice), len(instance)
@@ -119,4 +115,26 @@ def dev_evaluate_h(domain, graph: GraphEvaluator, fixed, advice, instance, chall
         a.sigma_cosets = C.cast(sig, C.POINTER(C.c_void_p))
         a.z_cosets = C.cast(zc, C.POINTER(C.c_void_p))
         a.l0, a.l_last, a.l_active_row = perm.l0.data_ptr(), perm.l_last.data_ptr(), perm.l_active_row.data_ptr()
+    keep += [ch, consts, rots, calcs]
+    return a, keep
+
+
+def dev_evaluate_h(domain, graph: GraphEvaluator, fixed, advice, instance, challenges: np.ndarray, beta, gamma, theta, y,
+                   perm: PermutationData | None, values_t, stream=None) -> None:
+    """Evaluator::evaluate_h (custom gates + permutation argument) into ``values_t`` ((2^extended_k, 4) int64 cuda
+    tensor).  Columns are cuda tensors holding extended cosets; scalars are (4,) uint64 Montgomery limbs."""
+    from .arithmetic import _stream_ptr
+    a, keep = _make_args(graph, fixed, advice, instance, challenges, beta, gamma, theta, y, perm)
     _ffi.check(_ffi.lib().h2b_dev_evaluate_h(C.byref(domain._d), C.byref(a), C.c_void_p(values_t.data_ptr()), _stream_ptr(stream)))
+
+
+def dev_evaluate_h_lookup(domain, lookup_graph: GraphEvaluator, fixed, advice, instance, challenges: np.ndarray, beta, gamma,
+                          theta, y, l0, l_last, l_active_row, product_t, permuted_input_t, permuted_table_t, values_t,
+                          stream=None) -> None:
+    """One lookup argument folded into ``values_t`` after dev_evaluate_h (call once per lookup, in order)."""
+    from .arithmetic import _stream_ptr
+    a, keep = _make_args(lookup_graph, fixed, advice, instance, challenges, beta, gamma, theta, y, None)
+    a.l0, a.l_last, a.l_active_row = l0.data_ptr(), l_last.data_ptr(), l_active_row.data_ptr()
+    _ffi.check(_ffi.lib().h2b_dev_evaluate_h_lookup(
+        C.byref(domain._d), C.byref(a), C.c_void_p(product_t.data_ptr()), C.c_void_p(permuted_input_t.data_ptr()),
+        C.c_void_p(permuted_table_t.data_ptr()), C.c_void_p(values_t.data_ptr()), _stream_ptr(stream)))

@@ -113,8 +113,8 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a);
  * (kzg/commitment.rs:68-114).  g_bases and out: 2^k x 8 u64 affine points. */
 int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out);
 /* G1Affine::to_bytes (halo2curves 0.3.2) of m projective results: normalise, x as 32 little-endian canonical
- * bytes with bit 6 of byte 31 = y mod 2, identity = zeros -- the bytes create_proof's transcript writes for a
- * commitment (`transcript.write_point`).  points: m x 12 u64, out: m x 32 bytes. */
+ * bytes with bit 6 of byte 31 = y mod 2 (pinned on the reference's proof bytes), identity = zeros (not
+ * exercised by those proofs) -- the bytes create_proof's transcript writes for a commitment.  points: m x 12 u64, out: m x 32 bytes. */
 int h2b_g1_to_bytes(const uint64_t *points, size_t m, uint8_t *out);
 
 /* m polynomials of n scalars each committed against bases[0..n] of ONE registered SRS in a single pass
@@ -188,6 +188,13 @@ typedef struct h2b_eval_h {
 } h2b_eval_h;
 /* d_values: 2^extended_k x 32 B in HBM, overwritten (upstream starts from domain.empty_extended()). */
 int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values, void *stream);
+/* One lookup argument folded into d_values after h2b_dev_evaluate_h (evaluation.rs, "Lookup constraints"; call once
+ * per lookup, in cs.lookups order).  `a` carries the column tables, the scalars, l0 / l_last / l_active_row and, as
+ * its graph, THAT lookup's GraphEvaluator ((compressed input + beta) * (compressed table + gamma)); its permutation
+ * fields are ignored.  d_product / d_permuted_input / d_permuted_table: that lookup's extended cosets.
+ * Parity of this entry point is not pinned on a reference record: none of the reference's circuits has a lookup. */
+int h2b_dev_evaluate_h_lookup(const h2b_domain *d, const h2b_eval_h *a, const void *d_product, const void *d_permuted_input,
+                              const void *d_permuted_table, void *d_values, void *stream);
 
 /* ---- tuning / introspection ------------------------------------------------------- */
 /* Override the MSM window (0 = automatic). */

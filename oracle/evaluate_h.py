@@ -140,6 +140,40 @@ class Permutation:
     l_active_row: Sequence[int]
 
 
+@dataclass
+class Lookup:
+    """lookup::Argument on the extended coset.  ``graph`` is upstream's per-lookup GraphEvaluator, whose value is
+    (theta-compressed input + beta) * (theta-compressed table + gamma).  PARITY UNPINNED: none of the reference's
+    circuits has a lookup argument, so this part rests on the upstream source as restated, not on a record."""
+    graph: Graph
+    product_coset: Sequence[int]
+    permuted_input_coset: Sequence[int]
+    permuted_table_coset: Sequence[int]
+
+
+def fold_lookup(values: List[int], lk: Lookup, fixed, advice, instance, sc: Scalars, l0, l_last, l_active_row,
+                k: int, extended_k: int) -> List[int]:
+    """evaluation.rs, "Lookup constraints": five terms folded into ``values`` with y."""
+    size = 1 << extended_k
+    rot_scale = 1 << (extended_k - k)
+    y, beta, gamma = sc.y, sc.beta, sc.gamma
+    out = list(values)
+    for idx in range(size):
+        table_value = graph_evaluate(lk.graph, fixed, advice, instance, sc, 0, idx, rot_scale, size)
+        r_next = get_rotation_idx(idx, 1, rot_scale, size)
+        r_prev = get_rotation_idx(idx, -1, rot_scale, size)
+        z, a, s_ = lk.product_coset, lk.permuted_input_coset, lk.permuted_table_coset
+        a_minus_s = a[idx] - s_[idx]
+        v = out[idx]
+        v = (v * y + (1 - z[idx]) * l0[idx]) % R
+        v = (v * y + (z[idx] * z[idx] - z[idx]) * l_last[idx]) % R
+        v = (v * y + (z[r_next] * (a[idx] + beta) * (s_[idx] + gamma) - z[idx] * table_value) * l_active_row[idx]) % R
+        v = (v * y + a_minus_s * l0[idx]) % R
+        v = (v * y + a_minus_s * (a[idx] - a[r_prev]) * l_active_row[idx]) % R
+        out[idx] = v
+    return out
+
+
 def evaluate_h(graph: Graph, fixed, advice, instance, sc: Scalars, perm: Permutation | None,
                k: int, extended_k: int, extended_omega: int, zeta: int) -> List[int]:
     """Evaluator::evaluate_h for one circuit instance without lookups; ``zeta`` is the domain's coset generator

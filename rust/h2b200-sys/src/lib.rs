@@ -54,6 +54,10 @@ extern "C" {
     pub fn h2b_params_read(bytes: *const u8, len: usize, k: *mut u32, g: *mut u64, g_lagrange: *mut u64) -> c_int;
     pub fn h2b_lagrange_to_coeff_many(d: *const H2bDomain, cols: *const *mut u64, m: usize) -> c_int;
     pub fn h2b_coeff_to_extended_many(d: *const H2bDomain, input: *const *const u64, out: *const *mut u64, m: usize) -> c_int;
+    pub fn h2b_dev_evaluate_h(d: *const H2bDomain, a: *const c_void /* h2b_eval_h, include/h2b200.h */, values: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_evaluate_h_lookup(d: *const H2bDomain, a: *const c_void, product: *const c_void, permuted_input: *const c_void,
+                                     permuted_table: *const c_void, values: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_divide_by_vanishing_poly(d: *const H2bDomain, a: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn h2b_g_to_lagrange(g: *const u64, k: u32, out: *mut u64) -> c_int;
     pub fn h2b_g1_to_bytes(points: *const u64, m: usize, out: *mut u8) -> c_int;
     pub fn h2b_dev_msm(c: *const c_void, b: *const c_void, n: usize, out: *mut c_void, stream: *mut c_void) -> c_int;

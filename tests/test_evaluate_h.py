@@ -224,6 +224,25 @@ def test_cuda_evaluate_h_random_graph_vs_oracle(h2b, spec, seed):
     assert got == want
     # no permutation argument, empty graph
     assert _run_gpu(h2b, spec, evaluation, ev.Graph(), fixed, advice, instance, sc, None, k, j)[0] == [0] * en
+    # a lookup argument folded in afterwards (parity not pinned on a reference record: no reference circuit has one)
+    import torch
+    lg = ev.Graph()
+    r0, r1 = lg.add_rotation(0), lg.add_rotation(-1)
+    cin = lg.add_calc(ev.HORNER, lg.add_constant(0), [(ev.ADVICE, 0, r0), (ev.ADVICE, 2, r1)], (ev.THETA, 0, 0))
+    ctab = lg.add_calc(ev.HORNER, lg.add_constant(0), [(ev.FIXED, 0, r0), (ev.FIXED, 1, r0)], (ev.THETA, 0, 0))
+    lg.add_calc(ev.MUL, lg.add_calc(ev.ADD, cin, (ev.BETA, 0, 0)), lg.add_calc(ev.ADD, ctab, (ev.GAMMA, 0, 0)))
+    lk = ev.Lookup(graph=lg, product_coset=rnd_col(), permuted_input_coset=rnd_col(), permuted_table_coset=rnd_col())
+    want2 = ev.fold_lookup(want, lk, fixed, advice, instance, sc, perm.l0, perm.l_last, perm.l_active_row, k, ext_k)
+    up = lambda col: torch.from_numpy(spec.fr_array(col).view(np.int64)).cuda()
+    dom = h2b.EvaluationDomain(j, k)
+    values = up(want)
+    fr1 = lambda v: spec.fr_array([v])[0]
+    evaluation.dev_evaluate_h_lookup(dom, _to_product_graph(lg, spec, evaluation), [up(c) for c in fixed], [up(c) for c in advice],
+                                     [up(c) for c in instance], spec.fr_array(list(sc.challenges)), fr1(sc.beta), fr1(sc.gamma),
+                                     fr1(sc.theta), fr1(sc.y), up(perm.l0), up(perm.l_last), up(perm.l_active_row),
+                                     up(lk.product_coset), up(lk.permuted_input_coset), up(lk.permuted_table_coset), values)
+    torch.cuda.synchronize()
+    assert spec.fr_ints(values.cpu().numpy().view(np.uint64)) == want2
 
 
 @pytest.mark.gpu
