@@ -390,3 +390,34 @@ def test_cuda_evaluate_h_collatz_reproduces_the_reference_quotient(h2b, spec):
     assert dom.extended_k == CEXT
     assert got == d["values"]
     assert (dom.divide_by_vanishing_poly(spec.fr_array(got)) == d["quotient_in"]).all()
+
+
+@pytest.mark.gpu
+def test_cuda_evaluate_h_rejects_malformed_graphs(h2b, spec):
+    """The serialised graph is validated before it is trusted with device pointers: out-of-range columns,
+    rotations, intermediates or a truncated stream are argument errors (upstream would panic on the index)."""
+    import torch
+    import evaluate_h as ev
+    from halo2_prover_b200 import _ffi, evaluation
+    dom = h2b.EvaluationDomain(3, 4)
+    en = 1 << dom.extended_k
+    col = torch.zeros((en, 4), dtype=torch.int64, device="cuda")
+    values = torch.zeros((en, 4), dtype=torch.int64, device="cuda")
+    zero = np.zeros(4, dtype=np.uint64)
+    none = np.zeros((0, 4), dtype=np.uint64)
+
+    def run(calcs, num_inter=1, rotations=(0,)):
+        g = evaluation.GraphEvaluator(rotations=list(rotations), calculations=calcs, num_intermediates=num_inter)
+        evaluation.dev_evaluate_h(dom, g, [col], [col], [], none, zero, zero, zero, zero, None, values)
+
+    run([(ev.STORE, 0, (ev.ADVICE, 0, 0))])                          # well-formed
+    for bad in ([(ev.STORE, 0, (ev.ADVICE, 1, 0))],                    # advice column 1 of 1
+                [(ev.STORE, 0, (ev.FIXED, 0, 1))],                     # rotation index 1 of 1
+                [(ev.STORE, 1, (ev.ADVICE, 0, 0))],                    # target beyond num_intermediates
+                [(ev.ADD, 0, (ev.INTERMEDIATE, 5, 0), (ev.Y, 0, 0))],  # intermediate 5 of 1
+                [(ev.STORE, 0, (ev.INSTANCE, 0, 0))],                  # no instance columns
+                [(ev.STORE, 0, (ev.CHALLENGE, 0, 0))]):                # no challenges
+        with pytest.raises(_ffi.H2BError):
+            run(bad)
+    with pytest.raises(_ffi.H2BError):
+        run([(ev.STORE, 0, (ev.ADVICE, 0, 0))], rotations=tuple(range(33)))   # more than 32 rotations
