@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libh2b200.so")
 SOURCES = ["h2b200.cu"]
-HEADERS = ["field.cuh", "curve.cuh", "ntt.cuh", "msm.cuh", "msm_comb.cuh", "ecntt.cuh", "evalh.cuh", "hostcopy.h", os.path.join("..", "..", "include", "h2b200.h")]
+HEADERS = ["field.cuh", "curve.cuh", "ntt.cuh", "msm.cuh", "msm_comb.cuh", "msm_reduce.cuh", "ecntt.cuh", "evalh.cuh", "hostcopy.h", os.path.join("..", "..", "include", "h2b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",

@@ -25,6 +25,7 @@
 #include "field.cuh"
 #include "msm.cuh"
 #include "msm_comb.cuh"
+#include "msm_reduce.cuh"
 #include "ntt.cuh"
 
 using namespace h2b;
@@ -79,6 +80,9 @@ struct Ctx {
     uint64_t launches = 0;
     uint32_t msm_window = 0;
     uint32_t reduce_lgrp = 0;  // tuning override (H2B_REDUCE_LGRP)
+    uint32_t reduce_tree = 1;  // bucket reduction: 1 = bit tree (msm_reduce.cuh), 0 = running sums (H2B_REDUCE_TREE)
+    uint32_t reduce_lone = 2;  // tree levels done by lone threads on large grids (H2B_REDUCE_LONE)
+    int reduce_q = -1;         // first-stage run length 2^q of the tree reduction, -1 = automatic (H2B_REDUCE_Q)
     size_t comb_max_n = (size_t)1 << 14;  // registered SRS up to this length get the bucket-free table
     uint32_t comb_c = 8;
     double e2e_ratio = 0;      // growth of the host-path chunk sizes (0 = automatic)
@@ -379,21 +383,98 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     return H2B_OK;
 }
 
+// Bucket reduction as a tree over the bits of the bucket index (msm_reduce.cuh): windows[w] = sum_b (b + 1) B_b.
+// Every level is one launch over ROWS: the first nwin rows are the windows (they produce bit sums), the others
+// are the bit sums of earlier levels (and the run sums of the optional first stage), which only need their total;
+// a level appends its nwin * lg bit-sum rows after the rows it received, so the last level leaves one array of
+// single values: [per-window totals | (run sums) | bit sums of level 1 | level 2 | ...].
+int msm_reduce_tree(const XYZZ *buckets, uint32_t bpw, uint32_t nwin, XYZZ *windows, cudaStream_t s) {
+    constexpr int kThreads = 256;
+    constexpr uint32_t kLgT = 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(msm_bit_tree_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(2 * sizeof(XYZZ) << kLgT)));
+        attr_set = true;
+    }
+    // wide windows are throughput-bound: fold runs of 2^q buckets by lone threads first (full lane efficiency)
+    // (measured: commits at 2^18 / 2^20 / 2^22 points, q = 0 / 2 / 4: 1.23 / 1.22 / 1.36, 3.52 / 3.39 / 3.20,
+    // 10.82 / 10.68 / 10.50 ms)
+    const uint64_t all = (uint64_t)bpw * nwin;
+    uint32_t q = g->reduce_q >= 0 ? (uint32_t)g->reduce_q : (all >= (1u << 19) ? 4 : all >= (1u << 16) ? 2 : 0);
+    while (q && (bpw >> q) < 2) q--;
+    const uint32_t leaves = bpw >> q;
+    size_t need = q ? (size_t)2 * nwin * leaves : 0;
+    {
+        size_t rows = q ? 2 * nwin : nwin;
+        for (uint32_t cnt = leaves; cnt > 1;) {
+            const uint32_t lg = std::min(kLgT, ceil_log2(cnt)), nblk = cnt >> lg;
+            rows += (size_t)nwin * lg;
+            need += rows * nblk;
+            cnt = nblk;
+        }
+        need += nwin;  // leaves == 1
+    }
+    XYZZ *scratch;
+    TRY(get_buf(BUF_WPART, need * sizeof(XYZZ), (void **)&scratch));
+    BitSums bs{};
+    bs.shift = q;
+    const XYZZ *cur = buckets;
+    uint32_t rows = nwin;
+    if (q) {
+        const uint32_t runs = nwin * leaves;
+        XYZZ *S = scratch, *Wp = S + runs;
+        scratch = Wp + runs;
+        msm_bucket_runs_kernel<<<(runs + 127) / 128, 128, 0, s>>>(buckets, runs, q, S, Wp);
+        LAUNCHED();
+        cur = S;
+        rows = 2 * nwin;
+    }
+    uint32_t bit_off[3] = {0, 0, 0};
+    for (uint32_t cnt = leaves; cnt > 1;) {
+        const uint32_t lg = std::min(kLgT, ceil_log2(cnt)), nblk = cnt >> lg;
+        if (bs.levels >= 3) return fail(H2B_ERR_ARG, "msm: bucket window too wide for the reduction tree");
+        XYZZ *next = scratch, *part = next + (size_t)rows * nblk;
+        scratch = part + (size_t)nwin * lg * nblk;
+        // on large grids the two lowest levels have one addition per two leaves, which lone threads do with less
+        // overhead than teams
+        const uint32_t lone = (uint64_t)nblk * rows >= 4u * g->sm_count ? g->reduce_lone : 0;
+        msm_bit_tree_kernel<kThreads><<<dim3(nblk, rows), kThreads, 2 * sizeof(XYZZ) << lg, s>>>(cur, cnt, lg, nwin, next,
+                                                                                                  part, lone);
+        LAUNCHED();
+        bit_off[bs.levels] = rows;
+        bs.lg[bs.levels] = lg;
+        bs.levels++;
+        rows += nwin * lg;
+        cur = next;
+        cnt = nblk;
+    }
+    for (uint32_t i = 0; i < bs.levels; i++) bs.rows[i] = cur + bit_off[i];
+    bs.total = q ? cur + nwin : cur;
+    msm_bit_horner_kernel<<<nwin, 32 * kHornerWarps, 0, s>>>(bs, windows);
+    LAUNCHED();
+    return H2B_OK;
+}
+
 int msm_finish(const MsmRun &run, Projective *d_out, cudaStream_t s) {
     MsmCfg cfg = run.cfg;
     if (cfg.shared) cfg.windows = cfg.cols;  // one bucket set per column: sum_k k * B_k is the result, no Horner
     XYZZ *windows, *wpart;
-    uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
-    uint32_t rthreads = G < 256 ? G : 256;      // power of two
-    // few groups in total (small MSMs): narrower blocks put the serial group chains on different SMs
-    while (rthreads > 32 && (uint64_t)(G / rthreads) * cfg.windows < 2u * g->sm_count) rthreads >>= 1;
-    uint32_t per_window = G / rthreads;         // blocks (= partials) per window
     TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
-    TRY(get_buf(BUF_WPART, (size_t)cfg.windows * per_window * sizeof(XYZZ), (void **)&wpart));
-    msm_reduce_kernel<<<dim3(per_window, cfg.windows), rthreads, rthreads * sizeof(XYZZ), s>>>(run.buckets, cfg, wpart);
-    LAUNCHED();
-    msm_window_fold_kernel<<<cfg.windows, 32, 0, s>>>(wpart, per_window, windows);
-    LAUNCHED();
+    if (g->reduce_tree) {
+        TRY(msm_reduce_tree(run.buckets, cfg.bpw, cfg.windows, windows, s));
+    } else {
+        uint32_t G = cfg.bpw >> cfg.lgrp;          // groups per window
+        uint32_t rthreads = G < 256 ? G : 256;      // power of two
+        // few groups in total (small MSMs): narrower blocks put the serial group chains on different SMs
+        while (rthreads > 32 && (uint64_t)(G / rthreads) * cfg.windows < 2u * g->sm_count) rthreads >>= 1;
+        uint32_t per_window = G / rthreads;         // blocks (= partials) per window
+        TRY(get_buf(BUF_WPART, (size_t)cfg.windows * per_window * sizeof(XYZZ), (void **)&wpart));
+        msm_reduce_kernel<<<dim3(per_window, cfg.windows), rthreads, rthreads * sizeof(XYZZ), s>>>(run.buckets, cfg, wpart);
+        LAUNCHED();
+        msm_window_fold_kernel<<<cfg.windows, 32, 0, s>>>(wpart, per_window, windows);
+        LAUNCHED();
+    }
     if (cfg.shared && cfg.cols > 1) {
         msm_batch_out_kernel<<<(cfg.cols + 31) / 32, 32, 0, s>>>(windows, cfg.cols, d_out);
         LAUNCHED();
@@ -1005,6 +1086,12 @@ int h2b_init(int device) {
     }
     const char *rl = getenv("H2B_REDUCE_LGRP");
     if (rl) c->reduce_lgrp = (uint32_t)atoi(rl);
+    const char *rt = getenv("H2B_REDUCE_TREE");
+    if (rt) c->reduce_tree = (uint32_t)atoi(rt);
+    const char *ro = getenv("H2B_REDUCE_LONE");
+    if (ro) c->reduce_lone = (uint32_t)atoi(ro);
+    const char *rq = getenv("H2B_REDUCE_Q");
+    if (rq) c->reduce_q = atoi(rq);
     const char *er = getenv("H2B_E2E_RATIO");
     if (er) c->e2e_ratio = atof(er);
     const char *sp = getenv("H2B_SRS_PRECOMPUTE");
