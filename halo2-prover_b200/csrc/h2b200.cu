@@ -82,6 +82,8 @@ struct Ctx {
     uint32_t reduce_lgrp = 0;  // tuning override (H2B_REDUCE_LGRP)
     uint32_t reduce_tree = 1;  // bucket reduction: 1 = bit tree (msm_reduce.cuh), 0 = running sums (H2B_REDUCE_TREE)
     uint32_t reduce_lone = 2;  // tree levels done by lone threads on large grids (H2B_REDUCE_LONE)
+    uint32_t min_slice = 16;   // shortest accumulation slice (H2B_MIN_SLICE)
+    uint32_t min_waves = 1;    // fewest accumulation waves (H2B_MIN_WAVES)
     int reduce_q = -1;         // first-stage run length 2^q of the tree reduction, -1 = automatic (H2B_REDUCE_Q)
     size_t comb_max_n = (size_t)1 << 14;  // registered SRS up to this length get the bucket-free table
     uint32_t comb_c = 8;
@@ -306,17 +308,20 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
     cfg.n = (uint32_t)m;
     cfg.ioff = (uint32_t)ioff;
     size_t entries = m * cfg.cols * cfg.windows;
-    uint32_t L = 512;  // slice: enough slices to fill the GPU several times over, at most 512 entries
-    while (L > 16 && entries / L < (size_t)g->sm_count * 2048) L >>= 1;
-    if (L == 512) {
-        // every slice is the same amount of work and 4 blocks of 128 slices are resident per SM, so the
-        // launch runs in lockstep waves: size the slices so that the last wave is full
-        // (2^24 x 13 entries: 3329 blocks = 5.6 waves at L = 512, 3550 blocks = 6.0 waves at L = 480)
+    // Slice length.  Every slice is the same amount of work and 4 blocks of 128 slices are resident per SM, so the
+    // launch runs in lockstep waves and the slices are sized so that the last wave is full (2^24 x 13 entries:
+    // 5.6 waves at L = 512, 6.0 at L = 480).  How many waves is a trade: more (shorter slices) let late blocks
+    // backfill and speed the accumulation up by up to 10 %, but every slice leaves a head and a tail piece for the
+    // fix-up tree.  Measured optimum on B200 (commits, 2^17..2^24 points): one wave up to ~5 M entries, then about
+    // one wave per 64 entries of slice length, 6 at most; slices never longer than 640 entries.
+    uint32_t L;
+    {
         const size_t per_wave = (size_t)g->sm_count * 4 * 128;
-        size_t waves = entries / (per_wave * 512);            // round down if the slices stay <= 640 entries
-        if (waves == 0 || (entries + waves * per_wave - 1) / (waves * per_wave) > 640) waves++;
+        size_t waves = std::min<size_t>(6, (entries + per_wave * 32) / (per_wave * 64));
+        waves = std::max<size_t>(waves, (entries + per_wave * 640 - 1) / (per_wave * 640));
+        waves = std::max<size_t>(waves, g->min_waves);
         const size_t fit = (entries + waves * per_wave - 1) / (waves * per_wave);
-        if (fit >= 64 && fit <= 640) L = (uint32_t)fit;
+        L = (uint32_t)std::min<size_t>(640, std::max<size_t>(g->min_slice, fit));
     }
     cfg.slice = L;
     size_t max_slices = entries / cfg.slice + 1;
@@ -1090,6 +1095,10 @@ int h2b_init(int device) {
     if (rt) c->reduce_tree = (uint32_t)atoi(rt);
     const char *ro = getenv("H2B_REDUCE_LONE");
     if (ro) c->reduce_lone = (uint32_t)atoi(ro);
+    const char *ms = getenv("H2B_MIN_SLICE");
+    if (ms && atoi(ms) >= 1) c->min_slice = (uint32_t)atoi(ms);
+    const char *mw = getenv("H2B_MIN_WAVES");
+    if (mw && atoi(mw) >= 1) c->min_waves = (uint32_t)atoi(mw);
     const char *rq = getenv("H2B_REDUCE_Q");
     if (rq) c->reduce_q = atoi(rq);
     const char *er = getenv("H2B_E2E_RATIO");
