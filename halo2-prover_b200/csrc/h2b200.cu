@@ -84,6 +84,8 @@ struct Ctx {
     uint32_t reduce_lone = 2;  // tree levels done by lone threads on large grids (H2B_REDUCE_LONE)
     uint32_t min_slice = 16;   // shortest accumulation slice (H2B_MIN_SLICE)
     uint32_t min_waves = 1;    // fewest accumulation waves (H2B_MIN_WAVES)
+    uint64_t epoch = 0;        // distinguishes successive contexts (init after shutdown, possibly on another device)
+    uint64_t reduce_attr_epoch = 0;
     int reduce_q = -1;         // first-stage run length 2^q of the tree reduction, -1 = automatic (H2B_REDUCE_Q)
     size_t comb_max_n = (size_t)1 << 14;  // registered SRS up to this length get the bucket-free table
     uint32_t comb_c = 8;
@@ -396,11 +398,10 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
 int msm_reduce_tree(const XYZZ *buckets, uint32_t bpw, uint32_t nwin, XYZZ *windows, cudaStream_t s) {
     constexpr int kThreads = 256;
     constexpr uint32_t kLgT = 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (g->reduce_attr_epoch != g->epoch) {  // per context: the attribute belongs to the device of h2b_init
         CU(cudaFuncSetAttribute(msm_bit_tree_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(2 * sizeof(XYZZ) << kLgT)));
-        attr_set = true;
+        g->reduce_attr_epoch = g->epoch;
     }
     // wide windows are throughput-bound: fold runs of 2^q buckets by lone threads first (full lane efficiency)
     // (measured: commits at 2^18 / 2^20 / 2^22 points, q = 0 / 2 / 4: 1.23 / 1.22 / 1.36, 3.52 / 3.39 / 3.20,
@@ -641,11 +642,11 @@ int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log
                 const NttIo &io, cudaStream_t s, uint32_t batch) {
     constexpr int R = 1 << S;
     size_t smem = ((size_t)2 * R * C + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    static uint64_t attr_epoch = 0;  // per instantiation; redone for every context (device may differ)
+    if (attr_epoch != g->epoch && smem > 48 * 1024) {
         CU(cudaFuncSetAttribute(ntt_pass_kernel<S, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-        attr_set = true;
+        attr_epoch = g->epoch;
     }
     uint32_t M = 1u << (log_n - S);
     uint32_t blocks = M / C;
@@ -1057,6 +1058,8 @@ int h2b_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(H2B_ERR_CUDA, "h2b_init: kernels are built for sm_100a only");
     Ctx *c = new Ctx();
+    static uint64_t epochs = 0;
+    c->epoch = ++epochs;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
