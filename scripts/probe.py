@@ -130,6 +130,31 @@ def main():
             print(f"NTT 2^{k}: {ms:.4f} ms ({n / ms * 1e3:.3e} elems/s, {n * k / 2 / ms * 1e-6:.2f} G modmul/s)", flush=True)
             res[f"ntt_{k}"] = ms
             del a_t
+        # the EvaluationDomain transforms, device-resident (PROBE_DOMAIN = list of k; j = 5, extended_k = k + 2)
+        for k in [int(x) for x in os.environ.get("PROBE_DOMAIN", "").split(",") if x]:
+            d = h2b.EvaluationDomain(5, k)
+            ek = d.extended_k
+            a_t = torch.from_numpy(rand_fr_np(1 << k, 5).view(np.int64)).cuda()
+            e_t = torch.empty((1 << ek, 4), dtype=torch.int64, device="cuda")
+            c_t = torch.empty((d.extended_len() if hasattr(d, "extended_len") else 1 << ek, 4), dtype=torch.int64, device="cuda")
+            fns = {"lagrange_to_coeff": lambda: d.dev_lagrange_to_coeff(a_t, stream=s),
+                   "coeff_to_extended": lambda: d.dev_coeff_to_extended(a_t, e_t, stream=s),
+                   "extended_to_coeff": lambda: d.dev_extended_to_coeff(e_t, c_t, stream=s)}
+            for name, fn in fns.items():
+                for _ in range(2):
+                    fn()
+                s.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10
+                e0.record(s)
+                for _ in range(reps):
+                    fn()
+                e1.record(s)
+                s.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                print(f"DOMAIN k={k} ext={ek} {name}: {ms:.4f} ms", flush=True)
+                res[f"{name}_{k}"] = ms
+            del a_t, e_t, c_t
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w") as f:
         json.dump(res, f, indent=1)
