@@ -118,7 +118,7 @@ def test_commit_against_registered_srs(h2b, spec, href):
     params.release()
 
 
-@pytest.mark.parametrize("mode,srs_c", [(1, 0), (2, 0), (1, 7), (1, 13), (1, 16)])
+@pytest.mark.parametrize("mode,srs_c", [(1, 0), (2, 0), (1, 7), (1, 13), (1, 16), (1, 20), (1, 22)])
 def test_commit_precomputed_window_table(h2b, spec, href, mode, srs_c):
     """Registered bases get a precomputed table: mode 1 / c = 0 the bucket-free table of all window multiples
     (small SRS), mode 2 or an explicit c the window table 2^(c*w) * P_i whose windows share one bucket set.
