@@ -20,25 +20,26 @@ batch_affine_kernel(const Affine *__restrict__ table, const uint32_t *__restrict
                     Affine *__restrict__ out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t *my = idx + (size_t)t * 2 * K;
-    Fe *pp = prefix + (size_t)t * K;
+    const size_t T = (size_t)gridDim.x * blockDim.x;  // prefix[i][t], out[i][t]: coalesced across the warp
+    Fe *pp = prefix + t;
     Fe acc = Fq::one();
     for (uint32_t i = 0; i < K; i++) {
         const Fe x1 = load_fe_ro(&table[my[2 * i]].x), x2 = load_fe_ro(&table[my[2 * i + 1]].x);
-        store_fe(&pp[i], acc);                    // p_(i-1)
+        store_fe(&pp[(size_t)i * T], acc);        // p_(i-1)
         acc = Fq::mul(acc, Fq::sub(x2, x1));
     }
     Fe inv = Fq::inv(acc);
     for (int i = (int)K - 1; i >= 0; i--) {
         const Affine p = load_affine(&table[my[2 * i]]), q = load_affine(&table[my[2 * i + 1]]);
         const Fe d = Fq::sub(q.x, p.x);
-        const Fe di = Fq::mul(inv, load_fe(&pp[i]));
+        const Fe di = Fq::mul(inv, load_fe(&pp[(size_t)i * T]));
         inv = Fq::mul(inv, d);
         const Fe lam = Fq::mul(Fq::sub(q.y, p.y), di);
         Affine r;
         r.x = Fq::sub(Fq::sub(Fq::sqr(lam), p.x), q.x);
         r.y = Fq::sub(Fq::mul(lam, Fq::sub(p.x, r.x)), p.y);
-        store_fe(&out[(size_t)t * K + i].x, r.x);
-        store_fe(&out[(size_t)t * K + i].y, r.y);
+        store_fe(&out[(size_t)i * T + t].x, r.x);
+        store_fe(&out[(size_t)i * T + t].y, r.y);
     }
 }
 
