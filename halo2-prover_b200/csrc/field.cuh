@@ -113,6 +113,83 @@ H2B_DI void shift_mad_row(uint32_t &e0, uint32_t (&o)[8], uint32_t x1, uint32_t 
         : "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(m));
 }
 
+// Row variants for the squaring: the first Z multiplicands are zero.  With no carry yet, the chain of cmad_row_fold
+// simply starts at the first non-zero product; in shift_mad_row the skipped products become plain carry adds.
+template <int Z>
+H2B_DI void cmad_row_fold_z(uint32_t (&e)[8], uint32_t &top, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6,
+                            uint32_t m) {
+    if constexpr (Z == 0) {
+        cmad_row_fold(e, top, x0, x2, x4, x6, m);
+    } else if constexpr (Z == 1) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, %6, 0;"
+            : "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(top)
+            : "r"(x2), "r"(x4), "r"(x6), "r"(m));
+    } else if constexpr (Z == 2) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(top)
+            : "r"(x4), "r"(x6), "r"(m));
+    } else if constexpr (Z == 3) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, %2, 0;"
+            : "+r"(e[6]), "+r"(e[7]), "+r"(top)
+            : "r"(x6), "r"(m));
+    }
+}
+template <int Z>
+H2B_DI void shift_mad_row_z(uint32_t &e0, uint32_t (&o)[8], uint32_t x1, uint32_t x3, uint32_t x5, uint32_t x7,
+                            uint32_t m) {
+    if constexpr (Z == 0) {
+        shift_mad_row(e0, o, x1, x3, x5, x7, m);
+    } else if constexpr (Z == 1) {
+        asm("add.cc.u32 %0, %0, %2;\n\t"
+            "addc.cc.u32 %1, %3, 0;\n\t"
+            "addc.cc.u32 %2, %4, 0;\n\t"
+            "madc.lo.cc.u32 %3, %9, %12, %5;\n\t"
+            "madc.hi.cc.u32 %4, %9, %12, %6;\n\t"
+            "madc.lo.cc.u32 %5, %10, %12, %7;\n\t"
+            "madc.hi.cc.u32 %6, %10, %12, %8;\n\t"
+            "madc.lo.cc.u32 %7, %11, %12, 0;\n\t"
+            "madc.hi.u32 %8, %11, %12, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(x3), "r"(x5), "r"(x7), "r"(m));
+    } else if constexpr (Z == 2) {
+        asm("add.cc.u32 %0, %0, %2;\n\t"
+            "addc.cc.u32 %1, %3, 0;\n\t"
+            "addc.cc.u32 %2, %4, 0;\n\t"
+            "addc.cc.u32 %3, %5, 0;\n\t"
+            "addc.cc.u32 %4, %6, 0;\n\t"
+            "madc.lo.cc.u32 %5, %9, %11, %7;\n\t"
+            "madc.hi.cc.u32 %6, %9, %11, %8;\n\t"
+            "madc.lo.cc.u32 %7, %10, %11, 0;\n\t"
+            "madc.hi.u32 %8, %10, %11, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(x5), "r"(x7), "r"(m));
+    } else if constexpr (Z == 3) {
+        asm("add.cc.u32 %0, %0, %2;\n\t"
+            "addc.cc.u32 %1, %3, 0;\n\t"
+            "addc.cc.u32 %2, %4, 0;\n\t"
+            "addc.cc.u32 %3, %5, 0;\n\t"
+            "addc.cc.u32 %4, %6, 0;\n\t"
+            "addc.cc.u32 %5, %7, 0;\n\t"
+            "addc.cc.u32 %6, %8, 0;\n\t"
+            "madc.lo.cc.u32 %7, %9, %10, 0;\n\t"
+            "madc.hi.u32 %8, %9, %10, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(x7), "r"(m));
+    }
+}
+
 template <class P>
 struct Field {
     H2B_DI static Fe zero() {
@@ -300,7 +377,62 @@ struct Field {
               "r"(od[7]));
         return reduce_once(r);
     }
-    H2B_DI static Fe sqr(const Fe &a) { return mul(a, a); }
+    // Montgomery square: the same rows as mul(), but row i multiplies a_i into
+    //   [0 .. 0, a_i, 2 a_(i+1) .. 2 a_7]  (as the limbs of a_i B^i + 2 (a >> 32(i+1)) B^(i+1); a < 2^254 so nothing
+    // is shifted out), i.e. every cross product a_i a_j is formed once, doubled: 36 limb products instead of 64.
+    // The zero entries are compile-time constants after unrolling, so their mad steps fold to plain carry adds.
+    H2B_DI static Fe sqr(const Fe &a) {
+        uint32_t t[8], u[8];  // t_j = limb j of 2a, u_j = a_j << 1 (limb j of 2 (a >> 32 j) B^j)
+        t[0] = u[0] = a.l[0] << 1;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            t[j] = __funnelshift_l(a.l[j - 1], a.l[j], 1);
+            u[j] = a.l[j] << 1;
+        }
+        // c(i, j): multiplicand limb j of row i
+#define H2B_SQ(i, j) ((j) < (i) ? 0u : ((j) == (i) ? a.l[(j) & 7] : ((j) == (i) + 1 ? u[(j) & 7] : t[(j) & 7])))
+        uint32_t ev[8], od[8];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            uint64_t p = (uint64_t)H2B_SQ(0, k) * a.l[0];
+            ev[k] = (uint32_t)p;
+            ev[k + 1] = (uint32_t)(p >> 32);
+            uint64_t q = (uint64_t)H2B_SQ(0, k + 1) * a.l[0];
+            od[k] = (uint32_t)q;
+            od[k + 1] = (uint32_t)(q >> 32);
+        }
+        redc_step(ev, od);
+        // rows 1..7: even-position multiplicands have (i + 1) / 2 leading zeros, odd-position ones i / 2
+#define H2B_SQ_ROW(i, E, O)                                                                                        \
+    shift_mad_row_z<(i) / 2>(E[0], O, H2B_SQ(i, 1), H2B_SQ(i, 3), H2B_SQ(i, 5), H2B_SQ(i, 7), a.l[i]);              \
+    cmad_row_fold_z<((i) + 1) / 2>(E, O[7], H2B_SQ(i, 0), H2B_SQ(i, 2), H2B_SQ(i, 4), H2B_SQ(i, 6), a.l[i]);        \
+    redc_step(E, O);
+        H2B_SQ_ROW(1, od, ev)
+        H2B_SQ_ROW(2, ev, od)
+        H2B_SQ_ROW(3, od, ev)
+        H2B_SQ_ROW(4, ev, od)
+        H2B_SQ_ROW(5, od, ev)
+        H2B_SQ_ROW(6, ev, od)
+        H2B_SQ_ROW(7, od, ev)
+#undef H2B_SQ_ROW
+#undef H2B_SQ
+        Fe r;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, 0;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]),
+              "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]),
+              "r"(ev[7]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]),
+              "r"(od[7]));
+        return reduce_once(r);
+    }
+    H2B_DI static Fe sqr_by_mul(const Fe &a) { return mul(a, a); }
 
     // Reference multiplication on 64-bit temporaries (no inline PTX); used by the self-test
     // kernel to cross-check mul() on the device.

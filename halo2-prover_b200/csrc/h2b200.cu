@@ -969,6 +969,7 @@ __global__ void test_field_kernel(int op, const Fe *a, const Fe *b, Fe *o, uint3
         case 2: r = F::sub(x, y); break;
         case 3: r = F::mul_portable(x, y); break;
         case 4: r = F::inv(x); break;
+        case 6: r = F::sqr(x); break;
         default: r = F::from_mont(x); break;
     }
     store_fe(&o[i], r);

@@ -49,6 +49,25 @@ def test_inverse_and_from_mont(h2b, spec, field):
     assert (canon == spec.ints_to_array(av, None)).all()
 
 
+@pytest.mark.parametrize("field", [0, 1])
+def test_dedicated_square(h2b, spec, field):
+    """Field::sqr forms every cross product once, doubled (36 limb products instead of 64): must equal a * a for
+    random elements and for limb patterns that maximise the doubled partial sums."""
+    mod = spec.R_MOD if field == 0 else spec.Q_MOD
+    top = mod >> 224
+    patterns = [mod - 1, mod - 2, mod >> 1, (mod >> 1) + 1,
+                ((top - 1) << 224) | ((1 << 224) - 1),            # every lower limb 0xffffffff
+                ((top - 1) << 224) | int("80000000" * 7, 16),     # top bit of every lower limb (the funnel shifts)
+                int("7fffffff" * 7, 16), int("ffffffff" * 7, 16), (1 << 253) + (1 << 31), (1 << 224) - 1, 1 << 223]
+    vals = _edge(spec, mod, 8192, 11) + [v % mod for v in patterns]
+    a = spec.ints_to_array(vals, mod)          # Montgomery form of vals
+    want = spec.ints_to_array([v * v % mod for v in vals], mod)
+    assert (_field_op(h2b, field, 6, a) == want).all()
+    # the limb patterns themselves as Montgomery REPRESENTATIVES (what the multiplier actually sees)
+    raw = spec.ints_to_array([v % mod for v in patterns], None)
+    assert (_field_op(h2b, field, 6, raw) == _field_op(h2b, field, 0, raw, raw)).all()
+
+
 def test_mul_against_c_oracle_large(h2b, href):
     a, b = href.random_fr(1 << 16, 5), href.random_fr(1 << 16, 6)
     assert (_field_op(h2b, 0, 0, a, b) == href.fr_mul(a, b)).all()
