@@ -78,7 +78,7 @@ H2B_DI XYZZ xyzz_dbl(const XYZZ &p) {
     Fe m = Fq::add(Fq::dbl(xx), xx);
     XYZZ r;
     r.x = Fq::sub(Fq::sub(Fq::sqr(m), s), s);
-    r.y = Fq::sub(Fq::mul(m, Fq::sub(s, r.x)), Fq::mul(w, p.y));
+    r.y = Fq::mul2_sub(m, Fq::sub(s, r.x), w, p.y);  // two products, one reduction
     r.zz = Fq::mul(v, p.zz);
     r.zzz = Fq::mul(w, p.zzz);
     return r;
@@ -114,7 +114,7 @@ H2B_DI void xyzz_madd(XYZZ &acc, const Affine &p) {
     Fe ppp = Fq::mul(pp_, pp);
     Fe q = Fq::mul(acc.x, pp);
     Fe x3 = Fq::sub(Fq::sub(Fq::sub(Fq::sqr(rr), ppp), q), q);
-    Fe y3 = Fq::sub(Fq::mul(rr, Fq::sub(q, x3)), Fq::mul(acc.y, ppp));
+    Fe y3 = Fq::mul2_sub(rr, Fq::sub(q, x3), acc.y, ppp);  // two products, one reduction
     acc.x = x3;
     acc.y = y3;
     acc.zz = Fq::mul(acc.zz, pp);
@@ -143,7 +143,7 @@ static __device__ __noinline__ void xyzz_add(XYZZ &acc, const XYZZ &q) {
     Fe ppp = Fq::mul(pp_, pp);
     Fe qq = Fq::mul(u1, pp);
     Fe x3 = Fq::sub(Fq::sub(Fq::sub(Fq::sqr(rr), ppp), qq), qq);
-    Fe y3 = Fq::sub(Fq::mul(rr, Fq::sub(qq, x3)), Fq::mul(s1, ppp));
+    Fe y3 = Fq::mul2_sub(rr, Fq::sub(qq, x3), s1, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = Fq::mul(Fq::mul(acc.zz, q.zz), pp);

@@ -970,6 +970,8 @@ __global__ void test_field_kernel(int op, const Fe *a, const Fe *b, Fe *o, uint3
         case 3: r = F::mul_portable(x, y); break;
         case 4: r = F::inv(x); break;
         case 6: r = F::sqr(x); break;
+        case 7: r = F::mul2_add(x, y, F::add(x, y), F::sub(x, y)); break;   // xy + x^2 - y^2
+        case 8: r = F::mul2_sub(x, y, y, x); break;                         // 0, through neg()
         default: r = F::from_mont(x); break;
     }
     store_fe(&o[i], r);

@@ -227,7 +227,8 @@ int h2b_set_kernel_timing(int enabled);
 int h2b_kernel_time_collect(double *total_ms, uint32_t *calls);
 
 /* ---- test hooks (element-wise device arithmetic, used by tests/ only) ---------------- */
-/* op: 0 mul, 1 add, 2 sub, 3 mul (portable 64-bit path), 4 inverse of a, 5 from_mont(a), 6 square of a
+/* op: 0 mul, 1 add, 2 sub, 3 mul (portable 64-bit path), 4 inverse of a, 5 from_mont(a), 6 square of a,
+ * 7 a*b + (a+b)*(a-b) and 8 a*b - b*a through the fused two-product multiply
  * field: 0 Fr, 1 Fq.  a, b, out: n x 4 u64 host buffers. */
 int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 /* out[i] = a[i] + b[i] on affine inputs (n x 8 u64) through the XYZZ mixed-add path -> n x 12 u64. */

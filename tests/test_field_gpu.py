@@ -68,6 +68,26 @@ def test_dedicated_square(h2b, spec, field):
     assert (_field_op(h2b, field, 6, raw) == _field_op(h2b, field, 0, raw, raw)).all()
 
 
+@pytest.mark.parametrize("field", [0, 1])
+def test_fused_two_product_multiply(h2b, spec, field):
+    """Field::mul2_add: (a b + c d) R^-1 under one Montgomery reduction, and mul2_sub through neg()."""
+    mod = spec.R_MOD if field == 0 else spec.Q_MOD
+    n = 8192
+    av, bv = _edge(spec, mod, n, 21), list(reversed(_edge(spec, mod, n, 22)))
+    av[:4], bv[:4] = [mod - 1, mod - 1, 0, mod - 2], [mod - 1, 1, mod - 1, mod - 1]
+    a, b = spec.ints_to_array(av, mod), spec.ints_to_array(bv, mod)
+    want = spec.ints_to_array([(x * y + (x + y) * (x - y)) % mod for x, y in zip(av, bv)], mod)
+    assert (_field_op(h2b, field, 7, a, b) == want).all()
+    assert (_field_op(h2b, field, 8, a, b) == 0).all()
+    # maximal limb patterns as raw representatives
+    top = mod >> 224
+    raw = spec.ints_to_array([((top - 1) << 224) | ((1 << 224) - 1), mod - 1, ((top - 1) << 224) | int("80000000" * 7, 16)], None)
+    rb = raw[::-1].copy()
+    x, y = _field_op(h2b, field, 1, raw, rb), _field_op(h2b, field, 2, raw, rb)
+    want = _field_op(h2b, field, 1, _field_op(h2b, field, 0, raw, rb), _field_op(h2b, field, 0, x, y))
+    assert (_field_op(h2b, field, 7, raw, rb) == want).all()
+
+
 def test_mul_against_c_oracle_large(h2b, href):
     a, b = href.random_fr(1 << 16, 5), href.random_fr(1 << 16, 6)
     assert (_field_op(h2b, 0, 0, a, b) == href.fr_mul(a, b)).all()
