@@ -339,7 +339,10 @@ def run_b200(args) -> None:
         achieved = imad_per_launch / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
         peak = imad.value / 1e3
         adds_per_point = srs_w.value if srs_w.value else 15
-        executed = float(n) * adds_per_point * 10 * MODMUL_IMAD / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+        # SASS of one XYZZ mixed addition: 6 products (120 IMAD.WIDE + 16 IMAD each), 2 dedicated squares (92 + 16) and
+        # one fused two-product multiply (184 + 16); IMAD.WIDE counts as two IMAD-class instructions (4 vs 2 pipe cycles)
+        MADD_IMAD = (6 * 120 + 2 * 92 + 184) * 2 + 9 * 16
+        executed = float(n) * adds_per_point * MADD_IMAD / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
         hbm_peak = peaks.get("hbm_gbs")
         line = {
             "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
@@ -360,16 +363,18 @@ def run_b200(args) -> None:
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TIMAD/s", "frac": (achieved / peak) if achieved and peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 / 13 windows from the
-                         # committed capture profiles/r01_ncu_full_commit_accumulate_v11.md (ncu cannot run inside the
+                         # committed capture profiles/r01_ncu_full_commit_accumulate_v12.md (ncu cannot run inside the
                          # timed bench); only quoted for the configuration it was captured on
                          "traffic": 29.40e9 if (args.log_n == 24 and srs_w.value == 13) else None,
-                         "traffic_source": "profiles/r01_ncu_full_commit_accumulate_v11.md (ncu --set full, per launch)",
+                         "traffic_source": "profiles/r01_ncu_full_commit_accumulate_v12.md (ncu --set full, per launch)",
                          "launch_ms": acc_ms,
                          "algorithmic": "43,520 IMAD-class/point (160 modmul x 272) x 2^%d points per launch" % args.log_n,
                          "executed": {"achieved": executed, "frac": (executed / peak) if executed and peak else None,
                                       "note": "%d mixed additions per point actually executed (precomputed window "
-                                              "table) x 10 modmul x 272; the algorithmic model assumes 16, so "
-                                              "frac above can exceed 1" % adds_per_point},
+                                              "table) x 2320 IMAD-class per addition from SASS (6 products, 2 dedicated "
+                                              "squares, 1 fused two-product multiply; 2720 = 10 x 272 in the algorithmic "
+                                              "model, which also assumes 16 additions, so frac above can exceed 1)"
+                                              % adds_per_point},
                          "peak_source": "measured live: mad.lo.u32 microbenchmark (h2b_imad_peak); "
                                         "IMAD.WIDE rate %.1f G/s" % imad_w.value,
                          "hbm": {"achieved_gbs": n * MSM_BYTES_PER_POINT / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
