@@ -365,7 +365,7 @@ def run_b200(args) -> None:
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 / 13 windows from the
                          # committed capture profiles/r01_ncu_full_commit_accumulate_v12.md (ncu cannot run inside the
                          # timed bench); only quoted for the configuration it was captured on
-                         "traffic": 29.40e9 if (args.log_n == 24 and srs_w.value == 13) else None,
+                         "traffic": 29.42e9 if (args.log_n == 24 and srs_w.value == 13) else None,
                          "traffic_source": "profiles/r01_ncu_full_commit_accumulate_v12.md (ncu --set full, per launch)",
                          "launch_ms": acc_ms,
                          "algorithmic": "43,520 IMAD-class/point (160 modmul x 272) x 2^%d points per launch" % args.log_n,
