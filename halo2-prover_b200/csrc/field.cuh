@@ -431,7 +431,7 @@ struct Field {
     // Montgomery square: the same rows as mul(), but row i multiplies a_i into
     //   [0 .. 0, a_i, 2 a_(i+1) .. 2 a_7]  (as the limbs of a_i B^i + 2 (a >> 32(i+1)) B^(i+1); a < 2^254 so nothing
     // is shifted out), i.e. every cross product a_i a_j is formed once, doubled: 36 limb products instead of 64.
-    // The zero entries are compile-time constants after unrolling, so their mad steps fold to plain carry adds.
+    // The zero entries are skipped by the *_z row variants above (ptxas does not fold a mad.cc with a zero operand).
     H2B_DI static Fe sqr(const Fe &a) {
         uint32_t t[8], u[8];  // t_j = limb j of 2a, u_j = a_j << 1 (limb j of 2 (a >> 32 j) B^j)
         t[0] = u[0] = a.l[0] << 1;
