@@ -4,13 +4,17 @@
   python bench.py --gpus N --steps K --warmup W            # this framework on N B200s
   python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm on host cores
 
-A step is one BN254 G1 multi-scalar multiplication of 2^24 points per GPU (uniform random
-scalars, distinct random bases) -- the configuration the metric "MSM points/s (2^24)" is quoted
-on.  At N > 1 the MSM is sharded by point range (weak scaling: every rank owns 2^24 points of an
-N * 2^24-point MSM), each rank reduces its own buckets and the N partial sums (96 B each) are
-all-gathered over NCCL and folded on every GPU inside the step.  The second headline quantity,
-NTT elements/s at k = 20 (plus the coset extended-domain transform), is measured on rank 0 and
-reported under "ntt" in the same JSON line.
+A step is one BN254 G1 multi-scalar multiplication of 2^24 points (uniform random scalars,
+distinct bases) -- the configuration the metric "MSM points/s (2^24)" is quoted on -- as
+ParamsKZG::commit issues it: the bases are registered once, every step brings only scalars.
+At N > 1 the SAME 2^24-point MSM is sharded by point range over the N ranks (strong scaling:
+2^24 / N points per GPU), each rank reduces its own buckets and the N partial sums (96 B each)
+are all-gathered over NCCL and folded on every GPU inside the step; `weak` in the same line is
+the weak-scaling variant (2^24 points per GPU) and `single_process` the same metric from ONE
+process that owns all N devices through the C ABI (h2b_init_devices).  The second headline
+quantity, NTT elements/s at k = 20 (plus the coset extended-domain transform), is measured on
+rank 0 and reported under "ntt" in the same JSON line.  `parity` is the oracle check of the
+folded N-rank result.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM),
 `e2e` is the same metric through the reference-facing call (ParamsKZG::commit ->
@@ -122,38 +126,58 @@ def measured_peaks() -> dict:
         return {}
 
 
+def workload_config(args) -> dict:
+    """The configuration both arms run and print (identical by construction)."""
+    return {"workload": f"BN254 G1 MSM of 2^{args.log_n} points (uniform random scalars in [0, r), distinct bases), as "
+                        "ParamsKZG::commit issues it: bases static across calls, scalars per call",
+            "global_points": 1 << args.log_n, "scaling": "strong",
+            "l2": "inputs (1.5 GiB per step on one device) exceed L2; no flush needed",
+            "ntt_workload": f"best_fft k={args.ntt_k} and coeff_to_extended {args.ntt_k - 2}->{args.ntt_k}, 8 rotating buffers (256 MiB > L2)"}
+
+
 # ------------------------------------------------------------------------------- reference arm
 def run_reference(args) -> None:
+    """The reference's CPU algorithm (best_multiexp: thread-chunked multiexp_serial, halo2_proofs@6b43b6b
+    arithmetic.rs:28-180) as restated in oracle/h2ref.c, on ALL host threads, on the metric's own configuration:
+    one 2^24-point MSM per step.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import h2ref
     threads = os.cpu_count() or 1
-    lg = args.ref_log_n
-    n = 1 << lg
-    scalars = h2ref.to_mont(rand_fr_np(n, 1))  # any value < r is a valid element; keep the oracle's convention
-    bases = h2ref.random_g1(1 << 12, 2)
-    bases = np.ascontiguousarray(np.tile(bases, (n >> 12, 1)))
+    n = 1 << args.log_n
+    scalars = rand_fr_np(n, 1)          # any value < r is the Montgomery form of a field element
+    bases = h2ref.progression_g1(n, 2, threads)  # n distinct points
     for _ in range(args.warmup):
         h2ref.best_multiexp(scalars, bases, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         h2ref.best_multiexp(scalars, bases, threads)
-    dt = (time.perf_counter() - t0) / args.steps
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
     val = n / dt
     print(json.dumps({
         "impl": "reference", "metric": "msm_points_per_s", "value": val, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 Montgomery (int)", "data": "synthetic",
-        "config": {"workload": f"BN254 G1 MSM, bounded sample of 2^{lg} points per step (full config: 2^24)",
-                   "parallelism": f"{threads} host threads, contiguous chunks (best_multiexp)"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64x4 Montgomery (int)", "data": "synthetic",
+        "config": workload_config(args),
+        "parallelism": f"{threads} host threads, contiguous chunks (best_multiexp)",
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"C restatement of halo2_proofs@6b43b6b best_multiexp (not the Rust binary), 2^{lg} points"},
+                         "sample": f"the whole workload (2^{args.log_n} points per step); C restatement of "
+                                   "halo2_proofs@6b43b6b best_multiexp (not the Rust binary)"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------- this framework
+def _wait_flag(dist, name: str, rank: int, setter: bool) -> None:
+    """Host-side rendezvous that keeps the GPUs idle (an NCCL barrier spins a kernel on every waiting GPU)."""
+    store = dist.distributed_c10d._get_default_store()
+    if setter:
+        store.set(name, "1")
+    else:
+        store.wait([name])
+
+
 def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
@@ -168,47 +192,124 @@ def run_b200(args) -> None:
     import halo2_prover_b200 as h2b  # raises if the CUDA library is missing: no fallback
     from halo2_prover_b200 import _ffi, arithmetic, multi_gpu
     import bn254
+    import h2ref
 
     _ffi.init(local)
     L = _ffi.lib()
-    n = 1 << args.log_n
+    n_global = 1 << args.log_n
     stream = torch.cuda.Stream()
     sp = C.c_void_p(stream.cuda_stream)
-
-    # ---- inputs: pinned host scalars, device scalars, device bases (distinct random points)
-    host_scalars = torch.from_numpy(rand_fr_np(n, 1000 + rank).view(np.int64)).pin_memory()
     gen = bn254.affine_to_array([bn254.G1_GENERATOR])[0]
-    with torch.cuda.stream(stream):
-        d_scalars = host_scalars.cuda(non_blocking=True)
-        seeds = torch.from_numpy(rand_fr_np(n, 2000 + rank).view(np.int64)).cuda()
-        d_bases = torch.empty((n, 8), dtype=torch.int64, device="cuda")
-        _ffi.check(L.h2b_dev_fixed_base_mul(C.c_void_p(seeds.data_ptr()), C.c_size_t(n), _ffi.u64p(gen),
-                                            C.c_void_p(d_bases.data_ptr()), sp))
-        stream.synchronize()
-        del seeds
-        out = torch.empty(12, dtype=torch.int64, device="cuda")
-        out_generic = torch.empty(12, dtype=torch.int64, device="cuda")
 
-    # the reference's call pattern: ParamsKZG holds the (static) bases, every commit brings only scalars.
-    # Registration copies this rank's shard of the SRS to HBM and precomputes its window table once.
-    t_reg = time.perf_counter()
-    stream.synchronize()
-    params = h2b.ParamsKZG.from_device(args.log_n, d_bases)
-    t_reg = time.perf_counter() - t_reg
+    def make_inputs(n, seed):
+        """pinned host scalars, device scalars, device bases [s_i] G (distinct random points) for one rank"""
+        hs = torch.from_numpy(rand_fr_np(n, 1000 + seed).view(np.int64)).pin_memory()
+        with torch.cuda.stream(stream):
+            ds = hs.cuda(non_blocking=True)
+            seeds = torch.from_numpy(rand_fr_np(n, 2000 + seed).view(np.int64)).cuda()
+            db = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+            _ffi.check(L.h2b_dev_fixed_base_mul(C.c_void_p(seeds.data_ptr()), C.c_size_t(n), _ffi.u64p(gen),
+                                                C.c_void_p(db.data_ptr()), sp))
+            stream.synchronize()
+        return hs, ds, db
+
+    def register(db, n):
+        # the reference's call pattern: ParamsKZG holds the (static) bases, every commit brings only scalars.
+        # Registration copies this rank's shard of the SRS to HBM and precomputes its window table once.
+        stream.synchronize()
+        t = time.perf_counter()
+        params = h2b.ParamsKZG.from_device(max((n - 1).bit_length(), 0), db)
+        return params, time.perf_counter() - t
+
+    def measure(params, ds, hs, n, steps, with_kernel_timing):
+        """device-resident steps (CUDA events, max over ranks) and end-to-end steps through h2b_commit"""
+        handle = C.c_uint64(params._handles["g"])
+        out = torch.empty(12, dtype=torch.int64, device="cuda")
+        with torch.cuda.stream(stream):
+            def step():
+                if world == 1:
+                    params.dev_commit(ds, out, stream=stream)
+                else:
+                    out.copy_(multi_gpu.sharded_commit(params, ds, stream=stream))
+            for _ in range(max(args.warmup, 3)):
+                step()
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            sampler = ClockSampler(local) if (rank == 0 and with_kernel_timing) else None
+            if sampler:
+                time.sleep(0.4)  # nvidia-smi needs a few hundred ms to deliver its first row
+                sampler.mark_begin()
+            if with_kernel_timing:
+                _ffi.check(L.h2b_set_kernel_timing(1))
+            launches0 = L.h2b_kernel_launches()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(steps):
+                step()
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms_total = e0.elapsed_time(e1)
+            launches = L.h2b_kernel_launches() - launches0
+            ktot, kcalls = C.c_double(), C.c_uint32()
+            if with_kernel_timing:
+                _ffi.check(L.h2b_kernel_time_collect(C.byref(ktot), C.byref(kcalls)))
+                _ffi.check(L.h2b_set_kernel_timing(0))
+            clocks = sampler.stop() if sampler else None
+            t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_step = float(t.item()) / steps
+        # ---- end to end through the reference-facing call: ParamsKZG::commit with pinned host scalars
+        res_host = np.zeros(12, dtype=np.uint64)
+        hs_ptr = C.cast(C.c_void_p(hs.data_ptr()), C.POINTER(C.c_uint64))
+
+        def e2e_step():
+            _ffi.check(L.h2b_commit(handle, hs_ptr, C.c_size_t(n), _ffi.u64p(res_host)))
+            if world > 1:
+                part = torch.from_numpy(res_host.view(np.int64)).cuda()
+                parts = multi_gpu.gather_partials(part)
+                folded = torch.empty(12, dtype=torch.int64, device="cuda")
+                arithmetic.dev_g1_fold(parts, folded, stream=torch.cuda.current_stream())
+                return folded.cpu().numpy().view(np.uint64)
+            return res_host
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_res = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item()) / steps * 1e3
+        # the device-resident and the end-to-end paths must agree on the (folded) result
+        assert (h2ref.g1_to_affine(out.cpu().numpy().view(np.uint64)) == h2ref.g1_to_affine(np.ascontiguousarray(e2e_res))).all()
+        return {"ms_step": ms_step, "e2e_ms": e2e_ms, "launches": int(launches), "acc_ms_total": ktot.value,
+                "acc_calls": kcalls.value, "clocks": clocks, "handle": handle}
+
+    # ---- strong scaling (the metric's configuration): 2^log_n points in total, 1/N of them per GPU
+    n = n_global // world
+    host_scalars, d_scalars, d_bases = make_inputs(n, rank)
+    params, t_reg = register(d_bases, n)
     handle = C.c_uint64(params._handles["g"])
     srs_c, srs_w, srs_bytes = C.c_uint32(), C.c_uint32(), C.c_size_t()
     _ffi.check(L.h2b_srs_info(handle, None, C.byref(srs_c), C.byref(srs_w), C.byref(srs_bytes)))
 
+    generic_step_ms = None
     with torch.cuda.stream(stream):
-        def step():
-            if world == 1:
-                params.dev_commit(d_scalars, out, stream=stream)
-            else:
-                res = multi_gpu.sharded_commit(params, d_scalars, stream=stream)
-                out.copy_(res)
-
-        # best_multiexp with caller-supplied (unregistered) bases: no table, one bucket set per window
-        def generic_ms():
+        if world == 1:
+            # best_multiexp with caller-supplied (unregistered) bases: no table, one bucket set per window
+            out_generic = torch.empty(12, dtype=torch.int64, device="cuda")
             for _ in range(2):
                 arithmetic.dev_msm(d_scalars, d_bases, out_generic, n=n, stream=stream)
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -217,71 +318,57 @@ def run_b200(args) -> None:
                 arithmetic.dev_msm(d_scalars, d_bases, out_generic, n=n, stream=stream)
             a1.record(stream)
             stream.synchronize()
-            return a0.elapsed_time(a1) / 3
-        generic_step_ms = generic_ms()
-
+            generic_step_ms = a0.elapsed_time(a1) / 3
         imad, imad_w, _mhz = C.c_double(), C.c_double(), C.c_double()
         _ffi.check(L.h2b_imad_peak(C.byref(imad), C.byref(imad_w), C.byref(_mhz)))
 
-        sampler = ClockSampler(local) if rank == 0 else None
-        for _ in range(max(args.warmup, 3)):
-            step()
+    m = measure(params, d_scalars, host_scalars, n, args.steps, True)
+    ms_step = m["ms_step"]
+    value = n_global / (ms_step * 1e-3)
+    e2e_value = n_global / (m["e2e_ms"] * 1e-3)
+
+    # ---- parity at N ranks against the oracle (every rank's first `ms` points; the fold of the per-rank partial
+    # sums must be the oracle's MSM over the concatenated sample)
+    ms_pts = min(n, 1 << args.ref_log_n)
+    part = torch.empty(12, dtype=torch.int64, device="cuda")
+    with torch.cuda.stream(stream):
+        params.dev_commit(d_scalars[:ms_pts], part, stream=stream)
         stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        if sampler:
-            sampler.mark_begin()
-        _ffi.check(L.h2b_set_kernel_timing(1))
-        launches0 = L.h2b_kernel_launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        stream.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms_total = e0.elapsed_time(e1)
-        launches = L.h2b_kernel_launches() - launches0
-        ktot, kcalls = C.c_double(), C.c_uint32()
-        _ffi.check(L.h2b_kernel_time_collect(C.byref(ktot), C.byref(kcalls)))
-        _ffi.check(L.h2b_set_kernel_timing(0))
-        clocks = sampler.stop() if sampler else None
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item()) / args.steps
-        value = world * n / (ms_step * 1e-3)
-
-    # ---- end to end through the reference-facing call: ParamsKZG::commit with pinned host scalars
-    res_host = np.zeros(12, dtype=np.uint64)
-    hs_ptr = C.cast(C.c_void_p(host_scalars.data_ptr()), C.POINTER(C.c_uint64))
-
-    def e2e_step():
-        _ffi.check(L.h2b_commit(handle, hs_ptr, C.c_size_t(n), _ffi.u64p(res_host)))
-        if world > 1:
-            part = torch.from_numpy(res_host.view(np.int64)).cuda()
-            parts = multi_gpu.gather_partials(part)
-            folded = torch.empty(12, dtype=torch.int64, device="cuda")
-            arithmetic.dev_g1_fold(parts, folded, stream=torch.cuda.current_stream())
-            folded.cpu()
-
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize()
+    sample_sc = d_scalars[:ms_pts].contiguous()
+    sample_b = d_bases[:ms_pts].contiguous()
     if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(t.item())
+        parts = multi_gpu.gather_partials(part)
+        folded = torch.empty(12, dtype=torch.int64, device="cuda")
+        arithmetic.dev_g1_fold(parts, folded, stream=torch.cuda.current_stream())
+        all_sc = torch.empty((world * ms_pts, 4), dtype=torch.int64, device="cuda")
+        all_b = torch.empty((world * ms_pts, 8), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(all_sc.view(-1), sample_sc.view(-1))
+        dist.all_gather_into_tensor(all_b.view(-1), sample_b.view(-1))
+    else:
+        folded, all_sc, all_b = part, sample_sc, sample_b
+    parity = None
+    cpu = None
+    if rank == 0:
+        threads = os.cpu_count() or 1
+        sc_h = np.ascontiguousarray(all_sc.cpu().numpy().view(np.uint64))
+        b_h = np.ascontiguousarray(all_b.cpu().numpy().view(np.uint64))
+        t0 = time.perf_counter()
+        want = h2ref.best_multiexp(sc_h, b_h, threads)
+        dt = time.perf_counter() - t0
+        ok = bool((h2ref.g1_to_affine(want) == h2ref.g1_to_affine(folded.cpu().numpy().view(np.uint64))).all())
+        assert ok, "folded per-rank partial sums differ from the oracle"
+        parity = {"ranks": world, "points_per_rank": ms_pts, "equals_oracle": ok,
+                  "what": "fold of the per-rank commits of each rank's first points == oracle MSM over the union"}
+        if world == 1 and not args.no_cpu:
+            check = np.zeros(12, dtype=np.uint64)
+            _ffi.check(L.h2b_best_multiexp(_ffi.u64p(sc_h), _ffi.u64p(b_h), C.c_size_t(ms_pts), _ffi.u64p(check)))
+            assert (h2ref.g1_to_affine(want) == h2ref.g1_to_affine(check)).all(), "GPU and CPU baseline disagree"
+            cpu = {"value": ms_pts / dt, "unit": "points/s", "cores": threads, "kind": "port",
+                   "sample": f"first 2^{args.ref_log_n} points of the workload; C restatement of halo2_proofs@6b43b6b "
+                             "best_multiexp (not the Rust binary); result equal to the GPU's on the same sample; "
+                             "`bench.py --impl reference` runs the whole 2^%d" % args.log_n}
+    del all_sc, all_b
+
     # the same call with ordinary (pageable) host memory, which is what the reference's Vec<Fr> is
     e2e_pageable = None
     if world == 1:
@@ -293,52 +380,57 @@ def run_b200(args) -> None:
         for _ in range(3):
             _ffi.check(L.h2b_commit(handle, _ffi.u64p(pageable), C.c_size_t(n), _ffi.u64p(res2)))
         e2e_pageable = n * 3 / (time.perf_counter() - t0)
-        import h2ref as _h2ref  # projective representatives differ with the (atomic) accumulation order
-        assert (_h2ref.g1_to_affine(res2) == _h2ref.g1_to_affine(res_host)).all()
         del pageable
-    # the device-resident and the end-to-end paths must agree on the result (rank-local shard)
-    if world == 1:
-        import h2ref
-        assert (h2ref.g1_to_affine(out.cpu().numpy().view(np.uint64)) == h2ref.g1_to_affine(res_host)).all()
-        assert (h2ref.g1_to_affine(out_generic.cpu().numpy().view(np.uint64)) == h2ref.g1_to_affine(res_host)).all()
     params.release()
+    del d_bases, d_scalars, host_scalars
+    torch.cuda.empty_cache()
+
+    # ---- weak scaling beside it (N > 1): 2^log_n points PER GPU
+    weak = None
+    if world > 1 and not args.no_weak:
+        hs_w, ds_w, db_w = make_inputs(n_global, 100 + rank)
+        params_w, t_reg_w = register(db_w, n_global)
+        mw = measure(params_w, ds_w, hs_w, n_global, min(args.steps, 5), False)
+        weak = {"scaling": "weak", "points_per_gpu": n_global, "global_points": world * n_global,
+                "value": world * n_global / (mw["ms_step"] * 1e-3), "ms_per_step": mw["ms_step"],
+                "e2e_value": world * n_global / (mw["e2e_ms"] * 1e-3), "steps": min(args.steps, 5), "register_s": t_reg_w}
+        params_w.release()
+        del hs_w, ds_w, db_w
+        torch.cuda.empty_cache()
 
     # ---- NTT k = 20 (rank 0): forward best_fft and the coset extended-domain transform
     ntt = None
     if rank == 0 and not args.no_ntt:
         ntt = bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, float(imad.value))
 
-    # ---- CPU baseline beside it (rank 0, N = 1): bounded sample on the host cores
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        import h2ref
-        threads = os.cpu_count() or 1
-        m = 1 << args.ref_log_n
-        sc = np.ascontiguousarray(host_scalars.numpy().view(np.uint64)[:m])
-        bs = np.ascontiguousarray(d_bases[:m].cpu().numpy().view(np.uint64))
-        t0 = time.perf_counter()
-        cpu_res = h2ref.best_multiexp(sc, bs, threads)
-        dt = time.perf_counter() - t0
-        check = np.zeros(12, dtype=np.uint64)
-        _ffi.check(L.h2b_best_multiexp(_ffi.u64p(sc), _ffi.u64p(bs), C.c_size_t(m), _ffi.u64p(check)))
-        assert (h2ref.g1_to_affine(cpu_res) == h2ref.g1_to_affine(check)).all(), "GPU and CPU baseline disagree"
-        cpu = {"value": m / dt, "unit": "points/s", "cores": threads, "kind": "port",
-               "sample": f"first 2^{args.ref_log_n} points of the workload; C restatement of halo2_proofs@6b43b6b "
-                         "best_multiexp (not the Rust binary); result equal to the GPU's on the same sample"}
-
-    replay = None
-    evalh = None
+    replay = evalh = None
     if rank == 0 and world == 1 and not args.no_cpu:
         replay = bench_proof_replay(args, h2b, _ffi)
         evalh = bench_evaluate_h(args, torch, h2b)
 
+    # ---- ONE process driving all N devices through the C ABI (h2b_init_devices): the other ranks park on the
+    # host while rank 0 re-initialises the library over every GPU of the job
+    single = None
+    if world > 1 and not args.no_single_process:
+        torch.cuda.synchronize()
+        dist.barrier()
+        _ffi.shutdown()
+        if rank == 0:
+            try:
+                single = bench_single_process(args, torch, _ffi, world, gen)
+            except Exception as exc:  # reported, never fatal for the headline line
+                single = {"error": repr(exc)}
+            _wait_flag(dist, "h2b_single_done", rank, True)
+        else:
+            _wait_flag(dist, "h2b_single_done", rank, False)
+
     if rank == 0:
         peaks = measured_peaks()
-        acc_ms = ktot.value / max(kcalls.value, 1)
-        imad_per_launch = float(n) * MSM_MODMUL_PER_POINT * MODMUL_IMAD
-        achieved = imad_per_launch / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+        acc_ms = m["acc_ms_total"] / max(m["acc_calls"], 1)
         peak = imad.value / 1e3
         adds_per_point = srs_w.value if srs_w.value else 15
+        # SURVEY 8d's algorithmic model: 16 additions x 10 modmul x 272 IMAD-class per point
+        model = float(n) * MSM_MODMUL_PER_POINT * MODMUL_IMAD / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
         # SASS of one XYZZ mixed addition: 6 products (120 IMAD.WIDE + 16 IMAD each), 2 dedicated squares (92 + 16) and
         # one fused two-product multiply (184 + 16); IMAD.WIDE counts as two IMAD-class instructions (4 vs 2 pipe cycles)
         MADD_IMAD = (6 * 120 + 2 * 92 + 184) * 2 + 9 * 16
@@ -346,42 +438,46 @@ def run_b200(args) -> None:
         hbm_peak = peaks.get("hbm_gbs")
         line = {
             "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32x8 Montgomery (int)", "data": "synthetic",
-            "config": {"workload": f"BN254 G1 MSM, 2^{args.log_n} points per GPU, uniform scalars, distinct random bases, "
-                                   "as ParamsKZG::commit issues it (bases registered once, scalars per call)",
-                       "srs": {"window_bits": srs_c.value, "windows": srs_w.value, "table_bytes": srs_bytes.value,
-                               "register_s": t_reg},
-                       "global_points": world * n, "parallelism": f"point-range shards x{world}, all-gather of 96 B partials",
-                       "l2": "inputs (1.5 GiB per step) exceed L2; no flush needed",
-                       "ntt_workload": "best_fft k=20 and coeff_to_extended 18->20, 8 rotating buffers (256 MiB > L2)"},
-            "clocks": clocks,
+            "config": workload_config(args),
+            "parallelism": f"point-range shards x{world} ({n} points per GPU), all-gather of 96 B partials, fold on every GPU",
+            "srs": {"points_per_gpu": n, "window_bits": srs_c.value, "windows": srs_w.value, "table_bytes": srs_bytes.value,
+                    "register_s": t_reg},
+            "clocks": m["clocks"],
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
-                    "api": "ParamsKZG.commit -> h2b_commit, pinned host scalars, SRS resident",
+                    "api": "ParamsKZG.commit -> h2b_commit per rank, pinned host scalars, SRS resident"
+                           + ("; all-gather + fold of the partials" if world > 1 else ""),
                     "pageable_host_value": e2e_pageable},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "TIMAD/s", "frac": (achieved / peak) if achieved and peak else None,
+            "gpu_launches": m["launches"],
+            "parity": parity,
+            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel",
+                         # utilisation: instructions the kernel EXECUTES (from its SASS) over the measured IMAD peak
+                         "achieved": executed, "peak": peak, "unit": "TIMAD/s",
+                         "frac": (executed / peak) if executed and peak else None,
+                         "frac_executed": (executed / peak) if executed and peak else None,
+                         "executed": "%d mixed additions per point (precomputed window table) x 2320 IMAD-class per addition "
+                                     "from SASS (6 products, 2 dedicated squares, 1 fused two-product multiply; IMAD.WIDE = 2)"
+                                     % adds_per_point,
+                         # SURVEY 8d's algorithmic work model, kept for comparison: it assumes 16 additions x 2720
+                         # IMAD-class per point, MORE than this kernel executes, so this ratio is not a utilisation
+                         "frac_model": (model / peak) if model and peak else None, "achieved_model": model,
+                         "model": "43,520 IMAD-class/point (160 modmul x 272) x %d points per launch" % n,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 / 13 windows from the
-                         # committed capture profiles/r01_ncu_full_commit_accumulate_v12.md (ncu cannot run inside the
-                         # timed bench); only quoted for the configuration it was captured on
-                         "traffic": 29.42e9 if (args.log_n == 24 and srs_w.value == 13) else None,
+                         # committed capture (ncu cannot run inside the timed bench); only quoted for that geometry
+                         "traffic": 29.42e9 if (n == 1 << 24 and srs_w.value == 13) else None,
                          "traffic_source": "profiles/r01_ncu_full_commit_accumulate_v12.md (ncu --set full, per launch)",
                          "launch_ms": acc_ms,
-                         "algorithmic": "43,520 IMAD-class/point (160 modmul x 272) x 2^%d points per launch" % args.log_n,
-                         "executed": {"achieved": executed, "frac": (executed / peak) if executed and peak else None,
-                                      "note": "%d mixed additions per point actually executed (precomputed window "
-                                              "table) x 2320 IMAD-class per addition from SASS (6 products, 2 dedicated "
-                                              "squares, 1 fused two-product multiply; 2720 = 10 x 272 in the algorithmic "
-                                              "model, which also assumes 16 additions, so frac above can exceed 1)"
-                                              % adds_per_point},
                          "peak_source": "measured live: mad.lo.u32 microbenchmark (h2b_imad_peak); "
                                         "IMAD.WIDE rate %.1f G/s" % imad_w.value,
                          "hbm": {"achieved_gbs": n * MSM_BYTES_PER_POINT / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
                                  "peak_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if hbm_peak else "absent"}},
-            "best_multiexp_resident": {"ms": generic_step_ms, "points_per_s": n / (generic_step_ms * 1e-3),
-                                       "what": "h2b_dev_msm with caller-supplied bases (no table), this rank's shard"},
+            "best_multiexp_resident": None if generic_step_ms is None else
+            {"ms": generic_step_ms, "points_per_s": n / (generic_step_ms * 1e-3),
+             "what": "h2b_dev_msm with caller-supplied bases (no table)"},
             "cpu_baseline": cpu,
+            "weak": weak,
+            "single_process": single,
             "ntt": ntt,
             "proof_replay": replay,
             "evaluate_h": evalh,
@@ -389,6 +485,105 @@ def run_b200(args) -> None:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_single_process(args, torch, _ffi, ndev: int, gen) -> dict:
+    """The metric through the C ABI from ONE process that owns all N devices (h2b_init_devices): the SRS is sharded
+    by point range at registration, h2b_commit splits the host scalars so that every device copies its slice over its
+    own PCIe link, the partial sums travel device-to-device and are folded on the primary device."""
+    import h2ref
+    L = _ffi.lib()
+    _ffi.init_devices(list(range(ndev)))
+    n = 1 << args.log_n
+    torch.cuda.set_device(0)
+    s = torch.cuda.Stream()
+    sp = C.c_void_p(s.cuda_stream)
+    hs = torch.from_numpy(rand_fr_np(n, 31337).view(np.int64)).pin_memory()
+    with torch.cuda.stream(s):
+        seeds = torch.from_numpy(rand_fr_np(n, 31338).view(np.int64)).cuda()
+        db = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        _ffi.check(L.h2b_dev_fixed_base_mul(C.c_void_p(seeds.data_ptr()), C.c_size_t(n), _ffi.u64p(gen),
+                                            C.c_void_p(db.data_ptr()), sp))
+        s.synchronize()
+        del seeds
+    t0 = time.perf_counter()
+    h = C.c_uint64(0)
+    _ffi.check(L.h2b_dev_srs_register(C.c_void_p(db.data_ptr()), C.c_size_t(n), C.byref(h)))
+    t_reg = time.perf_counter() - t0
+    parts, repl = C.c_uint32(), C.c_uint32()
+    _ffi.check(L.h2b_srs_layout(h, C.byref(parts), C.byref(repl), None))
+    # parity: scalars that are zero except at every 64th point (all shards touched) against the oracle over those points
+    stride = 64
+    idx = np.arange(0, n, stride)
+    sparse = np.zeros((n, 4), dtype=np.uint64)
+    vals = rand_fr_np(idx.size, 31339)
+    sparse[idx] = vals
+    res = np.zeros(12, dtype=np.uint64)
+    _ffi.check(L.h2b_commit(h, _ffi.u64p(sparse), C.c_size_t(n), _ffi.u64p(res)))
+    b_h = np.ascontiguousarray(db[torch.from_numpy(idx).cuda()].cpu().numpy().view(np.uint64))
+    want = h2ref.best_multiexp(np.ascontiguousarray(vals), b_h, os.cpu_count() or 1)
+    ok = bool((h2ref.g1_to_affine(want) == h2ref.g1_to_affine(res)).all())
+    del sparse
+    # end to end: pinned host scalars -> h2b_commit -> 96-byte result
+    hp = C.cast(C.c_void_p(hs.data_ptr()), C.POINTER(C.c_uint64))
+    for _ in range(3):
+        _ffi.check(L.h2b_commit(h, hp, C.c_size_t(n), _ffi.u64p(res)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _ffi.check(L.h2b_commit(h, hp, C.c_size_t(n), _ffi.u64p(res)))
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    res_e2e = res.copy()
+    # scalars resident on the primary device: the other devices pull their slices over NVLink
+    with torch.cuda.stream(s):
+        ds = hs.cuda(non_blocking=True)
+        out = torch.empty(12, dtype=torch.int64, device="cuda")
+        for _ in range(3):
+            _ffi.check(L.h2b_dev_commit(h, C.c_void_p(ds.data_ptr()), C.c_size_t(n), C.c_void_p(out.data_ptr()), sp))
+        s.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _ffi.check(L.h2b_dev_commit(h, C.c_void_p(ds.data_ptr()), C.c_size_t(n), C.c_void_p(out.data_ptr()), sp))
+        s.synchronize()
+        dev_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    same = bool((h2ref.g1_to_affine(out.cpu().numpy().view(np.uint64)) == h2ref.g1_to_affine(res_e2e)).all())
+    # what the host side can deliver: pinned host memory to every device at once
+    probe = h2d_probe(torch, ndev, 64 << 20)
+    _ffi.check(L.h2b_srs_release(h))
+    _ffi.shutdown()
+    return {"what": "one process, h2b_init_devices over %d GPUs, 2^%d-point ParamsKZG::commit through the C ABI" % (ndev, args.log_n),
+            "devices": ndev, "srs_parts": parts.value, "srs_replicated": bool(repl.value), "register_s": t_reg,
+            "e2e": {"value": n / (e2e_ms * 1e-3), "ms": e2e_ms, "unit": "points/s", "h2d_bytes_per_step": n * 32,
+                    "d2h_bytes_per_step": 96, "api": "h2b_commit, pinned host scalars (wall clock around the call)"},
+            "resident": {"value": n / (dev_ms * 1e-3), "ms": dev_ms,
+                         "api": "h2b_dev_commit, scalars on the primary device, slices pulled over NVLink"},
+            "equals_oracle_on_sample": ok, "sample": "every %dth scalar non-zero (2^%d points across all shards)" % (stride, (idx.size - 1).bit_length()),
+            "resident_equals_e2e": same, "h2d_probe": probe}
+
+
+def h2d_probe(torch, ndev: int, nbytes: int) -> dict:
+    """Pinned host memory -> HBM bandwidth, one device alone and all devices at once (GB/s): the ceiling of
+    every end-to-end number above, whatever the kernels do."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = [torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{d}") for d in range(ndev)]
+    streams = [torch.cuda.Stream(device=d) for d in range(ndev)]
+
+    def run(devs):
+        for d in devs:
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for _ in range(4):
+            for d in devs:
+                with torch.cuda.stream(streams[d]):
+                    dst[d].copy_(src, non_blocking=True)
+        for d in devs:
+            streams[d].synchronize()
+        return 4 * len(devs) * nbytes / (time.perf_counter() - t0) / 1e9
+
+    run([0])
+    alone = run([0])
+    run(list(range(ndev)))
+    allg = run(list(range(ndev)))
+    return {"bytes": nbytes, "one_device_gbs": alone, "all_devices_aggregate_gbs": allg, "devices": ndev}
 
 
 def bench_proof_replay(args, h2b, _ffi) -> dict:
@@ -406,7 +601,9 @@ def bench_proof_replay(args, h2b, _ffi) -> dict:
     dc = h2ref.domain_new(6, k)
     g = h2ref.random_g1(1 << 10, 5)
     g = np.ascontiguousarray(np.tile(g, (n >> 10, 1))) if n >= 1024 else g[:n].copy()
-    params = h2b.ParamsKZG(k, g, g)
+    t_reg = time.perf_counter()
+    params = h2b.ParamsKZG(k, g, g)  # both base arrays: copy to HBM + static-base precomputation, once per ParamsKZG
+    t_reg = time.perf_counter() - t_reg
     cols = [rand_fr_np(n, 300 + i) for i in range(7)]
     ext_in = rand_fr_np(1 << d.extended_k, 399)
 
@@ -537,6 +734,10 @@ def bench_proof_replay(args, h2b, _ffi) -> dict:
             "gpu_resident_ms": resident_ms, "resident_equals_single": bool(same_r),
             "resident_what": "the same 31 calls with every polynomial in HBM (batched) plus evaluate_h and "
                              "divide_by_vanishing_poly between coeff_to_extended and extended_to_coeff: no host copies",
+            "srs_register_ms": t_reg * 1e3,
+            "srs_register_what": "h2b_srs_register of g and g_lagrange (2 x 2^%d points): paid once per ParamsKZG, not per "
+                                 "proof; the reference re-reads its params on every wasm call (wasm.rs:79), a native "
+                                 "prover keeps ParamsKZG across proofs" % k,
             "cpu_ms": cpu_ms, "cpu_threads": threads, "commitments_equal": bool(same)}
 
 
@@ -657,9 +858,11 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log-n", type=int, default=24, help="log2 points per GPU")
+    ap.add_argument("--log-n", type=int, default=24, help="log2 points of the MSM (global)")
     ap.add_argument("--ntt-k", type=int, default=20)
-    ap.add_argument("--ref-log-n", type=int, default=18, help="log2 points of the bounded CPU sample")
+    ap.add_argument("--ref-log-n", type=int, default=18, help="log2 points of the bounded CPU sample / per-rank parity sample")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling measurement at N > 1")
+    ap.add_argument("--no-single-process", action="store_true", help="skip the one-process N-device run at N > 1")
     ap.add_argument("--proof-k", type=int, default=14, help="rows (log2) of the proof-shaped replay")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

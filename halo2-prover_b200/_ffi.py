@@ -19,14 +19,14 @@ ERR_NAMES = {-1: "H2B_ERR_ARG", -2: "H2B_ERR_CUDA", -3: "H2B_ERR_OOM", -4: "H2B_
 
 # every symbol include/h2b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "h2b_init", "h2b_shutdown", "h2b_last_error", "h2b_abi_version",
+    "h2b_init", "h2b_init_devices", "h2b_device_count", "h2b_shutdown", "h2b_last_error", "h2b_abi_version",
     "h2b_best_multiexp", "h2b_srs_register", "h2b_srs_release", "h2b_commit", "h2b_g1_fold", "h2b_g1_to_bytes", "h2b_g_to_lagrange", "h2b_dev_evaluate_h", "h2b_dev_evaluate_h_lookup",
     "h2b_best_fft", "h2b_domain_new", "h2b_lagrange_to_coeff", "h2b_coeff_to_extended",
     "h2b_extended_to_coeff", "h2b_divide_by_vanishing_poly", "h2b_lagrange_to_coeff_many", "h2b_coeff_to_extended_many",
     "h2b_dev_lagrange_to_coeff_many", "h2b_dev_coeff_to_extended_many", "h2b_dev_divide_by_vanishing_poly",
     "h2b_dev_srs_register", "h2b_dev_msm", "h2b_dev_commit", "h2b_dev_commit_many", "h2b_commit_many", "h2b_srs_device_ptr", "h2b_dev_best_fft", "h2b_dev_lagrange_to_coeff",
     "h2b_dev_coeff_to_extended", "h2b_dev_extended_to_coeff", "h2b_dev_g1_fold", "h2b_dev_fixed_base_mul",
-    "h2b_set_msm_window", "h2b_srs_info", "h2b_params_read", "h2b_set_srs_precompute", "h2b_set_e2e_chunking", "h2b_kernel_launches", "h2b_set_kernel_timing", "h2b_kernel_time_collect",
+    "h2b_set_msm_window", "h2b_srs_info", "h2b_srs_layout", "h2b_test_set_max_entries", "h2b_params_read", "h2b_set_srs_precompute", "h2b_set_e2e_chunking", "h2b_kernel_launches", "h2b_set_kernel_timing", "h2b_kernel_time_collect",
     "h2b_test_field_op", "h2b_test_g1_add_affine", "h2b_imad_peak",
 ]
 
@@ -92,6 +92,15 @@ def init(device: int | None = None) -> None:
         return
     check(lib().h2b_init(C.c_int(device)))
     _inited_device = device
+
+
+def init_devices(devices) -> None:
+    """h2b_init_devices: one process, several GPUs (devices[0] is the primary device)."""
+    global _inited_device
+    devices = [int(d) for d in devices]
+    arr = (C.c_int * len(devices))(*devices)
+    check(lib().h2b_init_devices(arr, C.c_int(len(devices))))
+    _inited_device = devices[0]
 
 
 def shutdown() -> None:

@@ -12,8 +12,11 @@
 
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -43,7 +46,7 @@ std::mutex g_mu;
 enum BufId {
     BUF_SCALARS = 0, BUF_BASES, BUF_COUNTS, BUF_CURSOR, BUF_NEOFF, BUF_NEID, BUF_SORTED, BUF_DIGITS, BUF_HEAD, BUF_TAIL,
     BUF_TAILJ, BUF_TOTALS, BUF_ECNTT, BUF_EVALH, BUF_EVALH_SCRATCH,
-    BUF_BUCKETS, BUF_BUCKETS2, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
+    BUF_BUCKETS, BUF_BUCKETS2, BUF_WINDOWS, BUF_WPART, BUF_BLOCKSUMS, BUF_HEAVY, BUF_OUT, BUF_GATHER, BUF_NTT_A, BUF_NTT_T, BUF_NTT_T2, BUF_NTT_IN,
     BUF_NTT_OUT, BUF_MISC,
     BUF_TEST_A, BUF_TEST_B, BUF_TEST_O, BUF_COUNT
 };
@@ -57,8 +60,11 @@ struct TwKey {
         return log_n < o.log_n;
     }
 };
+// One device's share of a registered base array.
 struct Srs {
-    Affine *d = nullptr;      // the registered bases (n x 64 B)
+    int dev = 0;              // index into g_all
+    size_t off = 0;           // first point of the share inside the registered array
+    Affine *d = nullptr;      // the bases of the share (n x 64 B)
     size_t n = 0;
     Affine *table = nullptr;  // precomputed windows: table[w * n + i] = 2^(c*w) * d[i], or null
     uint32_t c = 0, windows = 0;
@@ -67,13 +73,75 @@ struct Srs {
     uint32_t comb_c = 0, comb_w = 0;
 };
 
+// One persistent host thread per context: the multi-device paths hand each device's share of a call to its worker
+// so that the copies and launches for different devices are issued concurrently (each over its own PCIe link).
+class Worker {
+  public:
+    void start() {
+        th_ = std::thread([this] { loop(); });
+    }
+    void submit(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = std::move(f);
+            state_ = 1;
+        }
+        cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return state_ == 0; });
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        if (th_.joinable()) th_.join();
+    }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || state_ == 1; });
+                if (stop_) return;
+                f = std::move(job_);
+                state_ = 2;
+            }
+            f();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                state_ = 0;
+            }
+            cv_.notify_all();
+        }
+    }
+    std::thread th_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::function<void()> job_;
+    int state_ = 0;  // 0 idle, 1 submitted, 2 running
+    bool stop_ = false;
+};
+
+// A registered base array: one share on a single device, or -- with several devices (h2b_init_devices) -- either
+// the whole array replicated on every device (small SRS: whole columns are dealt to the devices) or contiguous
+// point ranges, one per device (large SRS: every commit is split by point range and the partial sums are folded).
+struct SrsSet {
+    size_t n = 0;
+    bool replicated = false;
+    std::vector<Srs> parts;   // parts[0] lives on the primary device
+};
+
 struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
     void *buf[BUF_COUNT] = {};
     size_t cap[BUF_COUNT] = {};
-    std::map<uint64_t, Srs> srs;
-    uint64_t next_handle = 1;
     std::map<TwKey, Fe *> twiddles;
     size_t twiddle_bytes = 0;
     std::map<uint64_t, h2b_domain> domains;
@@ -84,8 +152,8 @@ struct Ctx {
     uint32_t reduce_lone = 2;  // tree levels done by lone threads on large grids (H2B_REDUCE_LONE)
     uint32_t min_slice = 16;   // shortest accumulation slice (H2B_MIN_SLICE)
     uint32_t min_waves = 1;    // fewest accumulation waves (H2B_MIN_WAVES)
-    uint64_t epoch = 0;        // distinguishes successive contexts (init after shutdown, possibly on another device)
-    uint64_t reduce_attr_epoch = 0;
+    uint64_t max_entries = 1ull << 31;  // sorted entries per pass (H2B_MAX_ENTRIES_LOG lowers it for tests)
+    std::set<const void *> attr_done;  // kernels whose dynamic shared-memory limit was raised on this device
     int reduce_q = -1;         // first-stage run length 2^q of the tree reduction, -1 = automatic (H2B_REDUCE_Q)
     size_t comb_max_n = (size_t)1 << 14;  // registered SRS up to this length get the bucket-free table
     uint32_t comb_c = 8;
@@ -103,8 +171,17 @@ struct Ctx {
     uint32_t tev_used = 0;
     int sm_count = 148;
     HostCopier *copier = nullptr;  // pageable host memory <-> HBM through worker threads and a pinned ring
+    Worker worker;
 };
-Ctx *g = nullptr;
+// `g` is the context the calling thread works on.  API entry points set it to the primary context (ensure_ctx);
+// the multi-device paths run one worker thread per device, each with its own `g` (so every internal function
+// below is device-agnostic), while the API thread holds g_mu.
+thread_local Ctx *g = nullptr;
+Ctx *g_primary = nullptr;
+std::vector<Ctx *> g_all;  // every context of h2b_init / h2b_init_devices; g_all[0] == g_primary
+std::map<uint64_t, SrsSet> g_srs;
+uint64_t g_next_handle = 1;
+size_t g_shard_min_n = (size_t)1 << 21;  // registered arrays from this length up are sharded by point range (H2B_SHARD_MIN_LOG)
 
 int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
     char tmp[512];
@@ -131,6 +208,7 @@ int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
     } while (0)
 
 int ensure_ctx() {
+    g = g_primary;
     if (g) return H2B_OK;
     return fail(H2B_ERR_STATE, "h2b_init has not been called");
 }
@@ -179,10 +257,22 @@ int enter(cudaStream_t s) {
     if (g->last_stream && g->last_stream != s) CU(cudaStreamWaitEvent(s, g->last_done, 0));
     return H2B_OK;
 }
-int leave(cudaStream_t s, int rc) {
-    if (cudaEventRecord(g->last_done, s) == cudaSuccess) g->last_stream = s;
-    return rc;
-}
+// One per entry point: orders the call after the previous one (enter) and records the context's `last_done`
+// event on EVERY exit path, error returns included, so that the next call on another stream -- and
+// h2b_srs_release / workspace regrowth -- wait for whatever this call managed to enqueue.
+struct Scope {
+    Ctx *c = nullptr;
+    cudaStream_t s = nullptr;
+    int begin(cudaStream_t st) {
+        TRY(enter(st));
+        c = g;
+        s = st;
+        return H2B_OK;
+    }
+    ~Scope() {
+        if (c && cudaEventRecord(c->last_done, s) == cudaSuccess) c->last_stream = s;
+    }
+};
 
 constexpr uint32_t kMaxTimed = 256;
 void time_begin(cudaStream_t s) {
@@ -307,6 +397,15 @@ int msm_begin(size_t n_total, MsmRun *run, cudaStream_t s, const Srs *srs = null
 int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m, cudaStream_t s, size_t ioff = 0) {
     if (m == 0) return H2B_OK;
     MsmCfg cfg = run.cfg;
+    // Positions in the sorted entry list (cursor, ne_off, totals) are 32-bit: a chunk of 2^31 entries or more
+    // (from ~2^27 points at 15 windows) is split by point range; the halves add into the same buckets.
+    if ((uint64_t)m * cfg.cols * cfg.windows >= g->max_entries) {
+        if (cfg.cols > 1 || m < 2) return fail(H2B_ERR_ARG, "msm: batch too large for one pass");
+        size_t half = m / 2;
+        if (half >= 512) half &= ~(size_t)255;
+        TRY(msm_chunk(run, d_scalars, d_bases, half, s, ioff));
+        return msm_chunk(run, d_scalars + half, cfg.shared ? d_bases : d_bases + half, m - half, s, ioff + half);
+    }
     cfg.n = (uint32_t)m;
     cfg.ioff = (uint32_t)ioff;
     size_t entries = m * cfg.cols * cfg.windows;
@@ -398,10 +497,10 @@ int msm_chunk(MsmRun &run, const Fe *d_scalars, const Affine *d_bases, size_t m,
 int msm_reduce_tree(const XYZZ *buckets, uint32_t bpw, uint32_t nwin, XYZZ *windows, cudaStream_t s) {
     constexpr int kThreads = 256;
     constexpr uint32_t kLgT = 8;
-    if (g->reduce_attr_epoch != g->epoch) {  // per context: the attribute belongs to the device of h2b_init
+    if (!g->attr_done.count((const void *)msm_bit_tree_kernel<kThreads>)) {  // per context: the attribute belongs to its device
         CU(cudaFuncSetAttribute(msm_bit_tree_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(2 * sizeof(XYZZ) << kLgT)));
-        g->reduce_attr_epoch = g->epoch;
+        g->attr_done.insert((const void *)msm_bit_tree_kernel<kThreads>);
     }
     // wide windows are throughput-bound: fold runs of 2^q buckets by lone threads first (full lane efficiency)
     // (measured: commits at 2^18 / 2^20 / 2^22 points, q = 0 / 2 / 4: 1.23 / 1.22 / 1.36, 3.52 / 3.39 / 3.20,
@@ -642,11 +741,10 @@ int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log
                 const NttIo &io, cudaStream_t s, uint32_t batch) {
     constexpr int R = 1 << S;
     size_t smem = ((size_t)2 * R * C + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
-    static uint64_t attr_epoch = 0;  // per instantiation; redone for every context (device may differ)
-    if (attr_epoch != g->epoch && smem > 48 * 1024) {
+    if (smem > 48 * 1024 && !g->attr_done.count((const void *)ntt_pass_kernel<S, C, NT>)) {
         CU(cudaFuncSetAttribute(ntt_pass_kernel<S, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-        attr_epoch = g->epoch;
+        g->attr_done.insert((const void *)ntt_pass_kernel<S, C, NT>);
     }
     uint32_t M = 1u << (log_n - S);
     uint32_t blocks = M / C;
@@ -1032,7 +1130,6 @@ __global__ void imad_wide_bench_kernel(uint64_t *sink, uint32_t iters, uint32_t 
 
 // host staging helpers
 int stage_in(BufId id, const void *host, size_t bytes, void **dev) {
-    TRY(enter(g->stream));
     TRY(get_buf(id, bytes, dev));
     return copy_in(*dev, host, bytes, g->stream);
 }
@@ -1045,24 +1142,13 @@ extern "C" {
 uint32_t h2b_abi_version(void) { return 1; }
 const char *h2b_last_error(void) { return g_err.c_str(); }
 
-int h2b_init(int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g && g->device == device) return H2B_OK;
-    if (g) return fail(H2B_ERR_STATE, "h2b_init: already initialised on another device");
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        (void)cudaGetLastError();
-        return fail(H2B_ERR_CUDA, "h2b_init: no CUDA device (this library has no CPU fallback)", e);
-    }
-    if (device < 0 || device >= count) return fail(H2B_ERR_ARG, "h2b_init: bad device index");
+// One context per device: stream, copy stream, workspace, caches, tunables from the environment.
+static int ctx_create(int device, Ctx **out) {
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(H2B_ERR_CUDA, "h2b_init: kernels are built for sm_100a only");
     Ctx *c = new Ctx();
-    static uint64_t epochs = 0;
-    c->epoch = ++epochs;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1078,18 +1164,6 @@ int h2b_init(int device) {
         if (ct) threads = atoi(ct);
         c->copier = new HostCopier(threads);
     }
-    const char *mr = getenv("H2B_NTT_MAX_RADIX");
-    if (mr) {
-        int v = atoi(mr);
-        if (v >= 5 && v <= 10) g_ntt_max_radix = (uint32_t)v;
-    }
-    const char *tl = getenv("H2B_NTT_TILE_LOG");
-    if (tl) {
-        int v = atoi(tl);
-        if (v >= 8 && v <= 10) g_ntt_tile_log = (uint32_t)v;
-    }
-    if (g_ntt_tile_log == 9 && g_ntt_max_radix > 9) g_ntt_max_radix = 9;
-    if (g_ntt_tile_log == 8 && g_ntt_max_radix > 8) g_ntt_max_radix = 8;
     const char *sw = getenv("H2B_SRS_WINDOW");
     if (sw) {
         int v = atoi(sw);
@@ -1116,32 +1190,107 @@ int h2b_init(int device) {
         int v = atoi(ec);
         if (v >= 1 && v <= 64) c->e2e_chunks = (uint32_t)v;
     }
-    g = c;
+    c->worker.start();
+    *out = c;
+    return H2B_OK;
+}
+static void ctx_destroy(Ctx *c) {
+    c->worker.stop();
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < BUF_COUNT; i++)
+        if (c->buf[i]) cudaFree(c->buf[i]);
+    for (auto &kv : c->twiddles) cudaFree(kv.second);
+    for (auto e : c->tev0) cudaEventDestroy(e);
+    for (auto e : c->tev1) cudaEventDestroy(e);
+    for (auto e : c->chunk_events) cudaEventDestroy(e);
+    delete c->copier;
+    cudaEventDestroy(c->copy_fence);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->last_done);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int init_locked(const int *devices, int count) {
+    if (!devices || count < 1 || count > 64) return fail(H2B_ERR_ARG, "h2b_init: bad device list");
+    if (g_primary) {
+        bool same = (int)g_all.size() == count;
+        for (int i = 0; same && i < count; i++) same = g_all[i]->device == devices[i];
+        if (same) return H2B_OK;
+        return fail(H2B_ERR_STATE, "h2b_init: already initialised on other devices");
+    }
+    int have = 0;
+    cudaError_t e = cudaGetDeviceCount(&have);
+    if (e != cudaSuccess || have == 0) {
+        (void)cudaGetLastError();
+        return fail(H2B_ERR_CUDA, "h2b_init: no CUDA device (this library has no CPU fallback)", e);
+    }
+    for (int i = 0; i < count; i++) {
+        if (devices[i] < 0 || devices[i] >= have) return fail(H2B_ERR_ARG, "h2b_init: bad device index");
+        for (int j = 0; j < i; j++)
+            if (devices[j] == devices[i]) return fail(H2B_ERR_ARG, "h2b_init: device listed twice");
+    }
+    const char *sm = getenv("H2B_SHARD_MIN_LOG");
+    if (sm && atoi(sm) >= 8 && atoi(sm) <= 30) g_shard_min_n = (size_t)1 << atoi(sm);
+    const char *mr = getenv("H2B_NTT_MAX_RADIX");
+    if (mr) {
+        int v = atoi(mr);
+        if (v >= 5 && v <= 10) g_ntt_max_radix = (uint32_t)v;
+    }
+    std::vector<Ctx *> made;
+    for (int i = 0; i < count; i++) {
+        Ctx *c = nullptr;
+        int rc = ctx_create(devices[i], &c);
+        if (rc != H2B_OK) {
+            for (Ctx *m : made) ctx_destroy(m);
+            return rc;
+        }
+        made.push_back(c);
+    }
+    // the partial sums of a sharded commit travel device-to-device (96 bytes each): enable direct peer access where
+    // the topology offers it (NVLink / NVSwitch on an HGX board); without it the peer copies are staged by the driver
+    for (int i = 0; i < count && count > 1; i++) {
+        cudaSetDevice(devices[i]);
+        for (int j = 0; j < count; j++) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (pe != cudaSuccess) (void)cudaGetLastError();  // already enabled (e.g. by the host framework)
+            }
+        }
+    }
+    cudaSetDevice(devices[0]);
+    g_all = made;
+    g_primary = made[0];
+    g = g_primary;
     return H2B_OK;
 }
 
+int h2b_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return init_locked(&device, 1);
+}
+int h2b_init_devices(const int *devices, int count) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return init_locked(devices, count);
+}
+int h2b_device_count(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return (int)g_all.size();
+}
+
+static void srs_free(Srs &sr);
 void h2b_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g) return;
-    cudaSetDevice(g->device);
-    cudaDeviceSynchronize();
-    for (int i = 0; i < BUF_COUNT; i++)
-        if (g->buf[i]) cudaFree(g->buf[i]);
-    for (auto &kv : g->srs) {
-        cudaFree(kv.second.d);
-        if (kv.second.table) cudaFree(kv.second.table);
-        if (kv.second.comb) cudaFree(kv.second.comb);
-    }
-    for (auto &kv : g->twiddles) cudaFree(kv.second);
-    for (auto e : g->tev0) cudaEventDestroy(e);
-    for (auto e : g->tev1) cudaEventDestroy(e);
-    for (auto e : g->chunk_events) cudaEventDestroy(e);
-    delete g->copier;
-    cudaEventDestroy(g->copy_fence);
-    cudaStreamDestroy(g->copy_stream);
-    cudaEventDestroy(g->last_done);
-    cudaStreamDestroy(g->stream);
-    delete g;
+    if (!g_primary) return;
+    for (auto &kv : g_srs)
+        for (Srs &pt : kv.second.parts) srs_free(pt);
+    g_srs.clear();
+    for (Ctx *c : g_all) ctx_destroy(c);
+    g_all.clear();
+    g_primary = nullptr;
     g = nullptr;
 }
 
@@ -1149,50 +1298,63 @@ int h2b_set_msm_window(uint32_t c) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
     if (c != 0 && (c < 2 || c > 22)) return fail(H2B_ERR_ARG, "msm window must be 0 or in [2, 22]");
-    g->msm_window = c;
+    for (Ctx *x : g_all) x->msm_window = c;
     return H2B_OK;
 }
 int h2b_set_srs_precompute(int enabled, uint32_t c) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
     if (c != 0 && (c < 2 || c > 24)) return fail(H2B_ERR_ARG, "srs window must be 0 or in [2, 24]");
-    g->srs_precompute = enabled;  // 0: none, 1: automatic (bucket-free table up to 2^14 points), 2: window table only
-    g->srs_window = c;
+    for (Ctx *x : g_all) {
+        x->srs_precompute = enabled;  // 0: none, 1: automatic (bucket-free table up to 2^14 points), 2: window table only
+        x->srs_window = c;
+    }
     return H2B_OK;
 }
 int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
     if (chunks < 1 || chunks > 64) return fail(H2B_ERR_ARG, "e2e chunks must be in [1, 64]");
-    g->e2e_chunks = chunks;
-    g->e2e_min_n = min_n;
+    for (Ctx *x : g_all) {
+        x->e2e_chunks = chunks;
+        x->e2e_min_n = min_n;
+    }
     return H2B_OK;
 }
 uint64_t h2b_kernel_launches(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    return g ? g->launches : 0;
+    uint64_t sum = 0;
+    for (Ctx *x : g_all) sum += x->launches;
+    return sum;
 }
 int h2b_set_kernel_timing(int enabled) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    g->timing = enabled;
-    g->tev_used = 0;
+    for (Ctx *x : g_all) {
+        x->timing = enabled;
+        x->tev_used = 0;
+    }
     return H2B_OK;
 }
 int h2b_kernel_time_collect(double *total_ms, uint32_t *calls) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    CU(cudaSetDevice(g->device));
     double sum = 0;
-    for (uint32_t i = 0; i < g->tev_used; i++) {
-        CU(cudaEventSynchronize(g->tev1[i]));
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, g->tev0[i], g->tev1[i]));
-        sum += ms;
+    uint32_t n = 0;
+    for (Ctx *x : g_all) {  // every device's pairs: a sharded commit contributes one accumulation launch per device
+        CU(cudaSetDevice(x->device));
+        for (uint32_t i = 0; i < x->tev_used; i++) {
+            CU(cudaEventSynchronize(x->tev1[i]));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, x->tev0[i], x->tev1[i]));
+            sum += ms;
+        }
+        n += x->tev_used;
+        x->tev_used = 0;
     }
+    CU(cudaSetDevice(g->device));
     if (total_ms) *total_ms = sum;
-    if (calls) *calls = g->tev_used;
-    g->tev_used = 0;
+    if (calls) *calls = n;
     return H2B_OK;
 }
 
@@ -1203,30 +1365,12 @@ int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out
     if (!d_out || (n && (!d_coeffs || !d_bases))) return fail(H2B_ERR_ARG, "msm: null pointer");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, msm_run((const Fe *)d_coeffs, (const Affine *)d_bases, n, (Projective *)d_out, s));
+    Scope sc;
+    TRY(sc.begin(s));
+    return msm_run((const Fe *)d_coeffs, (const Affine *)d_bases, n, (Projective *)d_out, s);
 }
 
 int commit_many_device(const Srs &sr, const Fe *d_scalars, size_t n, size_t m, Projective *d_out, cudaStream_t s);
-int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out, void *stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(ensure_ctx());
-    auto it = g->srs.find(srs);
-    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit: unknown SRS handle");
-    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit: bases.len() < size");  // commitment.rs:319/:363
-    if (!d_out || (n && !d_coeffs)) return fail(H2B_ERR_ARG, "commit: null pointer");
-    CU(cudaSetDevice(g->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    if (n == 0) return leave(s, msm_identity_out((Projective *)d_out, s));
-    const Srs &sr = it->second;
-    if (sr.comb) return leave(s, commit_many_device(sr, (const Fe *)d_coeffs, n, 1, (Projective *)d_out, s));
-    MsmRun run;
-    int rc = msm_begin(n, &run, s, &sr);
-    if (rc == H2B_OK) rc = msm_chunk(run, (const Fe *)d_coeffs, sr.table ? sr.table : sr.d, n, s, 0);
-    if (rc == H2B_OK) rc = msm_finish(run, (Projective *)d_out, s);
-    return leave(s, rc);
-}
 
 // Bucket-free commit of `cols` columns against a small SRS (msm_comb.cuh): digits -> table indices, slice sums,
 // a binary tree over the slice sums.
@@ -1319,45 +1463,227 @@ int commit_many_device(const Srs &sr, const Fe *d_scalars, size_t n, size_t m, P
     return H2B_OK;
 }
 
+// ---- several devices ---------------------------------------------------------------------------------------
+// fn(i) runs for devs[i] on that context's worker thread with `g` bound to it (so every internal function above
+// works unchanged on any device) while the API thread, which holds g_mu, waits.  First error wins.
+int on_devices(const std::vector<int> &devs, const std::function<int(size_t)> &fn) {
+    Ctx *self = g;
+    std::vector<int> rcs(devs.size(), H2B_OK);
+    std::vector<std::string> errs(devs.size());
+    auto body = [&](size_t i) {
+        g = g_all[devs[i]];
+        if (cudaSetDevice(g->device) != cudaSuccess) {
+            rcs[i] = H2B_ERR_CUDA;
+            errs[i] = "cudaSetDevice";
+            return;
+        }
+        rcs[i] = fn(i);
+        if (rcs[i] != H2B_OK) errs[i] = g_err;
+    };
+    if (devs.size() == 1 && g_all[devs[0]] == self) {
+        body(0);
+    } else {
+        for (size_t i = 0; i < devs.size(); i++) g_all[devs[i]]->worker.submit([&body, i] { body(i); });
+        for (size_t i = 0; i < devs.size(); i++) g_all[devs[i]]->worker.wait();
+    }
+    g = self;
+    cudaSetDevice(self->device);
+    for (size_t i = 0; i < devs.size(); i++)
+        if (rcs[i] != H2B_OK) {
+            g_err = errs[i];
+            return rcs[i];
+        }
+    return H2B_OK;
+}
+
+// out[q] = sum over p of pts[p * cols + q]: the fold of per-device partial commitments, column by column
+// (arithmetic.rs:~176, `results.iter().fold(identity, |a, b| a + b)` with a device in place of a thread).
+__global__ void g1_fold_cols_kernel(const Projective *__restrict__ pts, uint32_t parts, uint32_t cols, Projective *__restrict__ out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= cols) return;
+    XYZZ acc = xyzz_identity();
+    for (uint32_t p = 0; p < parts; p++) {
+        Projective v;
+        v.x = load_fe(&pts[(size_t)p * cols + q].x);
+        v.y = load_fe(&pts[(size_t)p * cols + q].y);
+        v.z = load_fe(&pts[(size_t)p * cols + q].z);
+        XYZZ t = projective_to_xyzz(v);
+        xyzz_add(acc, t);
+    }
+    const Projective r = xyzz_to_projective(acc);
+    store_fe(&out[q].x, r.x);
+    store_fe(&out[q].y, r.y);
+    store_fe(&out[q].z, r.z);
+}
+
+// The polynomials of a commit: host columns, or columns one after the other in the PRIMARY device's memory.
+struct ColumnSrc {
+    const uint64_t *const *host = nullptr;
+    const Fe *dev = nullptr;
+};
+
+// One device's share of a commit: columns [q0, q0 + m) restricted to points [off, off + n) of polynomials of
+// length `n_poly`, against `part`; the m results land in d_out (device memory of the calling context).
+int commit_part(const Srs &part, const ColumnSrc &src, size_t n_poly, size_t off, size_t n, size_t q0, size_t m,
+                Projective *d_out, cudaStream_t s, int src_device) {
+    if (src.host && m == 1 && !part.comb) {  // large single commits: the copy is pipelined against the accumulation
+        (void)s;
+        return msm_run_pipelined(src.host[q0] + 4 * off, nullptr, &part, n, d_out);
+    }
+    Fe *ds;
+    TRY(get_buf(BUF_SCALARS, m * n * sizeof(Fe), (void **)&ds));
+    if (src.host) {
+        std::vector<HostCopier::Seg> segs;
+        for (size_t q = 0; q < m; q++)
+            segs.push_back({ds + q * n, const_cast<uint64_t *>(src.host[q0 + q] + 4 * off), n * sizeof(Fe)});
+        cudaError_t ce = g->copier->h2d(segs, s);
+        if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "host-to-device copy", ce);
+    } else if (src_device == g->device && (m == 1 || (off == 0 && n == n_poly))) {
+        ds = const_cast<Fe *>(src.dev + q0 * n_poly + off);  // already here, contiguous
+    } else {
+        for (size_t q = 0; q < m; q++) {
+            const Fe *from = src.dev + (q0 + q) * n_poly + off;
+            if (src_device == g->device) CU(cudaMemcpyAsync(ds + q * n, from, n * sizeof(Fe), cudaMemcpyDeviceToDevice, s));
+            else CU(cudaMemcpyPeerAsync(ds + q * n, g->device, from, src_device, n * sizeof(Fe), s));
+        }
+    }
+    if (m == 1 && !part.comb) {
+        MsmRun run;
+        TRY(msm_begin(n, &run, s, &part));
+        TRY(msm_chunk(run, ds, part.table ? part.table : part.d, n, s, 0));
+        return msm_finish(run, d_out, s);
+    }
+    return commit_many_device(part, ds, n, m, d_out, s);
+}
+
+// ParamsKZG::commit / commit_lagrange of m polynomials of n scalars against a registered set.  Results go to the
+// host (h_out, m x 12 u64) or to the primary device (d_out).  `s` is the stream of the primary device the call is
+// ordered on (the caller's for the _dev entry points).
+int commit_set(const SrsSet &set, const ColumnSrc &src, size_t n, size_t m, uint64_t *h_out, Projective *d_out, cudaStream_t s) {
+    if (m == 0) return H2B_OK;
+    Ctx *prim = g;
+    Scope sc;
+    TRY(sc.begin(s));
+    Projective *dres = d_out;
+    if (!dres) TRY(get_buf(BUF_OUT, m * sizeof(Projective), (void **)&dres));
+    if (n == 0) {
+        for (size_t q = 0; q < m; q++) TRY(msm_identity_out(dres + q, s));
+        if (h_out) TRY(copy_out(h_out, dres, m * sizeof(Projective), s));
+        return H2B_OK;
+    }
+    const size_t nparts = set.parts.size();
+    const bool deal = nparts > 1 && set.replicated && src.host && m >= 2;
+    const bool shard = nparts > 1 && !set.replicated;
+    if (!deal && !shard) {  // one device does it all
+        TRY(commit_part(set.parts[0], src, n, 0, n, 0, m, dres, s, prim->device));
+        if (h_out) TRY(copy_out(h_out, dres, m * sizeof(Projective), s));
+        return H2B_OK;
+    }
+    // the work list: (part, columns [q0, q0 + mq), points [off, off + np))
+    struct Job { size_t part, q0, mq, off, np; };
+    std::vector<Job> jobs;
+    if (deal) {  // whole columns, contiguous blocks per device
+        const size_t use = std::min(nparts, m);
+        for (size_t i = 0, q0 = 0; i < use; i++) {
+            const size_t mq = m / use + (i < m % use ? 1 : 0);
+            jobs.push_back({i, q0, mq, 0, n});
+            q0 += mq;
+        }
+    } else {
+        for (size_t i = 0; i < nparts; i++) {
+            const Srs &pt = set.parts[i];
+            if (pt.off >= n) break;
+            jobs.push_back({i, 0, m, pt.off, std::min(pt.n, n - pt.off)});
+        }
+    }
+    // partial results of job j arrive at gather + j * m (sharded) / straight at their columns (dealt)
+    Projective *gather = dres;
+    if (shard) TRY(get_buf(BUF_GATHER, jobs.size() * m * sizeof(Projective), (void **)&gather));
+    cudaEvent_t ready = nullptr;
+    if (src.dev) {  // the producers of the device columns run on `s`: the other devices' peer copies wait for them
+        ready = prim->copy_fence;
+        CU(cudaEventRecord(ready, s));
+    }
+    std::vector<int> devs;
+    for (const Job &j : jobs) devs.push_back(set.parts[j.part].dev);
+    TRY(on_devices(devs, [&](size_t i) -> int {
+        const Job &j = jobs[i];
+        const Srs &pt = set.parts[j.part];
+        const bool here = g == prim;
+        cudaStream_t ws = here ? s : g->stream;
+        Scope wsc;
+        if (!here) TRY(wsc.begin(ws));
+        if (ready && !here) CU(cudaStreamWaitEvent(ws, ready, 0));
+        Projective *target = gather + (shard ? i * m : j.q0);
+        Projective *local = target;
+        if (!here) TRY(get_buf(BUF_OUT, j.mq * sizeof(Projective), (void **)&local));
+        TRY(commit_part(pt, src, n, j.off, j.np, j.q0, j.mq, local, ws, prim->device));
+        if (!here) CU(cudaMemcpyPeerAsync(target, prim->device, local, g->device, j.mq * sizeof(Projective), ws));
+        if (!here) CU(cudaStreamSynchronize(ws));  // the primary folds what has arrived
+        return H2B_OK;
+    }));
+    if (shard) {
+        g1_fold_cols_kernel<<<(uint32_t)((m + 31) / 32), 32, 0, s>>>(gather, (uint32_t)jobs.size(), (uint32_t)m, dres);
+        LAUNCHED();
+    }
+    if (h_out) TRY(copy_out(h_out, dres, m * sizeof(Projective), s));
+    return H2B_OK;
+}
+
+int find_set(uint64_t handle, size_t n, const char *what, const SrsSet **out) {
+    auto it = g_srs.find(handle);
+    if (it == g_srs.end()) return fail(H2B_ERR_STATE, "unknown SRS handle");
+    if (n > it->second.n) return fail(H2B_ERR_ARG, what);  // commitment.rs:319/:363 assert!(bases.len() >= size)
+    *out = &it->second;
+    return H2B_OK;
+}
+
+int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    const SrsSet *set;
+    TRY(find_set(srs, n, "commit: bases.len() < size", &set));
+    if (!d_out || (n && !d_coeffs)) return fail(H2B_ERR_ARG, "commit: null pointer");
+    CU(cudaSetDevice(g->device));
+    ColumnSrc src;
+    src.dev = (const Fe *)d_coeffs;
+    return commit_set(*set, src, n, 1, nullptr, (Projective *)d_out, stream ? (cudaStream_t)stream : g->stream);
+}
 int h2b_dev_commit_many(uint64_t srs, const void *d_coeffs, size_t n, size_t m, void *d_out, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    auto it = g->srs.find(srs);
-    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit_many: unknown SRS handle");
-    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit_many: bases.len() < size");  // commitment.rs:319/:363
+    const SrsSet *set;
+    TRY(find_set(srs, n, "commit_many: bases.len() < size", &set));
     if (m && (!d_out || (n && !d_coeffs))) return fail(H2B_ERR_ARG, "commit_many: null pointer");
     CU(cudaSetDevice(g->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, commit_many_device(it->second, (const Fe *)d_coeffs, n, m, (Projective *)d_out, s));
+    ColumnSrc src;
+    src.dev = (const Fe *)d_coeffs;
+    return commit_set(*set, src, n, m, nullptr, (Projective *)d_out, stream ? (cudaStream_t)stream : g->stream);
 }
-
 int h2b_commit_many(uint64_t srs, const uint64_t *const *polys, size_t n, size_t m, uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    auto it = g->srs.find(srs);
-    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit_many: unknown SRS handle");
-    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit_many: bases.len() < size");  // commitment.rs:319/:363
+    const SrsSet *set;
+    TRY(find_set(srs, n, "commit_many: bases.len() < size", &set));
     if (m == 0) return H2B_OK;
     if (!out || !polys) return fail(H2B_ERR_ARG, "commit_many: null pointer");
     for (size_t q = 0; q < m && n; q++)
         if (!polys[q]) return fail(H2B_ERR_ARG, "commit_many: null column");
     CU(cudaSetDevice(g->device));
-    cudaStream_t s = g->stream;
-    TRY(enter(s));
-    Fe *ds = nullptr;
-    void *dout;
-    if (n) TRY(get_buf(BUF_SCALARS, m * n * sizeof(Fe), (void **)&ds));
-    TRY(get_buf(BUF_OUT, m * sizeof(Projective), &dout));
-    if (n) {
-        std::vector<HostCopier::Seg> segs;
-        for (size_t q = 0; q < m; q++) segs.push_back({ds + q * n, const_cast<uint64_t *>(polys[q]), n * sizeof(Fe)});
-        cudaError_t ce = g->copier->h2d(segs, s);
-        if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "host-to-device copy", ce);
-    }
-    TRY(commit_many_device(it->second, ds, n, m, (Projective *)dout, s));
-    TRY(copy_out(out, dout, m * sizeof(Projective), s));
-    return leave(s, H2B_OK);
+    ColumnSrc src;
+    src.host = polys;
+    return commit_set(*set, src, n, m, out, nullptr, g->stream);
+}
+int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    const SrsSet *set;
+    TRY(find_set(srs, n, "commit: bases.len() < size", &set));
+    if (!out || (n && !scalars)) return fail(H2B_ERR_ARG, "commit: null pointer");
+    CU(cudaSetDevice(g->device));
+    ColumnSrc src;
+    src.host = &scalars;
+    return commit_set(*set, src, n, 1, out, nullptr, g->stream);
 }
 
 int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out[12]) {
@@ -1365,15 +1691,163 @@ int h2b_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     TRY(ensure_ctx());
     if (!out || (n && (!coeffs || !bases))) return fail(H2B_ERR_ARG, "best_multiexp: null pointer");
     CU(cudaSetDevice(g->device));
-    TRY(enter(g->stream));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     void *dout;
     TRY(get_buf(BUF_OUT, 96, &dout));
     TRY(msm_run_pipelined(coeffs, bases, nullptr, n, (Projective *)dout));
     TRY(copy_out(out, dout, 96, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 
-static int srs_register_locked(const void *bases, size_t n, uint64_t *handle, bool on_device = false);
+static void srs_free(Srs &sr) {
+    cudaSetDevice(g_all[sr.dev]->device);
+    cudaDeviceSynchronize();  // commits on caller streams may still read the bases / tables
+    if (sr.d) cudaFree(sr.d);
+    if (sr.table) cudaFree(sr.table);
+    if (sr.comb) cudaFree(sr.comb);
+    sr.d = sr.table = sr.comb = nullptr;
+}
+
+// Builds one share on the calling thread's context: points [off, off + n) of the source array (host memory, or
+// memory of device `src_device`) go to HBM, then the static-base precomputation for a share of that length.
+static int srs_part_create(const void *src, bool src_on_device, int src_device, size_t off, size_t n, Srs *out) {
+    Srs s;
+    s.off = off;
+    s.n = n;
+    Scope sc;
+    TRY(sc.begin(g->stream));
+    cudaError_t e = cudaMalloc(&s.d, n * sizeof(Affine));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(H2B_ERR_OOM, "cudaMalloc(srs)", e);
+    }
+    const Affine *from = (const Affine *)src + off;
+    if (!src_on_device) e = g->copier->h2d(s.d, from, n * sizeof(Affine), g->stream);
+    else if (src_device == g->device) e = cudaMemcpyAsync(s.d, from, n * sizeof(Affine), cudaMemcpyDeviceToDevice, g->stream);
+    else e = cudaMemcpyPeerAsync(s.d, g->device, from, src_device, n * sizeof(Affine), g->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+    if (e != cudaSuccess) {
+        cudaFree(s.d);
+        return fail(H2B_ERR_CUDA, "cudaMemcpy(srs)", e);
+    }
+    // Static bases: precompute 2^(c*w) * P_i once so that every window of a commit feeds ONE bucket set
+    // (fewer, wider windows; no Horner).  Skipped when the table would not fit comfortably.
+    if (g->srs_precompute == 1 && g->srs_window == 0 && n <= g->comb_max_n) {
+        // small SRS (the reference's circuits: k <= 14): bucket-free table of all window multiples
+        const uint32_t c = g->comb_c, W = msm_windows_for(c), M = 1u << (c - 1);
+        const size_t count = (size_t)W * M * n + 1, bytes = count * sizeof(Affine);
+        const size_t scratch_bytes = (size_t)(M - 1) * n * W * sizeof(Fe);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes + scratch_bytes <= free_b / 3 && count < (1u << 31)) {
+            Fe *scratch = nullptr;
+            e = cudaMalloc(&s.comb, bytes);
+            if (e == cudaSuccess && (e = cudaMalloc(&scratch, scratch_bytes ? scratch_bytes : 16)) != cudaSuccess) {
+                cudaFree(s.comb);
+                s.comb = nullptr;
+            }
+            if (e == cudaSuccess) {
+                e = cudaMemsetAsync(s.comb + (count - 1), 0, sizeof(Affine), g->stream);  // the identity entry
+                msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, (size_t)M * n, s.comb);
+                msm_comb_multiples_kernel<<<(uint32_t)((n * W + 127) / 128), 128, 0, g->stream>>>((uint32_t)n, c, W, s.comb, scratch);
+                g->launches += 2;
+                if (e == cudaSuccess) e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+                cudaFree(scratch);
+                if (e != cudaSuccess) {
+                    cudaFree(s.comb);
+                    cudaFree(s.d);
+                    return fail(H2B_ERR_CUDA, "srs comb table", e);
+                }
+                s.comb_c = c;
+                s.comb_w = W;
+            } else {
+                (void)cudaGetLastError();
+                s.comb = nullptr;
+            }
+        }
+    }
+    if (!s.comb && g->srs_precompute && n >= 2) {
+        uint32_t c = srs_window_for(n), W = msm_windows_for(c);
+        size_t bytes = (size_t)W * n * sizeof(Affine), free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes <= free_b / 3 && (size_t)W * n < (1u << 31)) {
+            e = cudaMalloc(&s.table, bytes);
+            if (e == cudaSuccess) {
+                msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, n, s.table);
+                g->launches++;
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+                if (e != cudaSuccess) {
+                    cudaFree(s.table);
+                    cudaFree(s.d);
+                    return fail(H2B_ERR_CUDA, "srs precompute", e);
+                }
+                s.c = c;
+                s.windows = W;
+            } else {
+                (void)cudaGetLastError();
+                s.table = nullptr;
+            }
+        }
+    }
+    *out = s;
+    return H2B_OK;
+}
+
+// Registers a base array on every device of the library: replicated below g_shard_min_n points, sharded by
+// contiguous point range (each device precomputes the table of its own share) from there up.
+static int srs_register_locked(const void *bases, size_t n, uint64_t *handle, bool on_device = false) {
+    TRY(ensure_ctx());
+    if (!bases || !handle || n == 0) return fail(H2B_ERR_ARG, "srs_register: bad argument");
+    CU(cudaSetDevice(g->device));
+    if (on_device) CU(cudaDeviceSynchronize());  // the caller's producer of d_bases may run on any stream
+    const size_t D = g_all.size();
+    SrsSet set;
+    set.n = n;
+    set.replicated = D > 1 && n < g_shard_min_n;
+    const size_t nparts = D;
+    set.parts.resize(nparts);
+    std::vector<int> devs;
+    std::vector<size_t> lo(nparts), cnt(nparts);
+    for (size_t i = 0; i < nparts; i++) {
+        devs.push_back((int)i);
+        if (D == 1 || set.replicated) {
+            lo[i] = 0;
+            cnt[i] = n;
+        } else {  // equal ranges, boundaries on multiples of 256 points
+            const size_t per = ((n + D - 1) / D + 255) & ~(size_t)255;
+            lo[i] = std::min(n, i * per);
+            cnt[i] = std::min(n, (i + 1) * per) - lo[i];
+        }
+    }
+    while (!cnt.empty() && cnt.back() == 0) {  // fewer shares than devices (tiny tail)
+        cnt.pop_back();
+        lo.pop_back();
+        devs.pop_back();
+        set.parts.pop_back();
+    }
+    const int src_device = g->device;
+    int rc = on_devices(devs, [&](size_t i) -> int {
+        TRY(srs_part_create(bases, on_device, src_device, lo[i], cnt[i], &set.parts[i]));
+        set.parts[i].dev = devs[i];
+        return H2B_OK;
+    });
+    if (rc != H2B_OK) {
+        std::string keep = g_err;
+        for (Srs &pt : set.parts) {
+            pt.dev = pt.dev < (int)D ? pt.dev : 0;
+            srs_free(pt);
+        }
+        cudaSetDevice(g->device);
+        g_err = keep;
+        return rc;
+    }
+    *handle = g_next_handle++;
+    g_srs[*handle] = set;
+    return H2B_OK;
+}
 int h2b_srs_register(const uint64_t *bases, size_t n, uint64_t *handle) {
     std::lock_guard<std::mutex> lk(g_mu);
     return srs_register_locked(bases, n, handle);
@@ -1400,13 +1874,14 @@ int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k_out, uint64_t 
     TRY(srs_register_locked(bytes + 4, n, &hg));
     int rc = srs_register_locked(bytes + 4 + 64 * n, n, &hl);
     if (rc != H2B_OK) {
-        auto it = g->srs.find(hg);
-        if (it != g->srs.end()) {
-            cudaFree(it->second.d);
-            if (it->second.table) cudaFree(it->second.table);
-            if (it->second.comb) cudaFree(it->second.comb);
-            g->srs.erase(it);
+        std::string keep = g_err;
+        auto it = g_srs.find(hg);
+        if (it != g_srs.end()) {
+            for (Srs &pt : it->second.parts) srs_free(pt);
+            g_srs.erase(it);
         }
+        cudaSetDevice(g->device);
+        g_err = keep;
         return rc;
     }
     if (k_out) *k_out = k;
@@ -1414,113 +1889,32 @@ int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k_out, uint64_t 
     *g_lagrange_handle = hl;
     return H2B_OK;
 }
-static int srs_register_locked(const void *bases, size_t n, uint64_t *handle, bool on_device) {
-    TRY(ensure_ctx());
-    if (!bases || !handle || n == 0) return fail(H2B_ERR_ARG, "srs_register: bad argument");
-    CU(cudaSetDevice(g->device));
-    Srs s;
-    cudaError_t e = cudaMalloc(&s.d, n * sizeof(Affine));
-    if (e != cudaSuccess) {
-        (void)cudaGetLastError();
-        return fail(H2B_ERR_OOM, "cudaMalloc(srs)", e);
-    }
-    s.n = n;
-    if (on_device) {
-        e = cudaDeviceSynchronize();  // the caller's producer of d_bases may run on any stream
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s.d, bases, n * sizeof(Affine), cudaMemcpyDeviceToDevice, g->stream);
-    } else {
-        e = g->copier->h2d(s.d, bases, n * sizeof(Affine), g->stream);
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
-    if (e != cudaSuccess) {
-        cudaFree(s.d);
-        return fail(H2B_ERR_CUDA, "cudaMemcpy(srs)", e);
-    }
-    // Static bases: precompute 2^(c*w) * P_i once so that every window of a commit feeds ONE bucket set
-    // (fewer, wider windows; no Horner).  Skipped when the table would not fit comfortably.
-    if (g->srs_precompute == 1 && g->srs_window == 0 && n <= g->comb_max_n) {
-        // small SRS (the reference's circuits: k <= 14): bucket-free table of all window multiples
-        const uint32_t c = g->comb_c, W = msm_windows_for(c), M = 1u << (c - 1);
-        const size_t count = (size_t)W * M * n + 1, bytes = count * sizeof(Affine);
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if (bytes <= free_b / 3 && count < (1u << 31)) {
-            e = cudaMalloc(&s.comb, bytes);
-            if (e == cudaSuccess) {
-                e = cudaMemsetAsync(s.comb + (count - 1), 0, sizeof(Affine), g->stream);  // the identity entry
-                msm_comb_build_kernel<<<(uint32_t)((n * W + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, s.comb);
-                g->launches++;
-                if (e == cudaSuccess) e = cudaGetLastError();
-                if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
-                if (e != cudaSuccess) {
-                    cudaFree(s.comb);
-                    cudaFree(s.d);
-                    return fail(H2B_ERR_CUDA, "srs comb table", e);
-                }
-                s.comb_c = c;
-                s.comb_w = W;
-            } else {
-                (void)cudaGetLastError();
-                s.comb = nullptr;
-            }
-        }
-    }
-    if (!s.comb && g->srs_precompute && n >= 2) {
-        uint32_t c = srs_window_for(n), W = msm_windows_for(c);
-        size_t bytes = (size_t)W * n * sizeof(Affine), free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if (bytes <= free_b / 3 && (size_t)W * n < (1u << 31)) {
-            e = cudaMalloc(&s.table, bytes);
-            if (e == cudaSuccess) {
-                msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, s.table);
-                g->launches++;
-                e = cudaStreamSynchronize(g->stream);
-                if (e != cudaSuccess) {
-                    cudaFree(s.table);
-                    cudaFree(s.d);
-                    return fail(H2B_ERR_CUDA, "srs precompute", e);
-                }
-                s.c = c;
-                s.windows = W;
-            } else {
-                (void)cudaGetLastError();
-                s.table = nullptr;
-            }
-        }
-    }
-    *handle = g->next_handle++;
-    g->srs[*handle] = s;
-    return H2B_OK;
-}
 int h2b_srs_release(uint64_t handle) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    auto it = g->srs.find(handle);
-    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "srs_release: unknown handle");
+    auto it = g_srs.find(handle);
+    if (it == g_srs.end()) return fail(H2B_ERR_STATE, "srs_release: unknown handle");
+    for (Srs &pt : it->second.parts) srs_free(pt);
+    g_srs.erase(it);
     CU(cudaSetDevice(g->device));
-    CU(cudaStreamSynchronize(g->stream));
-    cudaFree(it->second.d);
-    if (it->second.table) cudaFree(it->second.table);
-    if (it->second.comb) cudaFree(it->second.comb);
-    g->srs.erase(it);
     return H2B_OK;
 }
 int h2b_srs_device_ptr(uint64_t srs, void **d_bases, size_t *n) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    auto it = g->srs.find(srs);
-    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "srs_device_ptr: unknown handle");
-    if (d_bases) *d_bases = it->second.d;
-    if (n) *n = it->second.n;
+    auto it = g_srs.find(srs);
+    if (it == g_srs.end()) return fail(H2B_ERR_STATE, "srs_device_ptr: unknown handle");
+    if (d_bases) *d_bases = it->second.parts[0].d;
+    if (n) *n = it->second.parts[0].n;
     return H2B_OK;
 }
 int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windows, size_t *table_bytes) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    auto it = g->srs.find(srs);
-    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "srs_info: unknown handle");
-    const Srs &sr = it->second;
-    if (n) *n = sr.n;
+    auto it = g_srs.find(srs);
+    if (it == g_srs.end()) return fail(H2B_ERR_STATE, "srs_info: unknown handle");
+    const Srs &sr = it->second.parts[0];
+    if (n) *n = it->second.n;
     if (window_bits) *window_bits = sr.comb ? sr.comb_c : (sr.table ? sr.c : 0);
     if (windows) *windows = sr.comb ? sr.comb_w : (sr.table ? sr.windows : 0);
     if (table_bytes)
@@ -1528,27 +1922,16 @@ int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windo
                                : (sr.table ? (size_t)sr.windows * sr.n * sizeof(Affine) : 0);
     return H2B_OK;
 }
-int h2b_commit(uint64_t srs, const uint64_t *scalars, size_t n, uint64_t out[12]) {
+int h2b_srs_layout(uint64_t srs, uint32_t *parts, uint32_t *replicated, size_t *part_n /* parts entries, may be null */) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    auto it = g->srs.find(srs);
-    if (it == g->srs.end()) return fail(H2B_ERR_STATE, "commit: unknown SRS handle");
-    if (n > it->second.n) return fail(H2B_ERR_ARG, "commit: bases.len() < size");  // commitment.rs:319/:363
-    if (!out || (n && !scalars)) return fail(H2B_ERR_ARG, "commit: null pointer");
-    CU(cudaSetDevice(g->device));
-    TRY(enter(g->stream));
-    void *dout;
-    TRY(get_buf(BUF_OUT, 96, &dout));
-    if (it->second.comb && n) {
-        Fe *ds;
-        TRY(get_buf(BUF_SCALARS, n * sizeof(Fe), (void **)&ds));
-        TRY(copy_in(ds, scalars, n * sizeof(Fe), g->stream));
-        TRY(commit_many_device(it->second, ds, n, 1, (Projective *)dout, g->stream));
-    } else {
-        TRY(msm_run_pipelined(scalars, nullptr, &it->second, n, (Projective *)dout));
-    }
-    TRY(copy_out(out, dout, 96, g->stream));
-    return leave(g->stream, H2B_OK);
+    auto it = g_srs.find(srs);
+    if (it == g_srs.end()) return fail(H2B_ERR_STATE, "srs_layout: unknown handle");
+    if (part_n)
+        for (size_t i = 0; i < it->second.parts.size(); i++) part_n[i] = it->second.parts[i].n;
+    if (parts) *parts = (uint32_t)it->second.parts.size();
+    if (replicated) *replicated = it->second.replicated ? 1u : 0u;
+    return H2B_OK;
 }
 
 int h2b_dev_g1_fold(const void *d_points, size_t count, void *d_out, void *stream) {
@@ -1557,10 +1940,11 @@ int h2b_dev_g1_fold(const void *d_points, size_t count, void *d_out, void *strea
     if (!d_out || (count && !d_points)) return fail(H2B_ERR_ARG, "g1_fold: null pointer");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
+    Scope sc;
+    TRY(sc.begin(s));
     g1_fold_kernel<<<1, 32, 0, s>>>((const Projective *)d_points, (uint32_t)count, (Projective *)d_out);
     LAUNCHED();
-    return leave(s, H2B_OK);
+    return H2B_OK;
 }
 int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[8], void *d_out, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1570,13 +1954,14 @@ int h2b_dev_fixed_base_mul(const void *d_scalars, size_t n, const uint64_t base[
     if (n == 0) return H2B_OK;
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
+    Scope sc;
+    TRY(sc.begin(s));
     Affine b;
     memcpy(&b, base, 64);
     g1_fixed_base_mul_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>((const Fe *)d_scalars, (uint32_t)n, b,
                                                                          (Affine *)d_out);
     LAUNCHED();
-    return leave(s, H2B_OK);
+    return H2B_OK;
 }
 // ---- evaluate_h
 static bool evalh_source_ok(uint64_t src, const h2b_eval_h *a) {
@@ -1646,7 +2031,8 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
     }
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
+    Scope sc;
+    TRY(sc.begin(s));
     const uint32_t size = 1u << d->extended_k;
     // one staging blob: pointer tables, scalars, graph
     std::vector<uint64_t> blob;
@@ -1701,7 +2087,7 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
         evalh_lookup_kernel<<<blocks, 128, 0, s>>>(eg, el, (Fe *)d_values);
         LAUNCHED();
         CU(cudaStreamSynchronize(s));
-        return leave(s, H2B_OK);
+        return H2B_OK;
     }
     evalh_gates_kernel<<<blocks, 128, 0, s>>>(eg, (Fe *)d_values);
     LAUNCHED();
@@ -1733,7 +2119,7 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
     // the staging blob lives on this frame: the copy above has consumed it once the stream reaches the kernels;
     // wait so that a pageable-source copy cannot outlive the vector
     CU(cudaStreamSynchronize(s));
-    return leave(s, H2B_OK);
+    return H2B_OK;
 }
 
 int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out) {
@@ -1743,7 +2129,8 @@ int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out) {
     if (k > 26) return fail(H2B_ERR_ARG, "g_to_lagrange: k > 26");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = g->stream;
-    TRY(enter(s));
+    Scope sc;
+    TRY(sc.begin(s));
     const size_t n = (size_t)1 << k;
     h2b_domain d;
     TRY(domain_build(3, k, &d));  // omega_inv and 1/2^k do not depend on j
@@ -1767,7 +2154,7 @@ int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out) {
     ec_ntt_finish_kernel<<<blocks, 128, 0, s>>>(work, (uint32_t)n, scale, dout);
     LAUNCHED();
     TRY(copy_out(out, dout, n * sizeof(Affine), s));
-    return leave(s, H2B_OK);
+    return H2B_OK;
 }
 int h2b_g1_to_bytes(const uint64_t *points, size_t m, uint8_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1775,26 +2162,30 @@ int h2b_g1_to_bytes(const uint64_t *points, size_t m, uint8_t *out) {
     if (m == 0) return H2B_OK;
     if (!points || !out) return fail(H2B_ERR_ARG, "g1_to_bytes: null pointer");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     void *dp = nullptr, *dout;
     TRY(stage_in(BUF_TEST_A, points, m * 96, &dp));
     TRY(get_buf(BUF_TEST_O, m * 32, &dout));
     g1_to_bytes_kernel<<<(uint32_t)((m + 63) / 64), 64, 0, g->stream>>>((const Projective *)dp, (uint32_t)m, (uint32_t *)dout);
     LAUNCHED();
     TRY(copy_out(out, dout, m * 32, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 int h2b_g1_fold(const uint64_t *points, size_t count, uint64_t out[12]) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
     if (!out || (count && !points)) return fail(H2B_ERR_ARG, "g1_fold: null pointer");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     void *dp = nullptr, *dout;
     TRY(stage_in(BUF_TEST_A, points, count * 96, &dp));
     TRY(get_buf(BUF_OUT, 96, &dout));
     g1_fold_kernel<<<1, 32, 0, g->stream>>>((const Projective *)dp, (uint32_t)count, (Projective *)dout);
     LAUNCHED();
     TRY(copy_out(out, dout, 96, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 
 // ---- NTT
@@ -1804,8 +2195,9 @@ int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *s
     if (!d_a || !omega) return fail(H2B_ERR_ARG, "best_fft: null pointer");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, ntt_run((const Fe *)d_a, (Fe *)d_a, log_n, omega, io_plain(log_n), s));
+    Scope sc;
+    TRY(sc.begin(s));
+    return ntt_run((const Fe *)d_a, (Fe *)d_a, log_n, omega, io_plain(log_n), s);
 }
 int h2b_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1813,12 +2205,14 @@ int h2b_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
     if (!a || !omega) return fail(H2B_ERR_ARG, "best_fft: null pointer");
     if (log_n > 28) return fail(H2B_ERR_ARG, "best_fft: log_n > 28");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     size_t bytes = ((size_t)1 << log_n) * 32;
     void *da;
     TRY(stage_in(BUF_NTT_A, a, bytes, &da));
     TRY(ntt_run((const Fe *)da, (Fe *)da, log_n, omega, io_plain(log_n), g->stream));
     TRY(copy_out(a, da, bytes, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 
 int h2b_domain_new(uint32_t j, uint32_t k, h2b_domain *out) {
@@ -1826,6 +2220,8 @@ int h2b_domain_new(uint32_t j, uint32_t k, h2b_domain *out) {
     TRY(ensure_ctx());
     if (!out) return fail(H2B_ERR_ARG, "domain_new: null pointer");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     return domain_build(j, k, out);
 }
 
@@ -1836,8 +2232,9 @@ int h2b_dev_lagrange_to_coeff(const h2b_domain *d, void *d_a, void *stream) {
     if (!d_a) return fail(H2B_ERR_ARG, "lagrange_to_coeff: null pointer");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, dev_lagrange_to_coeff(d, (Fe *)d_a, s));
+    Scope sc;
+    TRY(sc.begin(s));
+    return dev_lagrange_to_coeff(d, (Fe *)d_a, s);
 }
 int h2b_lagrange_to_coeff(const h2b_domain *d, uint64_t *a) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1845,12 +2242,14 @@ int h2b_lagrange_to_coeff(const h2b_domain *d, uint64_t *a) {
     TRY(check_domain(d));
     if (!a) return fail(H2B_ERR_ARG, "lagrange_to_coeff: null pointer");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     size_t bytes = ((size_t)1 << d->k) * 32;
     void *da;
     TRY(stage_in(BUF_NTT_A, a, bytes, &da));
     TRY(dev_lagrange_to_coeff(d, (Fe *)da, g->stream));
     TRY(copy_out(a, da, bytes, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 int h2b_dev_coeff_to_extended(const h2b_domain *d, const void *d_in, void *d_out, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1859,8 +2258,9 @@ int h2b_dev_coeff_to_extended(const h2b_domain *d, const void *d_in, void *d_out
     if (!d_in || !d_out) return fail(H2B_ERR_ARG, "coeff_to_extended: null pointer");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, dev_coeff_to_extended(d, (const Fe *)d_in, (Fe *)d_out, s));
+    Scope sc;
+    TRY(sc.begin(s));
+    return dev_coeff_to_extended(d, (const Fe *)d_in, (Fe *)d_out, s);
 }
 int h2b_coeff_to_extended(const h2b_domain *d, const uint64_t *in, uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1868,31 +2268,23 @@ int h2b_coeff_to_extended(const h2b_domain *d, const uint64_t *in, uint64_t *out
     TRY(check_domain(d));
     if (!in || !out) return fail(H2B_ERR_ARG, "coeff_to_extended: null pointer");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     size_t in_bytes = ((size_t)1 << d->k) * 32, out_bytes = ((size_t)1 << d->extended_k) * 32;
     void *din, *dout;
     TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din));
     TRY(get_buf(BUF_NTT_A, out_bytes, &dout));
     TRY(dev_coeff_to_extended(d, (const Fe *)din, (Fe *)dout, g->stream));
     TRY(copy_out(out, dout, out_bytes, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
-// Batched column transforms (create_proof runs lagrange_to_coeff over every advice / instance / product
-// column and coeff_to_extended over every column inside evaluate_h, one call each; SURVEY.md 3.1): the
-// columns are copied in one after the other, transformed by ONE launch per pass (gridDim.y = columns),
-// and copied back.  Sub-batches keep the device staging below 1 GiB.
-int h2b_lagrange_to_coeff_many(const h2b_domain *d, uint64_t *const *cols, size_t m) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(ensure_ctx());
-    TRY(check_domain(d));
-    if (m == 0) return H2B_OK;
-    if (!cols) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: null pointer");
-    for (size_t q = 0; q < m; q++)
-        if (!cols[q]) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: null column");
-    CU(cudaSetDevice(g->device));
+// The columns [0, m) on the calling thread's context.
+static int lagrange_to_coeff_many_local(const h2b_domain *d, uint64_t *const *cols, size_t m) {
     cudaStream_t s = g->stream;
-    TRY(enter(s));
+    Scope sc;
+    TRY(sc.begin(s));
     const size_t n = (size_t)1 << d->k, bytes = n * 32;
-    size_t step = std::max<size_t>(1, std::min<size_t>(m, ((size_t)1 << 30) / bytes));
+    size_t step = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(m, 65535), ((size_t)1 << 30) / bytes));
     for (size_t q0 = 0; q0 < m; q0 += step) {
         const size_t cnt = std::min(step, m - q0);
         Fe *da;
@@ -1905,21 +2297,14 @@ int h2b_lagrange_to_coeff_many(const h2b_domain *d, uint64_t *const *cols, size_
         ce = g->copier->d2h(segs, s);
         if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "device-to-host copy", ce);
     }
-    return leave(s, H2B_OK);
+    return H2B_OK;
 }
-int h2b_coeff_to_extended_many(const h2b_domain *d, const uint64_t *const *in, uint64_t *const *out, size_t m) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(ensure_ctx());
-    TRY(check_domain(d));
-    if (m == 0) return H2B_OK;
-    if (!in || !out) return fail(H2B_ERR_ARG, "coeff_to_extended_many: null pointer");
-    for (size_t q = 0; q < m; q++)
-        if (!in[q] || !out[q]) return fail(H2B_ERR_ARG, "coeff_to_extended_many: null column");
-    CU(cudaSetDevice(g->device));
+static int coeff_to_extended_many_local(const h2b_domain *d, const uint64_t *const *in, uint64_t *const *out, size_t m) {
     cudaStream_t s = g->stream;
-    TRY(enter(s));
+    Scope sc;
+    TRY(sc.begin(s));
     const size_t n = (size_t)1 << d->k, en = (size_t)1 << d->extended_k;
-    size_t step = std::max<size_t>(1, std::min<size_t>(m, ((size_t)1 << 30) / (en * 32)));
+    size_t step = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(m, 65535), ((size_t)1 << 30) / (en * 32)));
     for (size_t q0 = 0; q0 < m; q0 += step) {
         const size_t cnt = std::min(step, m - q0);
         Fe *din, *dout;
@@ -1936,7 +2321,48 @@ int h2b_coeff_to_extended_many(const h2b_domain *d, const uint64_t *const *in, u
         ce = g->copier->d2h(sout, s);
         if (ce != cudaSuccess) return fail(H2B_ERR_CUDA, "device-to-host copy", ce);
     }
-    return leave(s, H2B_OK);
+    return H2B_OK;
+}
+// Whole columns are independent transforms: with several devices they are dealt in contiguous blocks, one block per
+// device (a single NTT stays on one GPU), each over its own PCIe link.  fn(first column, count) runs per device.
+static int deal_columns(size_t m, const std::function<int(size_t, size_t)> &fn) {
+    const size_t use = std::min(g_all.size(), m);
+    if (use <= 1) return fn(0, m);
+    std::vector<int> devs;
+    std::vector<size_t> q0(use), cnt(use);
+    for (size_t i = 0, at = 0; i < use; i++) {
+        devs.push_back((int)i);
+        cnt[i] = m / use + (i < m % use ? 1 : 0);
+        q0[i] = at;
+        at += cnt[i];
+    }
+    return on_devices(devs, [&](size_t i) -> int { return fn(q0[i], cnt[i]); });
+}
+// Batched column transforms (create_proof runs lagrange_to_coeff over every advice / instance / product
+// column and coeff_to_extended over every column inside evaluate_h, one call each; SURVEY.md 3.1): the
+// columns are copied in one after the other, transformed by ONE launch per pass (gridDim.y = columns),
+// and copied back.  Sub-batches keep the device staging below 1 GiB.
+int h2b_lagrange_to_coeff_many(const h2b_domain *d, uint64_t *const *cols, size_t m) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (m == 0) return H2B_OK;
+    if (!cols) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: null pointer");
+    for (size_t q = 0; q < m; q++)
+        if (!cols[q]) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: null column");
+    CU(cudaSetDevice(g->device));
+    return deal_columns(m, [&](size_t q0, size_t cnt) { return lagrange_to_coeff_many_local(d, cols + q0, cnt); });
+}
+int h2b_coeff_to_extended_many(const h2b_domain *d, const uint64_t *const *in, uint64_t *const *out, size_t m) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    TRY(check_domain(d));
+    if (m == 0) return H2B_OK;
+    if (!in || !out) return fail(H2B_ERR_ARG, "coeff_to_extended_many: null pointer");
+    for (size_t q = 0; q < m; q++)
+        if (!in[q] || !out[q]) return fail(H2B_ERR_ARG, "coeff_to_extended_many: null column");
+    CU(cudaSetDevice(g->device));
+    return deal_columns(m, [&](size_t q0, size_t cnt) { return coeff_to_extended_many_local(d, in + q0, out + q0, cnt); });
 }
 int h2b_dev_lagrange_to_coeff_many(const h2b_domain *d, void *d_a, size_t m, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1947,8 +2373,9 @@ int h2b_dev_lagrange_to_coeff_many(const h2b_domain *d, void *d_a, size_t m, voi
     if (m > 65535) return fail(H2B_ERR_ARG, "lagrange_to_coeff_many: more than 65535 columns");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, dev_lagrange_to_coeff(d, (Fe *)d_a, s, (uint32_t)m));
+    Scope sc;
+    TRY(sc.begin(s));
+    return dev_lagrange_to_coeff(d, (Fe *)d_a, s, (uint32_t)m);
 }
 int h2b_dev_coeff_to_extended_many(const h2b_domain *d, const void *d_in, void *d_out, size_t m, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1959,8 +2386,9 @@ int h2b_dev_coeff_to_extended_many(const h2b_domain *d, const void *d_in, void *
     if (m > 65535) return fail(H2B_ERR_ARG, "coeff_to_extended_many: more than 65535 columns");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, dev_coeff_to_extended(d, (const Fe *)d_in, (Fe *)d_out, s, (uint32_t)m));
+    Scope sc;
+    TRY(sc.begin(s));
+    return dev_coeff_to_extended(d, (const Fe *)d_in, (Fe *)d_out, s, (uint32_t)m);
 }
 int h2b_dev_extended_to_coeff(const h2b_domain *d, const void *d_in, void *d_out, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1969,8 +2397,9 @@ int h2b_dev_extended_to_coeff(const h2b_domain *d, const void *d_in, void *d_out
     if (!d_in || !d_out) return fail(H2B_ERR_ARG, "extended_to_coeff: null pointer");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
-    return leave(s, dev_extended_to_coeff(d, (const Fe *)d_in, (Fe *)d_out, s));
+    Scope sc;
+    TRY(sc.begin(s));
+    return dev_extended_to_coeff(d, (const Fe *)d_in, (Fe *)d_out, s);
 }
 int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1978,6 +2407,8 @@ int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out
     TRY(check_domain(d));
     if (!in || !out) return fail(H2B_ERR_ARG, "extended_to_coeff: null pointer");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     size_t in_bytes = ((size_t)1 << d->extended_k) * 32;
     size_t out_bytes = ((size_t)(d->j - 1) << d->k) * 32;
     void *din, *dout;
@@ -1985,7 +2416,7 @@ int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out
     TRY(get_buf(BUF_NTT_OUT, out_bytes, &dout));
     TRY(dev_extended_to_coeff(d, (const Fe *)din, (Fe *)dout, g->stream));
     TRY(copy_out(out, dout, out_bytes, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1993,6 +2424,8 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
     TRY(check_domain(d));
     if (!a) return fail(H2B_ERR_ARG, "divide_by_vanishing_poly: null pointer");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     size_t n = (size_t)1 << d->extended_k;
     void *da, *dt;
     TRY(stage_in(BUF_NTT_A, a, n * 32, &da));
@@ -2001,7 +2434,7 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
                                                                                (const Fe *)dt, d->n_t);
     LAUNCHED();
     TRY(copy_out(a, da, n * 32, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 
 int h2b_dev_divide_by_vanishing_poly(const h2b_domain *d, void *d_a, void *stream) {
@@ -2011,14 +2444,15 @@ int h2b_dev_divide_by_vanishing_poly(const h2b_domain *d, void *d_a, void *strea
     if (!d_a) return fail(H2B_ERR_ARG, "divide_by_vanishing_poly: null pointer");
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    TRY(enter(s));
+    Scope sc;
+    TRY(sc.begin(s));
     const size_t n = (size_t)1 << d->extended_k;
     void *dt;
     TRY(get_buf(BUF_MISC, (size_t)d->n_t * 32, &dt));
     CU(cudaMemcpyAsync(dt, d->t_evaluations, (size_t)d->n_t * 32, cudaMemcpyHostToDevice, s));
     fr_scale_cyclic_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>((Fe *)d_a, (uint32_t)n, (const Fe *)dt, d->n_t);
     LAUNCHED();
-    return leave(s, H2B_OK);
+    return H2B_OK;
 }
 
 // ---- test hooks
@@ -2027,6 +2461,8 @@ int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, u
     TRY(ensure_ctx());
     if (!a || !out || n == 0) return fail(H2B_ERR_ARG, "test_field_op: bad argument");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     void *da, *db = nullptr, *dout;
     TRY(stage_in(BUF_TEST_A, a, n * 32, &da));
     if (b) TRY(stage_in(BUF_TEST_B, b, n * 32, &db));
@@ -2038,13 +2474,15 @@ int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, u
         test_field_kernel<Fq><<<blocks, 128, 0, g->stream>>>(op, (Fe *)da, (Fe *)db, (Fe *)dout, (uint32_t)n);
     LAUNCHED();
     TRY(copy_out(out, dout, n * 32, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
 }
 int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
     if (!a || !b || !out || n == 0) return fail(H2B_ERR_ARG, "test_g1_add_affine: bad argument");
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     void *da, *db, *dout;
     TRY(stage_in(BUF_TEST_A, a, n * 64, &da));
     TRY(stage_in(BUF_TEST_B, b, n * 64, &db));
@@ -2053,13 +2491,23 @@ int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, 
                                                                            (Projective *)dout, (uint32_t)n);
     LAUNCHED();
     TRY(copy_out(out, dout, n * 96, g->stream));
-    return leave(g->stream, H2B_OK);
+    return H2B_OK;
+}
+
+int h2b_test_set_max_entries(uint32_t log2_entries) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (log2_entries != 0 && (log2_entries < 10 || log2_entries > 31)) return fail(H2B_ERR_ARG, "max entries must be 0 or 2^10..2^31");
+    for (Ctx *x : g_all) x->max_entries = 1ull << (log2_entries ? log2_entries : 31);
+    return H2B_OK;
 }
 
 int h2b_imad_peak(double *imad_gops, double *imad_wide_gops, double *sm_mhz) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
     CU(cudaSetDevice(g->device));
+    Scope sc;
+    TRY(sc.begin(g->stream));
     void *sink;
     TRY(get_buf(BUF_MISC, 64, &sink));
     const uint32_t iters = 2000, threads = 512;

@@ -521,37 +521,65 @@ msm_batch_out_kernel(const XYZZ *__restrict__ window_sums, uint32_t cols, Projec
     store_fe(&out[q].z, j.z);
 }
 
-// table[w * n + i] = 2^(c*w) * bases[i] in affine form, w in [0, W): the one-time precomputation
-// behind the shared-bucket mode of a registered SRS (the bases of ParamsKZG are static).
+// table[w * wstride + i] = 2^(c*w) * bases[i] in affine form, w in [0, W): the one-time precomputation behind the
+// shared-bucket mode of a registered SRS (wstride = n; the bases of ParamsKZG are static) and the first column of the
+// bucket-free table of msm_comb.cuh (wstride = 2^(c-1) * n).
+// One thread per point walks the whole doubling chain in Jacobian coordinates (2M + 5S per doubling) and normalises
+// kPreGroup windows with ONE inversion (Montgomery's trick over the Z of the window boundaries): the raw X, Y
+// of a window are parked in its table slot, Z and the prefix products live in local memory, and the backward
+// sweep rewrites the slots in affine form.  (The per-window Fermat inversion this replaces was two thirds of
+// the kernel: 380 products against 20 doublings.)  Affine coordinates are unique, so the table is bit-identical.
+constexpr uint32_t kPreGroup = 16;
 __global__ void __launch_bounds__(128)
-msm_precompute_kernel(const Affine *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W,
-                      Affine *__restrict__ table) {
+msm_precompute_kernel(const Affine *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W, size_t wstride,
+                      Affine *table) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Affine p = load_affine(&bases[i]);
     store_fe(&table[i].x, p.x);
     store_fe(&table[i].y, p.y);
-    const bool is_id = affine_is_identity(p);
-    XYZZ acc = xyzz_from_affine(p);
-#pragma unroll 1
-    for (uint32_t w = 1; w < W; w++) {
-        Affine r;
-        if (is_id) {
-            r.x = Fq::zero();
-            r.y = Fq::zero();
-        } else {
-#pragma unroll 1
-            for (uint32_t d = 0; d < c; d++) acc = xyzz_dbl_ni(acc);
-            const Fe t = Fq::inv(Fq::mul(acc.zz, acc.zzz));
-            r.x = Fq::mul(Fq::mul(acc.x, t), acc.zzz);  // X / ZZ
-            r.y = Fq::mul(Fq::mul(acc.y, t), acc.zz);   // Y / ZZZ
-            acc.x = r.x;                                 // renormalise: keeps the chain exact and short
-            acc.y = r.y;
-            acc.zz = Fq::one();
-            acc.zzz = Fq::one();
+    if (affine_is_identity(p)) {
+        for (uint32_t w = 1; w < W; w++) {
+            store_fe(&table[(size_t)w * wstride + i].x, Fq::zero());
+            store_fe(&table[(size_t)w * wstride + i].y, Fq::zero());
         }
-        store_fe(&table[(size_t)w * n + i].x, r.x);
-        store_fe(&table[(size_t)w * n + i].y, r.y);
+        return;
+    }
+    Jac cur;
+    cur.x = p.x;
+    cur.y = p.y;
+    cur.z = Fq::one();
+#pragma unroll 1
+    for (uint32_t w0 = 1; w0 < W; w0 += kPreGroup) {
+        const uint32_t cnt = min(kPreGroup, W - w0);
+        Fe zs[kPreGroup], pre[kPreGroup];
+#pragma unroll 1
+        for (uint32_t t = 0; t < cnt; t++) {
+#pragma unroll 1
+            for (uint32_t d = 0; d < c; d++) jac_dbl_ni(cur);
+            Affine *slot = &table[(size_t)(w0 + t) * wstride + i];
+            store_fe(&slot->x, cur.x);
+            store_fe(&slot->y, cur.y);
+            zs[t] = cur.z;  // never zero: the group has prime order, so no doubling reaches the identity
+            pre[t] = t ? Fq::mul(pre[t - 1], cur.z) : cur.z;
+        }
+        Fe inv = Fq::inv(pre[cnt - 1]);
+#pragma unroll 1
+        for (int t = (int)cnt - 1; t >= 0; t--) {
+            const Fe zi = t ? Fq::mul(inv, pre[t - 1]) : inv;  // 1 / Z_t
+            if (t) inv = Fq::mul(inv, zs[t]);
+            const Fe zi2 = Fq::sqr(zi);
+            Affine *slot = &table[(size_t)(w0 + t) * wstride + i];
+            const Fe x = Fq::mul(load_fe(&slot->x), zi2);
+            const Fe y = Fq::mul(Fq::mul(load_fe(&slot->y), zi2), zi);
+            store_fe(&slot->x, x);
+            store_fe(&slot->y, y);
+            if (t == (int)cnt - 1) {  // the chain continues from the normalised point
+                cur.x = x;
+                cur.y = y;
+                cur.z = Fq::one();
+            }
+        }
     }
 }
 

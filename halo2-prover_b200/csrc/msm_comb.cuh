@@ -14,40 +14,73 @@
 
 namespace h2b {
 
-// One thread per (point, window): the 2^(c-1) multiples of 2^(c*w) * P_i, each normalised to affine.
+// The table is built in two launches.  msm_precompute_kernel (msm.cuh, wstride = M * n) fills the d = 1 column,
+// 2^(c*w) * P_i, with one doubling chain per point.  Then one thread per (point, window) adds the base to itself
+// M - 1 times in XYZZ coordinates and normalises ALL its multiples with one inversion: in a chain of mixed
+// additions of the same base  ZZ_(d+1) = ZZ_d * P_d^2,  ZZZ_(d+1) = ZZZ_d * P_d^3  with  P_d = x_B * ZZ_d - X_d,  so
+// ZZ_d = T_d^2 and ZZZ_d = T_d^3 for the running product T_d of the P_j, and 1 / T_d = (1 / T_(d+1)) * P_d: the raw
+// X, Y of a multiple are parked in its table slot, the P_d in a scratch array, and a backward sweep from the single
+// inverse 1 / T_M rewrites every slot as x = X / T^2, y = Y / T^3.  16 products per entry instead of ~395
+// (one Fermat inversion each).  Affine coordinates are unique, so the table is bit-identical to the former one.
+//   comb   : the table, column d = 1 already filled
+//   scratch: (M - 1) * n * W field elements, [d][t]
+static __device__ __noinline__ Fe xyzz_madd_keep_p(XYZZ &acc, const Affine &p) {
+    const Fe u2 = Fq::mul(p.x, acc.zz);
+    const Fe s2 = Fq::mul(p.y, acc.zzz);
+    const Fe pp_ = Fq::sub(u2, acc.x);
+    const Fe rr = Fq::sub(s2, acc.y);
+    const Fe pp = Fq::sqr(pp_);
+    const Fe ppp = Fq::mul(pp_, pp);
+    const Fe q = Fq::mul(acc.x, pp);
+    const Fe x3 = Fq::sub(Fq::sub(Fq::sub(Fq::sqr(rr), ppp), q), q);
+    const Fe y3 = Fq::mul2_sub(rr, Fq::sub(q, x3), acc.y, ppp);
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = Fq::mul(acc.zz, pp);
+    acc.zzz = Fq::mul(acc.zzz, ppp);
+    return pp_;
+}
 __global__ void __launch_bounds__(128)
-msm_comb_build_kernel(const Affine *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W, Affine *__restrict__ comb) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * W) return;
+msm_comb_multiples_kernel(uint32_t n, uint32_t c, uint32_t W, Affine *comb, Fe *__restrict__ scratch) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, threads = n * W;
+    if (t >= threads) return;
     const uint32_t i = t % n, w = t / n, M = 1u << (c - 1);
-    const Affine p = load_affine(&bases[i]);
     Affine *dst = comb + (size_t)w * M * n + i;
-    if (affine_is_identity(p)) {
-        for (uint32_t d = 0; d < M; d++) {
+    Affine base;
+    base.x = load_fe(&dst[0].x);
+    base.y = load_fe(&dst[0].y);
+    if (affine_is_identity(base)) {
+        for (uint32_t d = 1; d < M; d++) {
             store_fe(&dst[(size_t)d * n].x, Fq::zero());
             store_fe(&dst[(size_t)d * n].y, Fq::zero());
         }
         return;
     }
-    // base = 2^(c*w) * P_i
-    XYZZ acc = xyzz_from_affine(p);
+    if (M < 2) return;
+    // 2 * base: T_2 = P_1 = 2 y (dbl-2008-s-1 from an affine point: ZZ = (2y)^2, ZZZ = (2y)^3)
+    XYZZ acc = xyzz_dbl_ni(xyzz_from_affine(base));
+    Fe run = Fq::dbl(base.y);  // T_(d+1) after step d
+    store_fe(&scratch[t], run);
+    store_fe(&dst[n].x, acc.x);
+    store_fe(&dst[n].y, acc.y);
 #pragma unroll 1
-    for (uint32_t k = 0; k < c * w; k++) acc = xyzz_dbl_ni(acc);
-    Affine base;
-    {
-        const Fe inv = Fq::inv(Fq::mul(acc.zz, acc.zzz));
-        base.x = Fq::mul(Fq::mul(acc.x, inv), acc.zzz);
-        base.y = Fq::mul(Fq::mul(acc.y, inv), acc.zz);
+    for (uint32_t d = 2; d < M; d++) {  // slot d holds (d + 1) * base; d * base + base is never a doubling or a
+        const Fe p = xyzz_madd_keep_p(acc, base);  // cancellation: the group order is a 254-bit prime
+        store_fe(&scratch[(size_t)(d - 1) * threads + t], p);
+        run = Fq::mul(run, p);
+        store_fe(&dst[(size_t)d * n].x, acc.x);
+        store_fe(&dst[(size_t)d * n].y, acc.y);
     }
-    store_fe(&dst[0].x, base.x);
-    store_fe(&dst[0].y, base.y);
-    acc = xyzz_from_affine(base);
+    Fe inv = Fq::inv(run);  // 1 / T_M
 #pragma unroll 1
-    for (uint32_t d = 1; d < M; d++) {
-        xyzz_madd_ni(acc, base);  // (d + 1) * base; never the identity: the group order is a 254-bit prime
-        const Fe inv = Fq::inv(Fq::mul(acc.zz, acc.zzz));
-        store_fe(&dst[(size_t)d * n].x, Fq::mul(Fq::mul(acc.x, inv), acc.zzz));
-        store_fe(&dst[(size_t)d * n].y, Fq::mul(Fq::mul(acc.y, inv), acc.zz));
+    for (uint32_t d = M - 1; d >= 1; d--) {
+        const Fe i2 = Fq::sqr(inv);
+        Affine *slot = &dst[(size_t)d * n];
+        const Fe x = Fq::mul(load_fe(&slot->x), i2);
+        const Fe y = Fq::mul(Fq::mul(load_fe(&slot->y), i2), inv);
+        store_fe(&slot->x, x);
+        store_fe(&slot->y, y);
+        inv = Fq::mul(inv, load_fe(&scratch[(size_t)(d - 1) * threads + t]));  // 1 / T_d
     }
 }
 

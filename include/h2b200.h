@@ -25,6 +25,7 @@
  *
  * Threading: calls may come from any thread; the library serialises them on one
  * internal mutex (create_proof issues them sequentially from one thread anyway).
+ * `_dev` pointers must be 16-byte aligned (field elements move as 128-bit transactions).
  */
 #ifndef H2B200_H
 #define H2B200_H
@@ -46,6 +47,19 @@ extern "C" {
 /* Select the CUDA device and create the library context (stream, workspace pool).
  * Idempotent for the same device. */
 int h2b_init(int device);
+/* Several devices behind ONE process and one handle space (the reference's prover is a single process calling
+ * create_proof, /root/reference/circuits/src/utils.rs:105-120): devices[0] is the primary device -- every `_dev`
+ * pointer and stream belongs to it -- and the others take shares of the work:
+ *   - a registered SRS of at least 2^21 points is sharded by contiguous point range, each device precomputes the
+ *     window table of its own share, every commit is split the same way (each device copies its slice of the
+ *     host scalars over its own PCIe link), and the partial sums (96 B each) travel device-to-device and are
+ *     folded on the primary device: best_multiexp's own chunk + fold (arithmetic.rs:152-176) with a device in
+ *     place of a thread;
+ *   - a smaller SRS is replicated, and the independent columns of h2b_commit_many / h2b_lagrange_to_coeff_many /
+ *     h2b_coeff_to_extended_many are dealt to the devices in contiguous blocks (a single NTT stays on one device).
+ * Idempotent for the same list; h2b_init(d) is h2b_init_devices(&d, 1). */
+int h2b_init_devices(const int *devices, int count);
+int h2b_device_count(void);
 void h2b_shutdown(void);
 /* Human-readable description of the last error on the calling thread's last call. */
 const char *h2b_last_error(void);
@@ -207,6 +221,9 @@ int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k, uint64_t *g_h
  * width, the number of windows (= bucket additions per point of a commit) and the table's size in HBM
  * (zeros when there is no table). */
 int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windows, size_t *table_bytes);
+/* How a registered SRS is laid out over the library's devices: the number of shares, whether every share is the
+ * whole array (replicated) or a contiguous point range, and (part_n, `*parts` entries, may be NULL) their lengths. */
+int h2b_srs_layout(uint64_t srs, uint32_t *parts, uint32_t *replicated, size_t *part_n);
 /* What h2b_srs_register precomputes for the static bases.  enabled = 1 (default): SRS of up to 2^14 points get
  * every window multiple d * 2^(8w) * P_i (commits become bucket-free sums, msm_comb.cuh), larger ones the window
  * table 2^(c*w) * P_i (all windows of a commit share one bucket set); 2: the window table at every size;
@@ -233,6 +250,9 @@ int h2b_kernel_time_collect(double *total_ms, uint32_t *calls);
 int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 /* out[i] = a[i] + b[i] on affine inputs (n x 8 u64) through the XYZZ mixed-add path -> n x 12 u64. */
 int h2b_test_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* Lowers the number of sorted entries one MSM pass may hold (2^log2; the product limit is 2^31, beyond which a
+ * chunk is split by point range) so that the splitting can be exercised at test sizes.  0 restores the limit. */
+int h2b_test_set_max_entries(uint32_t log2_entries);
 /* Integer-pipe microbenchmark: returns measured 32-bit IMAD (mad.lo.u32) and IMAD.WIDE
  * (mad.wide.u32) throughput in G instr/s on the current device. */
 int h2b_imad_peak(double *imad_gops, double *imad_wide_gops, double *sm_mhz);

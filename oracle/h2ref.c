@@ -737,3 +737,95 @@ void h2ref_g1_add(const uint64_t a[12], const uint64_t b[12], uint64_t out[12]) 
     g1j_add(&r, &x, &y);
     jac_to_hom(out, &r);
 }
+
+/* n DISTINCT points B + i*G, i in [0, n), B = [seed-derived scalar] G: synthetic MSM bases at benchmark sizes, where
+ * try-and-increment (h2ref_random_g1, ~30 us per point) is too slow.  Each thread owns a contiguous range and walks
+ * K interleaved chains by adding D = K*G to all K chain heads with one shared inversion per step (Montgomery's
+ * trick), ~7 products per point.  Test / benchmark infrastructure only: the cost of an MSM does not depend on
+ * which distinct points it is given. */
+typedef struct { uint64_t *out; size_t lo, hi; fe start_scalar; } prog_job;
+static void g1_affine_from_jac(g1a *r, const g1j *p) {
+    uint64_t hom[12], aff[8];
+    jac_to_hom(hom, p);
+    h2ref_g1_to_affine(hom, aff);
+    memcpy(r, aff, 64);
+}
+static void g1a_scalar_mul_canonical(g1a *r, const g1a *p, const fe *k) {
+    g1j acc;
+    g1j_identity(&acc);
+    for (int i = 255; i >= 0; i--) {
+        g1j_double(&acc, &acc);
+        if ((k->l[i / 64] >> (i % 64)) & 1) g1j_add_mixed(&acc, &acc, p);
+    }
+    g1_affine_from_jac(r, &acc);
+}
+static void *prog_worker(void *arg) {
+    prog_job *j = (prog_job *)arg;
+    enum { K = 256 };
+    const size_t len = j->hi - j->lo;
+    if (len == 0) return NULL;
+    g1a G;
+    f_from_u64(&FQ, &G.x, 1);
+    f_from_u64(&FQ, &G.y, 2);
+    /* chain heads Q_t = [start + lo + t] G, t < K; D = [K] G */
+    g1a Q[K], D;
+    fe s = j->start_scalar, lo_fe = {{(uint64_t)j->lo, 0, 0, 0}}, one = {{1, 0, 0, 0}}, kk = {{K, 0, 0, 0}};
+    /* canonical integer arithmetic on small values: start < 2^200, so no reduction is ever needed */
+    unsigned __int128 c = 0;
+    for (int i = 0; i < 4; i++) { c += (unsigned __int128)s.l[i] + lo_fe.l[i]; s.l[i] = (uint64_t)c; c >>= 64; }
+    for (size_t t = 0; t < K && t < len; t++) {
+        g1a_scalar_mul_canonical(&Q[t], &G, &s);
+        c = 0;
+        for (int i = 0; i < 4; i++) { c += (unsigned __int128)s.l[i] + one.l[i]; s.l[i] = (uint64_t)c; c >>= 64; }
+    }
+    g1a_scalar_mul_canonical(&D, &G, &kk);
+    fe den[K], pre[K];
+    for (size_t base = 0; base < len; base += K) {
+        const size_t cnt = len - base < K ? len - base : K;
+        memcpy(j->out + 8 * (j->lo + base), Q, cnt * 64);
+        if (base + K >= len) break;
+        /* Q_t += D for every chain that still has a successor */
+        const size_t nxt = len - (base + K) < K ? len - (base + K) : K;
+        for (size_t t = 0; t < nxt; t++) {
+            f_sub(&FQ, &den[t], &D.x, &Q[t].x);
+            if (t == 0) pre[0] = den[0]; else f_mul(&FQ, &pre[t], &pre[t - 1], &den[t]);
+        }
+        fe inv;
+        f_inv(&FQ, &inv, &pre[nxt - 1]);
+        for (size_t t = nxt; t-- > 0;) {
+            fe di;
+            if (t) { f_mul(&FQ, &di, &inv, &pre[t - 1]); f_mul(&FQ, &inv, &inv, &den[t]); } else di = inv;
+            fe lam, x3, y3, tmp;
+            f_sub(&FQ, &tmp, &D.y, &Q[t].y);
+            f_mul(&FQ, &lam, &tmp, &di);
+            f_sqr(&FQ, &x3, &lam);
+            f_sub(&FQ, &x3, &x3, &Q[t].x);
+            f_sub(&FQ, &x3, &x3, &D.x);
+            f_sub(&FQ, &tmp, &Q[t].x, &x3);
+            f_mul(&FQ, &y3, &lam, &tmp);
+            f_sub(&FQ, &y3, &y3, &Q[t].y);
+            Q[t].x = x3;
+            Q[t].y = y3;
+        }
+    }
+    return NULL;
+}
+void h2ref_progression_g1(uint64_t *out, size_t n, uint64_t seed, int num_threads) {
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > n / 1024 + 1) num_threads = (int)(n / 1024 + 1);
+    fe start = {{0, 0, 0, 0}};
+    uint64_t st = seed;
+    for (int i = 0; i < 3; i++) start.l[i] = splitmix64(&st);  /* < 2^192 */
+    pthread_t th[256];
+    prog_job jobs[256];
+    if (num_threads > 256) num_threads = 256;
+    const size_t per = (n + num_threads - 1) / num_threads;
+    for (int t = 0; t < num_threads; t++) {
+        jobs[t].out = out;
+        jobs[t].lo = (size_t)t * per < n ? (size_t)t * per : n;
+        jobs[t].hi = (size_t)(t + 1) * per < n ? (size_t)(t + 1) * per : n;
+        jobs[t].start_scalar = start;
+        pthread_create(&th[t], NULL, prog_worker, &jobs[t]);
+    }
+    for (int t = 0; t < num_threads; t++) pthread_join(th[t], NULL);
+}

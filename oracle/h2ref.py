@@ -136,6 +136,13 @@ def random_g1(n: int, seed: int) -> np.ndarray:
     return out
 
 
+def progression_g1(n: int, seed: int, threads: int | None = None) -> np.ndarray:
+    """n distinct points B + i*G (synthetic MSM bases at benchmark sizes; see h2ref_progression_g1)."""
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().h2ref_progression_g1(_p(out), C.c_size_t(n), C.c_uint64(seed), C.c_int(threads or default_threads()))
+    return out
+
+
 def fr_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     out = np.zeros_like(a)
     lib().h2ref_fr_mul(_p(a), _p(b), _p(out), C.c_size_t(a.shape[0]))

@@ -5,7 +5,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../halo2-prover_b200/csrc/field.cuh"
-#include "../halo2-prover_b200/csrc/field52.cuh"
+#include "field52.cuh"
 #include "karatsuba_experiment.cuh"
 using namespace h2b;
 

@@ -1,7 +1,7 @@
-// Host harness around halo2-prover_b200/csrc/field52.cuh (the device's FP64-pipe field arithmetic compiled
+// Host harness around scripts/field52.cuh (the device's FP64-pipe field arithmetic compiled
 // for the CPU with std::fma under FE_TOWARDZERO) so tests/test_field52.py can check it against big integers.
 #include <cfenv>
-#include "../../halo2-prover_b200/csrc/field52.cuh"
+#include "../../scripts/field52.cuh"
 using namespace h2b;
 
 namespace {

@@ -1,4 +1,4 @@
-"""csrc/field52.cuh (5 x 52-bit limbs, products formed by FMA pairs) compiled for the host and checked
+"""scripts/field52.cuh (5 x 52-bit limbs, products formed by FMA pairs) compiled for the host and checked
 against big-integer arithmetic.  The device runs the same source with __fma_rz; tests/test_field_gpu.py
 repeats the comparison there."""
 import ctypes as C
@@ -11,7 +11,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "field52_host.cpp")
-HDR = os.path.join(HERE, "..", "halo2-prover_b200", "csrc", "field52.cuh")
+HDR = os.path.join(HERE, "..", "scripts", "field52.cuh")
 LIB = os.path.join(HERE, "native", "libfield52_host.so")
 Q = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
 M52 = (1 << 52) - 1
