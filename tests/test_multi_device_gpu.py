@@ -48,7 +48,7 @@ def test_single_device_through_init_devices():
                         "import h2ref, halo2_prover_b200 as h2b\n"
                         "from halo2_prover_b200 import _ffi\n"
                         "_ffi.init_devices([0]); assert _ffi.lib().h2b_device_count() == 1\n"
-                        "b, s = h2ref.random_g1(3000, 1), h2ref.random_fr(3000, 2)\n"
+                        "b, s = h2ref.random_g1(4096, 1), h2ref.random_fr(4096, 2)\n"
                         "p = h2b.ParamsKZG(12, b)\n"
                         "assert (h2ref.g1_to_affine(p.commit(s)) == h2ref.g1_to_affine(h2ref.best_multiexp(s, b))).all()\n"
                         "p.release(); _ffi.shutdown(); print('ok')\n" % (ROOT, os.path.join(ROOT, "oracle"))],
