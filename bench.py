@@ -231,14 +231,14 @@ def run_b200(args) -> None:
                     params.dev_commit(ds, out, stream=stream)
                 else:
                     out.copy_(multi_gpu.sharded_commit(params, ds, stream=stream))
+            # started before the warm-up: nvidia-smi needs a few hundred ms to deliver its first row
+            sampler = ClockSampler(local) if (rank == 0 and with_kernel_timing) else None
             for _ in range(max(args.warmup, 3)):
                 step()
             stream.synchronize()
             if world > 1:
                 dist.barrier()
-            sampler = ClockSampler(local) if (rank == 0 and with_kernel_timing) else None
             if sampler:
-                time.sleep(0.4)  # nvidia-smi needs a few hundred ms to deliver its first row
                 sampler.mark_begin()
             if with_kernel_timing:
                 _ffi.check(L.h2b_set_kernel_timing(1))
@@ -829,6 +829,12 @@ def bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, imad_gops) -> dict:
     peaks = measured_peaks()
     modmul = n // 2 * k
     imad_achieved = modmul * MODMUL_IMAD / (kms * 1e-3) / 1e12 if kms > 0 else None
+    # what the passes execute: every butterfly whose twiddle is not omega^0, plus one inter-pass twiddle per element
+    # and pass boundary; a lazy Montgomery product is 123 IMAD.WIDE (= 2 IMAD-class each) + 17 IMAD in SASS
+    passes = max(2, -(-k // 10)) if k > 10 else 1
+    radices = [k // passes + (1 if i < k % passes else 0) for i in range(passes)]
+    executed_mul = sum((n >> s_) * ((1 << s_) // 2 * s_ - ((1 << s_) - 1)) for s_ in radices) + (passes - 1) * n
+    executed = executed_mul * (123 * 2 + 17) / (kms * 1e-3) / 1e12 if kms > 0 else None
     hbm_achieved = 64.0 * n / (kms * 1e-3) / 1e9 if kms > 0 else None
     out = {
         "k": k, "elems_per_s": n / (ms * 1e-3), "ms": ms, "kernels_ms": kms,
@@ -837,6 +843,11 @@ def bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, imad_gops) -> dict:
                 "api": "best_fft -> h2b_best_fft, pinned host buffer, in place"},
         "roofline": {"bound": "imad", "achieved": imad_achieved, "peak": imad_gops / 1e3, "unit": "TIMAD/s",
                      "frac": imad_achieved / (imad_gops / 1e3) if imad_achieved else None,
+                     "frac_model": imad_achieved / (imad_gops / 1e3) if imad_achieved else None,
+                     "frac_executed": executed / (imad_gops / 1e3) if executed else None,
+                     "executed": "%d Montgomery products in %d passes of radix 2^%s (trivial twiddles skipped, one inter-pass "
+                                 "twiddle per element and boundary) x 263 IMAD-class each (123 IMAD.WIDE = 2, 17 IMAD)"
+                                 % (executed_mul, passes, radices),
                      "algorithmic": "(n/2)*k modmul x 272 IMAD; 64*n compulsory bytes",
                      "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": peaks.get("hbm_gbs"),
                              "frac": hbm_achieved / peaks["hbm_gbs"] if hbm_achieved and peaks.get("hbm_gbs") else None}},

@@ -44,6 +44,11 @@ struct FrP {
                                    0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
         return v[i];
     }
+    H2B_DI static constexpr uint32_t n2(int i) {  // 2 r
+        constexpr uint32_t v[8] = {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u,
+                                   0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
+        return v[i];
+    }
 };
 struct FqP {
     static constexpr uint32_t M0 = 0xe4866389u;
@@ -60,6 +65,11 @@ struct FqP {
     H2B_DI static constexpr uint32_t r2(int i) {  // R^2 mod q
         constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
                                    0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return v[i];
+    }
+    H2B_DI static constexpr uint32_t n2(int i) {  // 2 q
+        constexpr uint32_t v[8] = {0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u,
+                                   0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
         return v[i];
     }
 };
@@ -327,6 +337,81 @@ struct Field {
         return d;
     }
 
+    // ---- lazy range [0, 2N): the butterflies of the NTT keep their values there and reduce once at the very end
+    // a - 2N if a >= 2N else a      (a < 4N)
+    H2B_DI static Fe reduce_2n(const Fe &a) {
+        Fe t;
+        uint32_t borrow;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]),
+              "=r"(t.l[6]), "=r"(t.l[7]), "=r"(borrow)
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]),
+              "r"(a.l[6]), "r"(a.l[7]), "r"(P::n2(0)), "r"(P::n2(1)), "r"(P::n2(2)), "r"(P::n2(3)),
+              "r"(P::n2(4)), "r"(P::n2(5)), "r"(P::n2(6)), "r"(P::n2(7)));
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = borrow ? a.l[i] : t.l[i];
+        return r;
+    }
+    // a + b brought back to [0, 2N)      (a, b < 2N; 4N < 2^256: no carry out)
+    H2B_DI static Fe add_2n(const Fe &a, const Fe &b) {
+        Fe s;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s.l[0]), "=r"(s.l[1]), "=r"(s.l[2]), "=r"(s.l[3]), "=r"(s.l[4]), "=r"(s.l[5]),
+              "=r"(s.l[6]), "=r"(s.l[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]),
+              "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]),
+              "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+        return reduce_2n(s);
+    }
+    // a - b + 2N, in (0, 4N): no condition at all      (a, b < 2N)
+    H2B_DI static Fe sub_2n(const Fe &a, const Fe &b) {
+        Fe d;
+        asm("sub.cc.u32 %0, %8, %16;\n\t"
+            "subc.cc.u32 %1, %9, %17;\n\t"
+            "subc.cc.u32 %2, %10, %18;\n\t"
+            "subc.cc.u32 %3, %11, %19;\n\t"
+            "subc.cc.u32 %4, %12, %20;\n\t"
+            "subc.cc.u32 %5, %13, %21;\n\t"
+            "subc.cc.u32 %6, %14, %22;\n\t"
+            "subc.u32 %7, %15, %23;"
+            : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]),
+              "=r"(d.l[6]), "=r"(d.l[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]),
+              "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]),
+              "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+        Fe r;  // the wrap-around of a negative difference is undone by the addition
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]),
+              "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(d.l[0]), "r"(d.l[1]), "r"(d.l[2]), "r"(d.l[3]), "r"(d.l[4]), "r"(d.l[5]),
+              "r"(d.l[6]), "r"(d.l[7]), "r"(P::n2(0)), "r"(P::n2(1)), "r"(P::n2(2)), "r"(P::n2(3)),
+              "r"(P::n2(4)), "r"(P::n2(5)), "r"(P::n2(6)), "r"(P::n2(7)));
+        return r;
+    }
+
     // One Montgomery step on the (E, O) accumulator pair: add N * m so that E[0] becomes 0.
     H2B_DI static void redc_step(uint32_t (&E)[8], uint32_t (&O)[8]) {
         uint32_t m = E[0] * P::M0;
@@ -334,8 +419,10 @@ struct Field {
         cmad_row_fold(E, O[7], P::n(0), P::n(2), P::n(4), P::n(6), m);
     }
 
-    // Montgomery product a * b * R^-1 mod N, fully reduced.
-    H2B_DI static Fe mul(const Fe &a, const Fe &b) {
+    // Montgomery product without the final conditional subtraction: a * b * R^-1 + (a multiple of N), below
+    // a * b / R + N.  For a < 4N and b < N that is below 2N (both moduli are below 2^254, so 4N < R), and the running
+    // value of the interleaved accumulators stays below 5 N 2^32 < 2^288, inside their capacity.
+    H2B_DI static Fe mul_lazy(const Fe &a, const Fe &b) {
         uint32_t ev[8], od[8];
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
@@ -375,8 +462,10 @@ struct Field {
             : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]),
               "r"(ev[7]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]),
               "r"(od[7]));
-        return reduce_once(r);
+        return r;
     }
+    // Montgomery product a * b * R^-1 mod N, fully reduced (a * b < N R).
+    H2B_DI static Fe mul(const Fe &a, const Fe &b) { return reduce_once(mul_lazy(a, b)); }
     // (a * b + c * d) * R^-1 mod N, fully reduced: two products under ONE Montgomery reduction (24 instead of 32 limb
     // products per row pair).  Every term is non-negative and the running value stays below 3 N B < 2^288, so neither
     // accumulator can overflow; the final value is below N (1 + 2 N / R) < 2 N.  Inputs up to N inclusive.

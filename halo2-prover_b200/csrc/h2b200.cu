@@ -61,6 +61,10 @@ struct TwKey {
     }
 };
 // One device's share of a registered base array.
+struct TwEntry {
+    Fe *W = nullptr;          // omega^e, e in [0, 2^log_n)
+    Fe *pass[11] = {};        // inner twiddles of a radix-2^S pass, per level (ntt_pass_twiddles_kernel), by S
+};
 struct Srs {
     int dev = 0;              // index into g_all
     size_t off = 0;           // first point of the share inside the registered array
@@ -142,7 +146,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     void *buf[BUF_COUNT] = {};
     size_t cap[BUF_COUNT] = {};
-    std::map<TwKey, Fe *> twiddles;
+    std::map<TwKey, TwEntry> twiddles;
     size_t twiddle_bytes = 0;
     std::map<uint64_t, h2b_domain> domains;
     uint64_t launches = 0;
@@ -695,20 +699,24 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
 }
 
 // ------------------------------------------------------------------------------ NTT
-int get_twiddles(const uint64_t omega[4], uint32_t log_n, cudaStream_t s, const Fe **out) {
+int get_twiddles(const uint64_t omega[4], uint32_t log_n, cudaStream_t s, TwEntry **out) {
     TwKey key;
     memcpy(key.w, omega, 32);
     key.log_n = log_n;
     auto it = g->twiddles.find(key);
     if (it != g->twiddles.end()) {
-        *out = it->second;
+        *out = &it->second;
         return H2B_OK;
     }
     size_t n = (size_t)1 << log_n;
     size_t bytes = n * sizeof(Fe);
     if (g->twiddle_bytes + bytes > ((size_t)24 << 30)) {  // bound the cache
         CU(cudaDeviceSynchronize());
-        for (auto &kv : g->twiddles) cudaFree(kv.second);
+        for (auto &kv : g->twiddles) {
+            cudaFree(kv.second.W);
+            for (Fe *t : kv.second.pass)
+                if (t) cudaFree(t);
+        }
         g->twiddles.clear();
         g->twiddle_bytes = 0;
     }
@@ -730,80 +738,154 @@ int get_twiddles(const uint64_t omega[4], uint32_t log_n, cudaStream_t s, const 
     ntt_pow_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(small, small + n_lo, lo_bits,
                                                                      (uint32_t)n, W);
     LAUNCHED();
-    g->twiddles[key] = W;
+    TwEntry ent;
+    ent.W = W;
+    auto ins = g->twiddles.emplace(key, ent);
     g->twiddle_bytes += bytes;
-    *out = W;
+    *out = &ins.first->second;
+    return H2B_OK;
+}
+// The per-level inner twiddle tables of a radix-2^S pass of a 2^log_n transform (built on first use).
+int get_pass_twiddles(TwEntry *ent, uint32_t log_n, uint32_t S, cudaStream_t s, const Fe **out) {
+    if (!ent->pass[S]) {
+        Fe *t = nullptr;
+        cudaError_t e = cudaMalloc(&t, ((size_t)1 << S) * sizeof(Fe));
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(H2B_ERR_OOM, "cudaMalloc(pass twiddles)", e);
+        }
+        ntt_pass_twiddles_kernel<<<((1u << S) + 127) / 128, 128, 0, s>>>(ent->W, log_n, S, t);
+        LAUNCHED();
+        ent->pass[S] = t;
+    }
+    *out = ent->pass[S];
     return H2B_OK;
 }
 
-template <int S, int C, int NT>
-int launch_pass(const Fe *in, Fe *out, const Fe *W, uint32_t log_n, uint32_t log_ns, bool last,
-                const NttIo &io, cudaStream_t s, uint32_t batch) {
-    constexpr int R = 1 << S;
-    size_t smem = ((size_t)2 * R * C + 2 * (R / 2 > 0 ? R / 2 : 1)) * sizeof(uint4);
-    if (smem > 48 * 1024 && !g->attr_done.count((const void *)ntt_pass_kernel<S, C, NT>)) {
-        CU(cudaFuncSetAttribute(ntt_pass_kernel<S, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-        g->attr_done.insert((const void *)ntt_pass_kernel<S, C, NT>);
+// Which exchanges of a pass stay inside a warp: bit r is set when, after round r, every thread reads only elements
+// written by threads of its own warp (then __syncwarp orders them; otherwise the round ends with a block barrier).
+// Enumerated once per tile shape: the row sets of the rounds are those of ntt_pass_kernel.
+uint32_t ntt_warp_sync_mask(uint32_t S, uint32_t C, uint32_t EL) {
+    static std::map<uint32_t, uint32_t> cache;
+    const uint32_t key = S | (C << 8) | (EL << 24);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const uint32_t E = 1u << EL, groups = ((1u << S) * C) >> EL;
+    std::vector<uint32_t> ss;  // s_r of every round
+    for (uint32_t lvl = 0; lvl < S;) {
+        const uint32_t er = std::min(EL, S - lvl);
+        ss.push_back(er < EL ? 0u : S - lvl - EL);
+        lvl += er;
     }
-    uint32_t M = 1u << (log_n - S);
-    uint32_t blocks = M / C;
+    auto elem = [&](uint32_t gidx, uint32_t t, uint32_t s) {
+        const uint32_t col = gidx % C, rest = gidx / C, lo = rest & ((1u << s) - 1u), hi = rest >> s;
+        return (((hi << (s + EL)) | (t << s) | lo) * C) + col;
+    };
+    uint32_t mask = 0;
+    std::vector<uint32_t> owner((size_t)(1u << S) * C);
+    for (size_t r = 0; r + 1 < ss.size(); r++) {
+        for (uint32_t gidx = 0; gidx < groups; gidx++)
+            for (uint32_t t = 0; t < E; t++) owner[elem(gidx, t, ss[r])] = gidx;
+        bool local = true;
+        for (uint32_t gidx = 0; gidx < groups && local; gidx++)
+            for (uint32_t t = 0; t < E; t++)
+                if ((owner[elem(gidx, t, ss[r + 1])] >> 5) != (gidx >> 5)) {
+                    local = false;
+                    break;
+                }
+        if (local) mask |= 1u << r;
+    }
+    cache[key] = mask;
+    return mask;
+}
+
+template <int S, int C, int EL, int NT, int MINB = 1>
+int launch_pass(const Fe *in, Fe *out, const Fe *W, const Fe *TW, uint32_t log_n, uint32_t log_ns, bool last,
+                const NttIo &io, cudaStream_t s, uint32_t batch) {
+    static_assert(S >= EL && S <= 10, "a round needs EL levels; tiles hold at most 2^10 rows");
+    constexpr int R = 1 << S;
+    const size_t smem = ((size_t)2 * R * C + 2 * (R >> EL)) * sizeof(uint4);  // tile + the later rounds' twiddles
+    if (smem > 48 * 1024 && !g->attr_done.count((const void *)ntt_pass_kernel<S, C, EL, NT, MINB>)) {
+        CU(cudaFuncSetAttribute(ntt_pass_kernel<S, C, EL, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+        g->attr_done.insert((const void *)ntt_pass_kernel<S, C, EL, NT, MINB>);
+    }
+    const uint32_t M = 1u << (log_n - S);
+    const uint32_t blocks = M / C;
     if (blocks == 0) return fail(H2B_ERR_ARG, "ntt: tile wider than the pass");
-    ntt_pass_kernel<S, C, NT><<<dim3(blocks, batch), NT, smem, s>>>(in, out, W, log_n, log_ns, last ? 1u : 0u, io);
+    ntt_pass_kernel<S, C, EL, NT, MINB><<<dim3(blocks, batch), NT, smem, s>>>(in, out, W, TW, log_n, log_ns, last ? 1u : 0u,
+                                                                      ntt_warp_sync_mask(S, C, EL), io);
     LAUNCHED();
     return H2B_OK;
 }
 
-uint32_t g_ntt_tile_log = 10;  // log2 elements per multi-pass tile (8, 9 or 10); 10 measured best on B200
-
-int dispatch_pass(uint32_t S, bool single, const Fe *in, Fe *out, const Fe *W, uint32_t log_n,
-                  uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s, uint32_t batch) {
-    // threads per block = tile elements / 8 (one radix-8 group per thread and round)
-    if (!single && g_ntt_tile_log == 9) {
-        switch (S) {
-            case 5: return launch_pass<5, 16, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 6: return launch_pass<6, 8, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 7: return launch_pass<7, 4, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 8: return launch_pass<8, 2, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
-        }
-    }
-    if (!single && g_ntt_tile_log == 10) {
-        switch (S) {
-            case 5: return launch_pass<5, 32, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 6: return launch_pass<6, 16, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 7: return launch_pass<7, 8, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 8: return launch_pass<8, 4, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 9: return launch_pass<9, 2, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
-        }
-    }
-    if (!single && g_ntt_tile_log == 8) {
-        switch (S) {
-            case 5: return launch_pass<5, 8, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 6: return launch_pass<6, 4, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 7: return launch_pass<7, 2, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-        }
+// Tile shapes.  A transform of up to 2^10 elements is one single-column tile.  Multi-pass transforms use tiles of
+// 2^TL elements with 2^EL elements per thread: TL = 10 is the throughput shape (EL = 3 / 2 / 1 on 128 / 256 / 512
+// threads), TL = 9 and 8 on 128 threads give more and smaller blocks to transforms that would otherwise leave most
+// SMs idle (those are latency-bound, not throughput-bound).
+extern int g_ntt_dense;
+int dispatch_pass(uint32_t S, uint32_t EL, uint32_t TL, bool single, const Fe *in, Fe *out, const Fe *W, const Fe *TW,
+                  uint32_t log_n, uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s, uint32_t batch) {
+#define H2B_PASS(S_, C_, EL_, NT_) return launch_pass<S_, C_, EL_, NT_>(in, out, W, TW, log_n, log_ns, last, io, s, batch)
+#define H2B_PASSB(S_, C_, EL_, NT_, B_) return launch_pass<S_, C_, EL_, NT_, B_>(in, out, W, TW, log_n, log_ns, last, io, s, batch)
+#define H2B_TILE10(EL_, NT_, B_)                      \
+    switch (S) {                                      \
+        case 5: H2B_PASSB(5, 32, EL_, NT_, B_);       \
+        case 6: H2B_PASSB(6, 16, EL_, NT_, B_);       \
+        case 7: H2B_PASSB(7, 8, EL_, NT_, B_);        \
+        case 8: H2B_PASSB(8, 4, EL_, NT_, B_);        \
+        case 9: H2B_PASSB(9, 2, EL_, NT_, B_);        \
+        case 10: H2B_PASSB(10, 1, EL_, NT_, B_);      \
     }
     if (single) {
         switch (S) {
-            case 1: return launch_pass<1, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 2: return launch_pass<2, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 3: return launch_pass<3, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 4: return launch_pass<4, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 5: return launch_pass<5, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 6: return launch_pass<6, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 7: return launch_pass<7, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 8: return launch_pass<8, 1, 32>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 9: return launch_pass<9, 1, 64>(in, out, W, log_n, log_ns, last, io, s, batch);
-            case 10: return launch_pass<10, 1, 128>(in, out, W, log_n, log_ns, last, io, s, batch);
+            case 1: H2B_PASS(1, 1, 1, 32);
+            case 2: H2B_PASS(2, 1, 2, 32);
+            case 3: H2B_PASS(3, 1, 3, 32);
+            case 4: H2B_PASS(4, 1, 3, 32);
+            case 5: H2B_PASS(5, 1, 3, 32);
+            case 6: H2B_PASS(6, 1, 3, 32);
+            case 7: H2B_PASS(7, 1, 3, 32);
+            case 8: H2B_PASS(8, 1, 3, 32);
+            case 9: H2B_PASS(9, 1, 3, 64);
+            case 10: H2B_PASS(10, 1, 3, 128);
+        }
+    } else if (TL == 10 && EL == 3) {
+        if (g_ntt_dense) { H2B_TILE10(3, 128, 5) } else { H2B_TILE10(3, 128, 4) }
+    } else if (TL == 10 && EL == 2) {
+        if (g_ntt_dense) { H2B_TILE10(2, 256, 3) } else { H2B_TILE10(2, 256, 2) }
+    } else if (TL == 10 && EL == 1) {
+        H2B_TILE10(1, 512, 2)
+    } else if (TL == 9 && EL == 2) {
+        switch (S) {
+            case 5: H2B_PASS(5, 16, 2, 128);
+            case 6: H2B_PASS(6, 8, 2, 128);
+            case 7: H2B_PASS(7, 4, 2, 128);
+            case 8: H2B_PASS(8, 2, 2, 128);
+            case 9: H2B_PASS(9, 1, 2, 128);
+        }
+    } else if (TL == 8 && EL == 1) {
+        switch (S) {
+            case 4: H2B_PASS(4, 16, 1, 128);
+            case 5: H2B_PASS(5, 8, 1, 128);
+            case 6: H2B_PASS(6, 4, 1, 128);
+            case 7: H2B_PASS(7, 2, 1, 128);
+            case 8: H2B_PASS(8, 1, 1, 128);
         }
     }
+#undef H2B_TILE10
+#undef H2B_PASSB
+#undef H2B_PASS
     return fail(H2B_ERR_ARG, "ntt: unsupported radix / tile configuration");
 }
 
-uint32_t g_ntt_max_radix = 10;  // two passes up to 2^20, three up to 2^28 (measured best on B200)
+uint32_t g_ntt_max_radix = 10;  // two passes up to 2^20, three up to 2^28 (H2B_NTT_MAX_RADIX)
+int g_ntt_el_big = 2;           // elements per thread (log2) of the 2^10-element throughput tiles (H2B_NTT_EL_BIG): measured
+                                // on B200 at k = 20 / 22 / 24: 4 per thread on 256 threads, 3 blocks per SM (24 warps) 0.200 / 0.874 /
+                                // 3.53 ms; 8 per thread on 128 threads, 4 blocks (16 warps) 0.220 / 0.919 / 3.62; 2 per thread on 512
+                                // threads (32 warps, but ten exchanges) 0.225 / 0.955 / 4.05
+int g_ntt_tile = 0;             // forced tile size as log2, 8..10 (H2B_NTT_TILE); 0 = by size
+int g_ntt_dense = 1;            // 1: registers held to 5 (EL = 3) / 3 (EL = 2) blocks per SM instead of 4 / 2 (H2B_NTT_DENSE)
 
 // Transform `src` (n_in valid elements of a 2^log_n domain) into `dst`; `dst` may equal `src`.
 // dst_full: `dst` holds 2^log_n elements and may carry intermediate passes; otherwise (truncated
@@ -835,17 +917,30 @@ int ntt_run(const Fe *src, Fe *dst, uint32_t log_n, const uint64_t omega[4], Ntt
         }
         return H2B_OK;
     }
-    const Fe *W;
-    TRY(get_twiddles(omega, log_n, s, &W));
-    uint32_t P, radix[4];
+    TwEntry *tw;
+    TRY(get_twiddles(omega, log_n, s, &tw));
+    uint32_t P, radix[4], EL = 3, TL = 10;
     bool single = log_n <= 10;
     if (single) {
         P = 1;
         radix[0] = log_n;
     } else {
-        P = (log_n + g_ntt_max_radix - 1) / g_ntt_max_radix;
-        if (P < 2) P = 2;
-        uint32_t base = log_n / P, rem = log_n % P;
+        // 2^10-element tiles when that already gives every SM two of them; smaller tiles (more blocks) for transforms
+        // that would leave SMs idle
+        const uint64_t tiles10 = ((uint64_t)batch << log_n) >> 10;
+        if (g_ntt_tile) TL = (uint32_t)g_ntt_tile;
+        else if (tiles10 >= 2u * (uint32_t)g->sm_count) TL = 10;
+        else if (tiles10 >= (uint32_t)g->sm_count) TL = 9;
+        else TL = 8;
+        auto passes = [&](uint32_t tl) {
+            const uint32_t mr = std::min(g_ntt_max_radix, tl);
+            return std::max(2u, (log_n + mr - 1) / mr);
+        };
+        while (TL < 10 && passes(TL) > passes(10)) TL++;  // never more passes than the throughput shape needs
+        EL = TL == 10 ? (uint32_t)g_ntt_el_big : TL - 7;
+        P = passes(TL);
+        if (P > 4) return fail(H2B_ERR_ARG, "ntt: too many passes");
+        const uint32_t base = log_n / P, rem = log_n % P;  // log_n >= 11: every radix >= 5
         for (uint32_t i = 0; i < P; i++) radix[i] = base + (i < rem ? 1 : 0);
     }
     Fe *tmp = nullptr, *tmp2 = dst;
@@ -856,6 +951,8 @@ int ntt_run(const Fe *src, Fe *dst, uint32_t log_n, const uint64_t omega[4], Ntt
         TRY(get_buf(BUF_NTT_T2, (size_t)batch * N * sizeof(Fe), (void **)&tmp2));
         tmp2_stride = N;
     }
+    const Fe *TW[4];
+    for (uint32_t i = 0; i < P; i++) TRY(get_pass_twiddles(tw, log_n, radix[i], s, &TW[i]));
     time_begin(s);
     const Fe *cur = src;
     uint32_t log_ns = 0, cur_stride = io.bin;
@@ -865,7 +962,7 @@ int ntt_run(const Fe *src, Fe *dst, uint32_t log_n, const uint64_t omega[4], Ntt
         NttIo pio = io;
         if (i != 0) { pio.pro = 0; pio.n_in = 1u << log_n; pio.bin = cur_stride; }
         if (!last) { pio.epi = 0; pio.n_out = 1u << log_n; pio.bout = (to == tmp) ? N : tmp2_stride; }
-        TRY(dispatch_pass(radix[i], single, cur, to, W, log_n, log_ns, last, pio, s, batch));
+        TRY(dispatch_pass(radix[i], EL, TL, single, cur, to, tw->W, TW[i], log_n, log_ns, last, pio, s, batch));
         cur = to;
         cur_stride = pio.bout;
         log_ns += radix[i];
@@ -1070,6 +1167,9 @@ __global__ void test_field_kernel(int op, const Fe *a, const Fe *b, Fe *o, uint3
         case 6: r = F::sqr(x); break;
         case 7: r = F::mul2_add(x, y, F::add(x, y), F::sub(x, y)); break;   // xy + x^2 - y^2
         case 8: r = F::mul2_sub(x, y, y, x); break;                         // 0, through neg()
+        case 9: r = F::reduce_once(F::mul_lazy(x, y)); break;               // x < 4N (raw limbs), y < N
+        case 10: r = F::reduce_once(F::reduce_2n(F::sub_2n(x, y))); break;  // x, y < 2N (raw limbs)
+        case 11: r = F::reduce_once(F::add_2n(x, y)); break;                // x, y < 2N (raw limbs)
         default: r = F::from_mont(x); break;
     }
     store_fe(&o[i], r);
@@ -1200,7 +1300,11 @@ static void ctx_destroy(Ctx *c) {
     cudaDeviceSynchronize();
     for (int i = 0; i < BUF_COUNT; i++)
         if (c->buf[i]) cudaFree(c->buf[i]);
-    for (auto &kv : c->twiddles) cudaFree(kv.second);
+    for (auto &kv : c->twiddles) {
+        cudaFree(kv.second.W);
+        for (Fe *t : kv.second.pass)
+            if (t) cudaFree(t);
+    }
     for (auto e : c->tev0) cudaEventDestroy(e);
     for (auto e : c->tev1) cudaEventDestroy(e);
     for (auto e : c->chunk_events) cudaEventDestroy(e);
@@ -1233,6 +1337,12 @@ static int init_locked(const int *devices, int count) {
     }
     const char *sm = getenv("H2B_SHARD_MIN_LOG");
     if (sm && atoi(sm) >= 8 && atoi(sm) <= 30) g_shard_min_n = (size_t)1 << atoi(sm);
+    const char *el = getenv("H2B_NTT_EL_BIG");
+    if (el && atoi(el) >= 1 && atoi(el) <= 3) g_ntt_el_big = atoi(el);
+    const char *dn = getenv("H2B_NTT_DENSE");
+    if (dn) g_ntt_dense = atoi(dn) != 0;
+    const char *tl = getenv("H2B_NTT_TILE");
+    if (tl && atoi(tl) >= 8 && atoi(tl) <= 10) g_ntt_tile = atoi(tl);
     const char *mr = getenv("H2B_NTT_MAX_RADIX");
     if (mr) {
         int v = atoi(mr);
@@ -2141,7 +2251,11 @@ int h2b_g_to_lagrange(const uint64_t *g_bases, uint32_t k, uint64_t *out) {
     TRY(get_buf(BUF_ECNTT, n * sizeof(XYZZ), (void **)&work));
     TRY(get_buf(BUF_TEST_O, n * sizeof(Affine), (void **)&dout));
     const Fe *W = nullptr;
-    if (k > 0) TRY(get_twiddles(d.omega_inv, k, s, &W));
+    if (k > 0) {
+        TwEntry *tw;
+        TRY(get_twiddles(d.omega_inv, k, s, &tw));
+        W = tw->W;
+    }
     const uint32_t blocks = (uint32_t)((n + 127) / 128);
     ec_ntt_load_kernel<<<blocks, 128, 0, s>>>((const Affine *)din, k, work);
     LAUNCHED();

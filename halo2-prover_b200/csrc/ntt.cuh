@@ -12,9 +12,10 @@
 // whole array).  It is an autosort (Stockham) decimation-in-frequency transform
 // split into at most four passes; each pass works on a [2^S rows] x [C columns] tile:
 // 128-bit coalesced loads of C adjacent elements per row straight into registers,
-// S butterfly levels in rounds of three levels held in registers (8 rows per thread,
-// shared memory only between rounds), the inter-pass twiddle from a cached table of
-// powers of omega, and stores of C adjacent elements per output row.
+// S butterfly levels in rounds of up to three levels held in registers (2, 4 or 8 rows
+// per thread, a swizzled shared-memory exchange between rounds, block barrier only after
+// the first), inner twiddles from per-level tables, the inter-pass twiddle from a cached
+// table of powers of omega, and stores of C adjacent elements per output row.
 // The scaling steps of the domain transforms are fused into the first load
 // (coset powers, zero padding) and the last store (1/n, inverse coset powers,
 // truncation), so every transform costs exactly its passes and nothing else.
@@ -69,137 +70,235 @@ H2B_DI Fe fe_from_u4(const uint4 &a, const uint4 &b) {
     return r;
 }
 
-// RB decimation-in-frequency levels on 2^RB rows held in registers.  The rows are
-// u_t = row_base + t * st of the tile (row_base mod st = lo), the levels are the tile levels
-// lvl .. lvl + RB - 1; the butterfly (u, u + h) of tile level L uses omega_R^((u mod h) << L).
-template <int RB>
-H2B_DI void dif_levels(Fe (&a)[1 << RB], uint32_t lo, uint32_t st, uint32_t lvl,
-                       const uint4 *__restrict__ t_lo, const uint4 *__restrict__ t_hi) {
-#pragma unroll
-    for (int q = 0; q < RB; q++) {
-        const int half = 1 << (RB - 1 - q);
-#pragma unroll
-        for (int t = 0; t < (1 << RB); t++) {
-            if (t & half) continue;
-            const Fe x = a[t], y = a[t + half];
-            a[t] = Fr::add(x, y);
-            Fe d = Fr::sub(x, y);
-            const uint32_t e = (lo + (uint32_t)(t & (half - 1)) * st) << (lvl + q);
-            if (e != 0) d = Fr::mul(d, fe_from_u4(t_lo[e], t_hi[e]));
-            a[t + half] = d;
-        }
-    }
+// Inner twiddles of a radix-2^S pass, one table per tile level L, entries contiguous in the butterfly index so that the
+// lanes of a warp read neighbouring entries:  TW[off(L) + j] = omega_R^(j << L),  j < R >> (L + 1),  off(L) = R - (R >> L)
+// (R - 1 entries; omega_R = omega^(N / R)).  Built once per (omega, log_n, S) from the table of all powers.
+__global__ void ntt_pass_twiddles_kernel(const Fe *__restrict__ W, uint32_t log_n, uint32_t S, Fe *__restrict__ TW) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, R = 1u << S;
+    if (i >= R - 1) return;
+    uint32_t L = 0;
+    while (i >= R - (R >> (L + 1))) L++;
+    const uint32_t j = i - (R - (R >> L));
+    store_fe(&TW[i], load_fe_ro(&W[((size_t)j << L) << (log_n - S)]));
 }
+
+// Shared-memory slot of tile element i = row * C + col.  The two 16-byte halves of an element live in two planes;
+// within a plane the low three index bits are XORed with the next three, which makes every access pattern of the
+// rounds below conflict-free for 8 elements per thread (a quarter-warp touches eight distinct 16-byte bank groups
+// whether its lanes walk consecutive rows or rows 2, 4 or 8 apart; checked by enumeration for every tile shape).
+H2B_DI uint32_t tile_slot(uint32_t i) { return i ^ ((i >> 3) & 7u); }
+
+// Out of line: the fused input / output scalings of the domain transforms sit on paths a plain best_fft never takes,
+// and eight inlined copies of each would double the kernel's instruction footprint.
+static __device__ __noinline__ Fe fr_mul_ni(Fe a, Fe b) { return Fr::mul(a, b); }
 
 struct PassArgs {
     const Fe *in;
     Fe *out;
-    const Fe *W;
+    const Fe *W;    // all powers of omega (inter-pass twiddles)
+    const Fe *TW;   // inner twiddles of this pass, per level (ntt_pass_twiddles_kernel)
     uint32_t log_n, log_ns, last, q0, M;
+    uint32_t warp_sync;  // bit r set: the exchange after round r stays inside each warp (__syncwarp suffices)
 };
 
-// Rounds of a pass: 3 levels per round while possible (2 + 2 when four remain), the first round
-// reads global memory, the last one writes it, intermediate results live in shared memory.
-template <int S, int C, int NT, int LVL>
-H2B_DI void pass_rounds(const PassArgs &pa, const NttIo &io, uint4 *s_lo, uint4 *s_hi,
-                        const uint4 *t_lo, const uint4 *t_hi, uint32_t tid) {
-    constexpr int REM = S - LVL;
-    constexpr int RB = (REM >= 3 && REM != 4) ? 3 : (REM >= 2 ? 2 : 1);
-    constexpr bool FIRST = LVL == 0, LAST = LVL + RB == S;
-    constexpr uint32_t ST = (1u << S) >> (LVL + RB);
-    constexpr uint32_t GROUPS = ((1u << S) * C) >> RB;
-    for (uint32_t g = tid; g < GROUPS; g += NT) {
-        const uint32_t col = g % C, rest = g / C;
-        const uint32_t lo = rest % ST, hi = rest / ST;
-        const uint32_t row_base = hi * (ST << RB) + lo;
-        Fe a[1 << RB];
-        if (FIRST) {
+// 16-byte asynchronous global -> shared copies (LDGSTS): twiddles are fetched ahead of their use without holding
+// registers; .ca keeps the lines in L1 for the other blocks of the SM, which read the same tables.
+H2B_DI void cp_async16(void *smem_dst, const void *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+H2B_DI void cp_async_fe(uint4 *s_lo, uint4 *s_hi, uint32_t slot, const Fe *src) {
+    cp_async16(&s_lo[slot], src);
+    cp_async16(&s_hi[slot], reinterpret_cast<const uint4 *>(src) + 1);
+}
+H2B_DI void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+// One pass.  S = log2 radix, C = columns per tile, EL = log2 elements per thread, NT = threads per block
+// (NT * 2^EL >= 2^S * C; surplus threads only take part in the barriers), MINB = blocks per SM the register
+// allocation is held to.
+//
+// A thread keeps E = 2^EL tile elements in registers and the S levels run in rounds of EL levels on them; between
+// rounds the tile is exchanged through shared memory.  Round r works on the rows whose bits [s_r, s_r + EL) are the
+// register index (s_0 = S - EL: the largest strides first, decimation in frequency); after the first exchange the
+// sub-transforms of different warps are independent, so only that exchange needs a block barrier -- the later ones
+// are __syncwarp (the host works out which, `warp_sync`).  The loop over rounds is NOT unrolled: there is one copy of
+// the butterfly code whatever S is.  When EL does not divide S the last round is partial: it runs the last S mod EL
+// levels of the same code.
+//
+// Values stay in [0, 2N) between butterflies (x + y is brought back with one conditional subtraction of 2N,
+// x - y + 2N < 4N goes into the twiddle product as it is, and a Montgomery product of a value below 4N with a
+// canonical twiddle is below 2N without its final subtraction: N < 2^254); intermediate passes store such values
+// and only the last pass reduces to the canonical representative, so the results are bit-identical to the
+// reference's.
+//
+// No multiplication waits for a global load.  The twiddles of the first round (E - 1 per thread, each used once per
+// tile) are copied asynchronously into the thread's OWN tile slots, which are idle until the first exchange; those of
+// the later rounds (2^(S - EL) - 1 values shared by the whole block) into a small table behind the tile; the
+// inter-pass twiddles of the last round again into the thread's own slots, as soon as it has read them for the last
+// time.  All of them are then read with shared-memory latency.
+template <int S, int C, int EL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__restrict__ TW, uint32_t log_n,
+                uint32_t log_ns, uint32_t last, uint32_t warp_sync, NttIo io) {
+    constexpr int R = 1 << S, E = 1 << EL, TILE = R * C;
+    constexpr uint32_t GROUPS = TILE / E;
+    constexpr uint32_t LATE = (R >> EL) - 1;  // twiddles of the levels >= EL
+    extern __shared__ uint4 smem_u4[];
+    uint4 *s_lo = smem_u4;                   // low 16 bytes of the tile elements
+    uint4 *s_hi = smem_u4 + TILE;            // high 16 bytes
+    uint4 *tw_late = smem_u4 + 2 * TILE;     // TW[R - (R >> EL) ..): low halves, then (R >> EL entries on) high halves
+
+    const Fe *src = in + (size_t)blockIdx.y * io.bin;
+    Fe *dst = out + (size_t)blockIdx.y * io.bout;
+    const uint32_t M = 1u << (log_n - S);  // columns in the whole pass
+    const uint32_t q0 = blockIdx.x * C;
+    const uint32_t g = threadIdx.x;
+    const bool active = GROUPS >= NT || g < GROUPS;
+    const uint32_t col = g % C, rest = g / C;
+
+    // later rounds' twiddles -> shared table (visible to the block after the first exchange's barrier)
+    for (uint32_t i = g; i < 2 * LATE; i += NT)
+        cp_async16(&tw_late[(i >> 1) + (i & 1u) * (R >> EL)], reinterpret_cast<const uint4 *>(TW + (R - (R >> EL))) + i);
+
+    Fe a[E];
+    uint32_t lvl = 0;
+#pragma unroll 1
+    for (uint32_t r = 0; lvl < S; r++) {
+        const uint32_t er = min((uint32_t)EL, S - lvl);          // levels of this round
+        const uint32_t s = er < EL ? 0u : S - lvl - EL;           // register field = row bits [s, s + EL)
+        const uint32_t lo = rest & ((1u << s) - 1u), hi = rest >> s;
+        const uint32_t row_base = (hi << (s + EL)) | lo;
+        const bool final_round = lvl + er >= S;
+        if (active) {
+            if (r == 0) {
+                // first-round twiddles -> own slots: level q needs T_q[j], j = (t' << s) | lo, t' < E >> (q + 1);
+                // it goes to the slot of register number (E >> (q + 1)) - 1 + t'
 #pragma unroll
-            for (int t = 0; t < (1 << RB); t++) {
-                const uint32_t idx = pa.q0 + col + (row_base + t * ST) * pa.M;
-                Fe v;
-                if (idx < io.n_in) {
-                    v = load_fe(&pa.in[idx]);
-                    if (io.pro) {
-                        const uint32_t m3 = idx % 3;
-                        if (m3) v = Fr::mul(v, io.pro_c[m3]);
+                for (int q = 0; q < EL; q++) {
+                    const int half = E >> (q + 1);
+                    const Fe *T = TW + (R - (R >> q));
+#pragma unroll
+                    for (int tp = 0; tp < half; tp++) {
+                        const uint32_t j = ((uint32_t)tp << s) | lo;
+                        const uint32_t e = tile_slot((row_base + ((uint32_t)(half - 1 + tp) << s)) * C + col);
+                        cp_async_fe(s_lo, s_hi, e, &T[j]);
                     }
-                } else {
-                    v = Fr::zero();
                 }
-                a[t] = v;
-            }
-        } else {
+                // first round: straight from global memory (128-bit loads of C adjacent elements per row), with the
+                // fused input scaling (coset powers) and zero padding
 #pragma unroll
-            for (int t = 0; t < (1 << RB); t++) {
-                const uint32_t e = (row_base + t * ST) * C + col;
-                a[t] = fe_from_u4(s_lo[e], s_hi[e]);
+                for (int t = 0; t < E; t++) {
+                    const uint32_t idx = q0 + col + (row_base + ((uint32_t)t << s)) * M;
+                    Fe v;
+                    if (idx < io.n_in) {
+                        v = load_fe(&src[idx]);
+                        if (io.pro) {
+                            const uint32_t m3 = idx % 3;
+                            if (m3) v = fr_mul_ni(v, io.pro_c[m3]);
+                        }
+                    } else {
+                        v = Fr::zero();
+                    }
+                    a[t] = v;
+                }
+                cp_async_wait_all();
+            } else {
+#pragma unroll
+                for (int t = 0; t < E; t++) {
+                    const uint32_t e = tile_slot((row_base + ((uint32_t)t << s)) * C + col);
+                    a[t] = fe_from_u4(s_lo[e], s_hi[e]);
+                }
+                if (final_round && !last) {
+                    // inter-pass twiddles omega^(jp * K << log_ns) of this thread's outputs -> its own slots, which it
+                    // has just read for the last time; they arrive while the last butterflies run
+                    const uint32_t q = q0 + col, jp = q >> log_ns;
+#pragma unroll
+                    for (int t = 0; t < E; t++) {
+                        const uint32_t k = bitrev_s<S>(row_base + (uint32_t)t);
+                        const uint32_t ex = (jp * k) << log_ns;  // < N
+                        cp_async_fe(s_lo, s_hi, tile_slot((row_base + (uint32_t)t) * C + col), &W[ex]);
+                    }
+                }
+            }
+            // the last `er` of the EL static levels: static level q pairs registers t and t + (E >> (q + 1))
+#pragma unroll
+            for (int q = 0; q < EL; q++) {
+                if ((uint32_t)q + er >= (uint32_t)EL) {  // uniform
+                    const int half = E >> (q + 1);
+                    const uint32_t L = lvl + (uint32_t)q - ((uint32_t)EL - er);  // tile level of this static level
+                    // twiddle source: own slots in the first round, the shared table afterwards
+                    const uint4 *T = tw_late + ((R >> EL) - (R >> L));
+#pragma unroll
+                    for (int t = 0; t < E; t++) {
+                        if (t & half) continue;
+                        const Fe x = a[t], y = a[t + half];
+                        a[t] = Fr::add_2n(x, y);
+                        Fe d = Fr::sub_2n(x, y);  // in (0, 4N)
+                        const uint32_t tp = (uint32_t)(t & (half - 1));
+                        const uint32_t j = (tp << s) | lo;  // butterfly index mod its half-span
+                        if (j != 0) {
+                            Fe w;
+                            if (r == 0) {
+                                const uint32_t e = tile_slot((row_base + (((uint32_t)(half - 1) + tp) << s)) * C + col);
+                                w = fe_from_u4(s_lo[e], s_hi[e]);
+                            } else {
+                                w = fe_from_u4(T[j], T[j + (R >> EL)]);
+                            }
+                            d = Fr::mul_lazy(d, w);  // back in [0, 2N)
+                        } else {
+                            d = Fr::reduce_2n(d);
+                        }
+                        a[t + half] = d;
+                    }
+                }
             }
         }
-        dif_levels<RB>(a, lo, ST, LVL, t_lo, t_hi);
-        if (LAST) {
-            // ST == 1: the rows are row_base .. row_base + 2^RB - 1; row u holds output K = bitrev_S(u)
-            const uint32_t q = pa.q0 + col;
-            const uint32_t jp = q >> pa.log_ns, p = q & ((1u << pa.log_ns) - 1);
+        if (!active && r == 0) cp_async_wait_all();  // its share of the shared twiddle table
+        lvl += er;
+        if (lvl < S) {
+            if (active) {
 #pragma unroll
-            for (int t = 0; t < (1 << RB); t++) {
-                const uint32_t u = row_base + t * ST;
+                for (int t = 0; t < E; t++) {
+                    const uint32_t e = tile_slot((row_base + ((uint32_t)t << s)) * C + col);
+                    s_lo[e] = make_uint4(a[t].l[0], a[t].l[1], a[t].l[2], a[t].l[3]);
+                    s_hi[e] = make_uint4(a[t].l[4], a[t].l[5], a[t].l[6], a[t].l[7]);
+                }
+            }
+            // (the shared twiddle table is published by the first barrier: multi-warp blocks never skip it)
+            if (((warp_sync >> r) & 1u) && (r != 0 || NT == 32)) __syncwarp();
+            else __syncthreads();
+        } else if (active) {
+            // last round (s == 0): the registers are rows row_base .. row_base + E - 1; row u holds output K = bitrev_S(u)
+            const uint32_t q = q0 + col;
+            const uint32_t jp = q >> log_ns, p = q & ((1u << log_ns) - 1);
+            if (!last && r != 0) cp_async_wait_all();
+#pragma unroll
+            for (int t = 0; t < E; t++) {
+                const uint32_t u = row_base + (uint32_t)t;
                 const uint32_t k = bitrev_s<S>(u);
-                const uint32_t oidx = (jp << (pa.log_ns + S)) + p + (k << pa.log_ns);
+                const uint32_t oidx = (jp << (log_ns + S)) + p + (k << log_ns);
                 if (oidx >= io.n_out) continue;
                 Fe v = a[t];
-                if (!pa.last) {
-                    const uint32_t ex = (jp * k) << pa.log_ns;  // < N
-                    if (ex) v = Fr::mul(v, load_fe_ro(&pa.W[ex]));
+                if (!last) {
+                    const uint32_t ex = (jp * k) << log_ns;  // < N
+                    if (ex) {
+                        Fe w;
+                        if (r != 0) {
+                            const uint32_t e = tile_slot(u * C + col);
+                            w = fe_from_u4(s_lo[e], s_hi[e]);
+                        } else {
+                            w = load_fe_ro(&W[ex]);  // single-round tile: nothing to hide the load behind
+                        }
+                        v = Fr::mul_lazy(v, w);
+                    }
                 }
-                if (io.epi) v = Fr::mul(v, io.epi_c[oidx % 3]);
-                store_fe(&pa.out[oidx], v);
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < (1 << RB); t++) {
-                const uint32_t e = (row_base + t * ST) * C + col;
-                s_lo[e] = make_uint4(a[t].l[0], a[t].l[1], a[t].l[2], a[t].l[3]);
-                s_hi[e] = make_uint4(a[t].l[4], a[t].l[5], a[t].l[6], a[t].l[7]);
+                // intermediate passes hand their values on in [0, 2N); the last pass stores canonical ones
+                if (io.epi) v = fr_mul_ni(v, io.epi_c[oidx % 3]);
+                else if (last) v = Fr::reduce_once(v);
+                store_fe(&dst[oidx], v);
             }
         }
     }
-    if constexpr (!LAST) {
-        __syncthreads();
-        pass_rounds<S, C, NT, LVL + RB>(pa, io, s_lo, s_hi, t_lo, t_hi, tid);
-    }
-}
-
-// One pass.  S = log2 radix, C = columns per tile, NT = threads per block.
-template <int S, int C, int NT>
-__global__ void __launch_bounds__(NT)
-ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, uint32_t log_n, uint32_t log_ns,
-                uint32_t last, NttIo io) {
-    constexpr int R = 1 << S;
-    constexpr int TILE = R * C;
-    extern __shared__ uint4 smem_u4[];
-    uint4 *s_lo = smem_u4;              // low 16 bytes of tile elements  [R][C]
-    uint4 *s_hi = smem_u4 + TILE;       // high 16 bytes
-    uint4 *t_lo = smem_u4 + 2 * TILE;   // inner twiddles (omega^M)^t, t < R/2
-    uint4 *t_hi = t_lo + (R / 2 > 0 ? R / 2 : 1);
-
-    PassArgs pa;
-    pa.in = in + (size_t)blockIdx.y * io.bin;
-    pa.out = out + (size_t)blockIdx.y * io.bout;
-    pa.W = W;
-    pa.log_n = log_n; pa.log_ns = log_ns; pa.last = last;
-    pa.M = 1u << (log_n - S);           // columns in the whole pass
-    pa.q0 = blockIdx.x * C;
-    const uint32_t tid = threadIdx.x;
-
-    // inner twiddles: W[t * M]
-    for (uint32_t t = tid; t < R / 2; t += NT) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(&W[(size_t)t * pa.M]);
-        t_lo[t] = __ldg(p);
-        t_hi[t] = __ldg(p + 1);
-    }
-    __syncthreads();
-    pass_rounds<S, C, NT, 0>(pa, io, s_lo, s_hi, t_lo, t_hi, tid);
 }
 
 // a[i] *= c[i % m]  (parallelize-style elementwise maps: divide_by_vanishing_poly, log_n = 0 scaling)

@@ -245,7 +245,8 @@ int h2b_kernel_time_collect(double *total_ms, uint32_t *calls);
 
 /* ---- test hooks (element-wise device arithmetic, used by tests/ only) ---------------- */
 /* op: 0 mul, 1 add, 2 sub, 3 mul (portable 64-bit path), 4 inverse of a, 5 from_mont(a), 6 square of a,
- * 7 a*b + (a+b)*(a-b) and 8 a*b - b*a through the fused two-product multiply
+ * 7 a*b + (a+b)*(a-b) and 8 a*b - b*a through the fused two-product multiply, 9 lazy product (a < 4N as raw limbs,
+ * b < N), 10 lazy difference and 11 lazy sum (a, b < 2N as raw limbs) of the NTT butterflies, each brought back to [0, N)
  * field: 0 Fr, 1 Fq.  a, b, out: n x 4 u64 host buffers. */
 int h2b_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 /* out[i] = a[i] + b[i] on affine inputs (n x 8 u64) through the XYZZ mixed-add path -> n x 12 u64. */

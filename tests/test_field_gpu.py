@@ -113,3 +113,38 @@ def test_g1_mixed_add_special_cases(h2b, spec, href):
         assert spec.projective_array_to_affine(out[i]) == spec.g1_add(a[i], b[i]), i
     # identity is reported as (0, R, 0) like G1::identity()
     assert out[2][8:].sum() == 0 and (out[2][4:8] == spec.ints_to_array([1], spec.Q_MOD)[0]).all()
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_lazy_butterfly_arithmetic(h2b, spec, field):
+    """The NTT butterflies keep values in [0, 2N) and multiply values below 4N by canonical twiddles without the final
+    subtraction (field.cuh: mul_lazy, add_2n, sub_2n, reduce_2n).  Raw (non-canonical) limb patterns up to the
+    bounds the kernel can produce, including the extremes, must give the same field elements as big integers."""
+    mod = spec.R_MOD if field == 0 else spec.Q_MOD
+    rinv = pow(1 << 256, -1, mod)
+    g = spec.SplitMix64(77 + field)
+
+    def raw(vals):
+        return np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)] for v in vals], dtype=np.uint64)
+
+    def rnd(bound):
+        return sum(g.next() << (64 * i) for i in range(4)) % bound
+
+    n = 4096
+    # product: a < 4N raw, b < N raw -> a * b * R^-1 mod N
+    av = [4 * mod - 1, 4 * mod - 2, 3 * mod, 2 * mod, 2 * mod - 1, mod, 0, 1, 4 * mod - 3]
+    bv = [mod - 1, mod - 2, mod - 1, mod - 1, 1, mod - 1, mod - 1, 0, mod - 1]
+    while len(av) < n:
+        av.append(rnd(4 * mod))
+        bv.append(rnd(mod))
+    assert max(av) < min(4 * mod, 1 << 256)
+    got = _field_op(h2b, field, 9, raw(av), raw(bv))
+    assert (got == raw([x * y * rinv % mod for x, y in zip(av, bv)])).all()
+    # difference / sum: a, b < 2N raw
+    xv = [2 * mod - 1, 0, 2 * mod - 1, 0, mod, mod - 1, 1, 2 * mod - 2]
+    yv = [0, 2 * mod - 1, 2 * mod - 1, 0, mod, mod, 2 * mod - 1, 1]
+    while len(xv) < n:
+        xv.append(rnd(2 * mod))
+        yv.append(rnd(2 * mod))
+    assert (_field_op(h2b, field, 10, raw(xv), raw(yv)) == raw([(x - y) % mod for x, y in zip(xv, yv)])).all()
+    assert (_field_op(h2b, field, 11, raw(xv), raw(yv)) == raw([(x + y) % mod for x, y in zip(xv, yv)])).all()
