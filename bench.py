@@ -403,10 +403,14 @@ def run_b200(args) -> None:
     if rank == 0 and not args.no_ntt:
         ntt = bench_ntt(args, torch, L, _ffi, arithmetic, h2b, stream, float(imad.value))
 
-    replay = evalh = None
+    replay = evalh = poseidon = None
     if rank == 0 and world == 1 and not args.no_cpu:
         replay = bench_proof_replay(args, h2b, _ffi)
         evalh = bench_evaluate_h(args, torch, h2b)
+        try:
+            poseidon = bench_poseidon_proof(args)
+        except Exception as exc:  # reported, never fatal for the headline line
+            poseidon = {"error": repr(exc)}
 
     # ---- ONE process driving all N devices through the C ABI (h2b_init_devices): the other ranks park on the
     # host while rank 0 re-initialises the library over every GPU of the job
@@ -479,6 +483,7 @@ def run_b200(args) -> None:
             "weak": weak,
             "single_process": single,
             "ntt": ntt,
+            "poseidon_proof": poseidon,
             "proof_replay": replay,
             "evaluate_h": evalh,
         }
@@ -741,6 +746,39 @@ def bench_proof_replay(args, h2b, _ffi) -> dict:
             "cpu_ms": cpu_ms, "cpu_threads": threads, "commitments_equal": bool(same)}
 
 
+def bench_poseidon_proof(args) -> dict | None:
+    """"Poseidon proof ms" of the metric, on REAL proofs: the reference's own compiled prover (its Poseidon W3/R2
+    circuit, /root/reference/circuits/src/poseidon_circuit.rs, through wasm_generate_proof) runs under the in-repo
+    WebAssembly harness with every best_multiexp / best_fft call of keygen + create_proof answered by libh2b200.so, and
+    again with the calls answered by the CPU port on all host threads.  Both proofs are checked byte for byte against
+    each other and accepted by the reference verifier.  `hot_ms` is the time inside those calls (the path this
+    repository replaces); the rest of the prover is the reference's interpreted code and is not timed here.
+    One-shot processes: the GPU figure includes first-use costs (kernel loading, workspace growth)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "wasm"))
+    try:
+        import harness
+    except Exception:
+        return None
+    if not harness.available():
+        return {"unavailable": "reference wasm (oracle/_ref) or harness binary not present on this box"}
+    out = {"what": "hot-path (best_multiexp + best_fft) time inside real Poseidon proofs of the reference prover, "
+                   "keygen_vk + keygen_pk + create_proof (wasm.rs:76-122 re-runs keygen on every call)", "runs": []}
+    for k in args.poseidon_k:
+        mg, sg = harness.run("poseidon", k, 4242, hot="gpu")
+        mc, sc = harness.run("poseidon", k, 4242, hot="cpu")
+        out["runs"].append({
+            "k": k, "proof_bytes": len(mg["proof"]), "proofs_identical": mg["proof"] == mc["proof"],
+            "verified_by_reference_verifier": bool(mg["verify_ok"] == 1 and mc["verify_ok"] == 1),
+            "msm_calls": sg["msm_calls_prove"], "fft_calls": sg["fft_calls_prove"],
+            "gpu_hot_ms": sg["hot_msm_ms_prove"] + sg["hot_fft_ms_prove"], "gpu_msm_ms": sg["hot_msm_ms_prove"],
+            "gpu_fft_ms": sg["hot_fft_ms_prove"], "gpu_srs_register_ms": sg["srs_register_ms"],
+            "gpu_srs_registered": sg["srs_registered"],
+            "cpu_hot_ms": sc["hot_msm_ms_prove"] + sc["hot_fft_ms_prove"], "cpu_msm_ms": sc["hot_msm_ms_prove"],
+            "cpu_fft_ms": sc["hot_fft_ms_prove"], "cpu_threads": sc["cpu_threads"],
+            "interpreted_rest_s": sg["prove_s"] - (sg["hot_msm_ms_prove"] + sg["hot_fft_ms_prove"]) * 1e-3})
+    return out
+
+
 def bench_evaluate_h(args, torch, h2b) -> dict:
     """Device time of the quotient numerator (h2b_dev_evaluate_h) for a circuit shaped like the reference's
     arithmetic circuit (one degree-3 gate over 3 advice + 5 fixed columns, 4 permutation columns in 4 chunks) at
@@ -875,6 +913,8 @@ def main() -> None:
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling measurement at N > 1")
     ap.add_argument("--no-single-process", action="store_true", help="skip the one-process N-device run at N > 1")
     ap.add_argument("--proof-k", type=int, default=14, help="rows (log2) of the proof-shaped replay")
+    ap.add_argument("--poseidon-k", type=lambda v: [int(x) for x in v.split(",") if x], default=[10],
+                    help="rows (log2) of the real Poseidon proofs run through the reference prover (comma list; empty = skip)")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
