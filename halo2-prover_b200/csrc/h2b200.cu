@@ -608,7 +608,9 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
                       Projective *d_out) {
     cudaStream_t s = g->stream;
     if (n == 0) return msm_identity_out(d_out, s);
-    uint32_t chunks = n >= g->e2e_min_n ? g->e2e_chunks : 1;
+    // pieces: every piece pays the fixed latency of a sort + fix-up pass (~0.3 ms), so below 2^23 points -- a device's
+    // share of a 2^24-point commit on 4 or 8 GPUs -- two pieces hide the copy better than four
+    uint32_t chunks = n >= g->e2e_min_n ? (n < ((size_t)1 << 23) ? std::min(2u, g->e2e_chunks) : g->e2e_chunks) : 1;
     Fe *ds;
     Affine *db = nullptr;
     TRY(get_buf(BUF_SCALARS, n * sizeof(Fe), (void **)&ds));
@@ -1239,7 +1241,7 @@ int stage_in(BufId id, const void *host, size_t bytes, void **dev) {
 // ============================================================================== C ABI
 extern "C" {
 
-uint32_t h2b_abi_version(void) { return 1; }
+uint32_t h2b_abi_version(void) { return 2; }
 const char *h2b_last_error(void) { return g_err.c_str(); }
 
 // One context per device: stream, copy stream, workspace, caches, tunables from the environment.
@@ -2139,6 +2141,63 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
             if (a->perm_kind[c] > 2 || a->perm_index[c] >= lim) return fail(H2B_ERR_ARG, "evaluate_h: permutation column out of range");
         }
     }
+    // Intermediates are renumbered by liveness: a slot is free again once its value has been read for the last
+    // time, so the working set of a row is the graph's width, not its length (upstream's GraphEvaluator numbers every
+    // calculation; a few hundred of them at extended_k = 22 would otherwise need tens of GiB of scratch).
+    std::vector<uint64_t> calcs(a->calcs, a->calcs + a->calc_words);
+    uint32_t slots = 0;
+    {
+        const uint32_t NI = a->num_intermediates, NC = a->num_calcs;
+        std::vector<size_t> at(NC);                 // word offset of every calculation
+        std::vector<uint32_t> last_use(NI, 0);      // last calculation that reads intermediate t (as numbered by the caller)
+        size_t w = 0;
+        auto nsrc_of = [&](uint64_t hdr) -> size_t {
+            const uint32_t op = (uint32_t)(hdr & 0xff), nparts = (uint32_t)(hdr >> 40);
+            return op == CALC_HORNER ? 2 + (size_t)nparts : (op <= CALC_MUL ? 2 : 1);
+        };
+        for (uint32_t c = 0; c < NC; c++) {
+            at[c] = w;
+            const size_t ns = nsrc_of(calcs[w]);
+            for (size_t k = 1; k <= ns; k++)
+                if ((calcs[w + k] & 0xff) == VS_INTERMEDIATE) last_use[(uint32_t)((calcs[w + k] >> 8) & 0xfffffff)] = c;
+            w += 1 + ns;
+        }
+        std::vector<int64_t> slot_of(NI, -1);
+        std::vector<uint32_t> free_slots;
+        for (uint32_t c = 0; c < NC; c++) {
+            const size_t o = at[c], ns = nsrc_of(calcs[o]);
+            std::vector<uint32_t> dying;
+            for (size_t k = 1; k <= ns; k++) {
+                uint64_t &src = calcs[o + k];
+                if ((src & 0xff) != VS_INTERMEDIATE) continue;
+                const uint32_t t = (uint32_t)((src >> 8) & 0xfffffff);
+                if (slot_of[t] < 0) return fail(H2B_ERR_ARG, "evaluate_h: intermediate read before it is written");
+                src = (src & ~((uint64_t)0xfffffff << 8)) | ((uint64_t)slot_of[t] << 8);
+                if (last_use[t] == c) dying.push_back(t);
+            }
+            for (uint32_t t : dying)
+                if (slot_of[t] >= 0) {
+                    free_slots.push_back((uint32_t)slot_of[t]);
+                    slot_of[t] = -1;
+                }
+            const uint32_t target = (uint32_t)((calcs[o] >> 8) & 0xffffffffu);
+            if (slot_of[target] >= 0) free_slots.push_back((uint32_t)slot_of[target]);  // rewritten: the old value is dead
+            uint32_t sl;
+            if (!free_slots.empty()) {
+                sl = free_slots.back();
+                free_slots.pop_back();
+            } else {
+                sl = slots++;
+            }
+            slot_of[target] = sl;
+            calcs[o] = (calcs[o] & ~((uint64_t)0xffffffffu << 8)) | ((uint64_t)sl << 8);
+            if (last_use[target] <= c) {  // never read afterwards (the row's value is taken from the last calculation)
+                free_slots.push_back(sl);
+                slot_of[target] = -1;
+            }
+        }
+    }
+    const bool local = slots <= kLocalSlots;
     CU(cudaSetDevice(g->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     Scope sc;
@@ -2156,7 +2215,7 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
     const size_t o_fixed = put(a->fixed, a->num_fixed * sizeof(void *)), o_adv = put(a->advice, a->num_advice * sizeof(void *));
     const size_t o_inst = put(a->instance, a->num_instance * sizeof(void *));
     const size_t o_chal = put(a->challenges, (size_t)a->num_challenges * 32), o_const = put(a->constants, (size_t)a->num_constants * 32);
-    const size_t o_rot = put(a->rotations, a->num_rotations * sizeof(int32_t)), o_calc = put(a->calcs, a->calc_words * 8);
+    const size_t o_rot = put(a->rotations, a->num_rotations * sizeof(int32_t)), o_calc = put(calcs.data(), calcs.size() * 8);
     std::vector<const void *> cols(P);
     for (uint32_t c = 0; c < P; c++)
         cols[c] = a->perm_kind[c] == 0 ? a->advice[a->perm_index[c]] : (a->perm_kind[c] == 1 ? a->fixed[a->perm_index[c]] : a->instance[a->perm_index[c]]);
@@ -2164,10 +2223,10 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
     const size_t o_z = put(a->z_cosets, sets * sizeof(void *));
     uint64_t *dblob;
     TRY(get_buf(BUF_EVALH, blob.size() * 8 + 8, (void **)&dblob));
+    // (a copy from pageable memory has left the source buffer when cudaMemcpyAsync returns: `blob` may go out of scope)
     if (!blob.empty()) CU(cudaMemcpyAsync(dblob, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice, s));
-    Fe *scratch;
-    TRY(get_buf(BUF_EVALH_SCRATCH, (size_t)std::max(a->num_intermediates, 1u) * size * sizeof(Fe), (void **)&scratch));
-    if (!lookup) CU(cudaMemsetAsync(d_values, 0, (size_t)size * sizeof(Fe), s));
+    Fe *scratch = nullptr;
+    if (!local) TRY(get_buf(BUF_EVALH_SCRATCH, (size_t)slots * size * sizeof(Fe), (void **)&scratch));
     EvalGates eg;
     eg.fixed = (const Fe *const *)(dblob + o_fixed);
     eg.advice = (const Fe *const *)(dblob + o_adv);
@@ -2194,23 +2253,25 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
         el.l0 = (const Fe *)a->l0;
         el.l_last = (const Fe *)a->l_last;
         el.l_active = (const Fe *)a->l_active_row;
-        evalh_lookup_kernel<<<blocks, 128, 0, s>>>(eg, el, (Fe *)d_values);
+        if (local) evalh_lookup_kernel<true><<<blocks, 128, 0, s>>>(eg, el, (Fe *)d_values);
+        else evalh_lookup_kernel<false><<<blocks, 128, 0, s>>>(eg, el, (Fe *)d_values);
         LAUNCHED();
-        CU(cudaStreamSynchronize(s));
         return H2B_OK;
     }
-    evalh_gates_kernel<<<blocks, 128, 0, s>>>(eg, (Fe *)d_values);
-    LAUNCHED();
+    EvalPerm ep;
+    memset(&ep, 0, sizeof ep);
     if (P) {
         static const uint32_t kDeltaMont[8] = {0xefd78855u, 0x9a0c322bu, 0x249b563cu, 0x46e82d14u,
                                                0xe0b0b7a7u, 0x5983a663u, 0xaaa111adu, 0x22ab452bu};  // Fr::DELTA = 7^(2^28)
-        EvalPerm ep;
+        TwEntry *tw;  // extended_omega^i: the table the extended-domain transforms use anyway
+        TRY(get_twiddles(d->extended_omega, d->extended_k, s, &tw));
         ep.columns = (const Fe *const *)(dblob + o_cols);
         ep.sigma = (const Fe *const *)(dblob + o_sig);
         ep.z = (const Fe *const *)(dblob + o_z);
         ep.l0 = (const Fe *)a->l0;
         ep.l_last = (const Fe *)a->l_last;
         ep.l_active = (const Fe *)a->l_active_row;
+        ep.ext_pows = tw->W;
         ep.num_columns = P;
         ep.chunk_len = a->chunk_len;
         ep.num_sets = sets;
@@ -2220,15 +2281,12 @@ static int evalh_run(const h2b_domain *d, const h2b_eval_h *a, const EvalhLookup
         ep.beta = eg.beta;
         ep.gamma = eg.gamma;
         ep.y = eg.y;
-        memcpy(&ep.zeta, d->g_coset, 32);
-        memcpy(&ep.ext_omega, d->extended_omega, 32);
         memcpy(&ep.delta, kDeltaMont, 32);
-        evalh_permutation_kernel<<<blocks, 128, 0, s>>>(ep, (Fe *)d_values);
-        LAUNCHED();
+        memcpy(&ep.zeta, d->g_coset, 32);
     }
-    // the staging blob lives on this frame: the copy above has consumed it once the stream reaches the kernels;
-    // wait so that a pageable-source copy cannot outlive the vector
-    CU(cudaStreamSynchronize(s));
+    if (local) evalh_fused_kernel<true><<<blocks, 128, 0, s>>>(eg, ep, (Fe *)d_values, a->flags & H2B_EVALH_ACCUMULATE ? 1u : 0u);
+    else evalh_fused_kernel<false><<<blocks, 128, 0, s>>>(eg, ep, (Fe *)d_values, a->flags & H2B_EVALH_ACCUMULATE ? 1u : 0u);
+    LAUNCHED();
     return H2B_OK;
 }
 

@@ -157,8 +157,9 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__res
     const uint32_t col = g % C, rest = g / C;
 
     // later rounds' twiddles -> shared table (visible to the block after the first exchange's barrier)
-    for (uint32_t i = g; i < 2 * LATE; i += NT)
-        cp_async16(&tw_late[(i >> 1) + (i & 1u) * (R >> EL)], reinterpret_cast<const uint4 *>(TW + (R - (R >> EL))) + i);
+    if constexpr (LATE > 0)
+        for (uint32_t i = g; i < 2 * LATE; i += NT)
+            cp_async16(&tw_late[(i >> 1) + (i & 1u) * (R >> EL)], reinterpret_cast<const uint4 *>(TW + (R - (R >> EL))) + i);
 
     Fe a[E];
     uint32_t lvl = 0;

@@ -58,7 +58,11 @@ class _EvalH(C.Structure):
         ("perm_kind", C.POINTER(C.c_uint8)), ("perm_index", C.POINTER(C.c_uint32)),
         ("sigma_cosets", C.POINTER(C.c_void_p)), ("z_cosets", C.POINTER(C.c_void_p)),
         ("l0", C.c_void_p), ("l_last", C.c_void_p), ("l_active_row", C.c_void_p),
+        ("flags", C.c_uint32),
     ]
+
+
+EVALH_ACCUMULATE = 1  # start from the values already in values_t (PreviousValue threaded through several circuits)
 
 
 @dataclass
@@ -120,11 +124,12 @@ def _make_args(graph: GraphEvaluator, fixed, advice, instance, challenges, beta,
 
 
 def dev_evaluate_h(domain, graph: GraphEvaluator, fixed, advice, instance, challenges: np.ndarray, beta, gamma, theta, y,
-                   perm: PermutationData | None, values_t, stream=None) -> None:
+                   perm: PermutationData | None, values_t, stream=None, accumulate: bool = False) -> None:
     """Evaluator::evaluate_h (custom gates + permutation argument) into ``values_t`` ((2^extended_k, 4) int64 cuda
     tensor).  Columns are cuda tensors holding extended cosets; scalars are (4,) uint64 Montgomery limbs."""
     from .arithmetic import _stream_ptr
     a, keep = _make_args(graph, fixed, advice, instance, challenges, beta, gamma, theta, y, perm)
+    a.flags = EVALH_ACCUMULATE if accumulate else 0
     _ffi.check(_ffi.lib().h2b_dev_evaluate_h(C.byref(domain._d), C.byref(a), C.c_void_p(values_t.data_ptr()), _stream_ptr(stream)))
 
 

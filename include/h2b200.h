@@ -64,7 +64,7 @@ void h2b_shutdown(void);
 /* Human-readable description of the last error on the calling thread's last call. */
 const char *h2b_last_error(void);
 /* ABI version of this header. */
-uint32_t h2b_abi_version(void);
+uint32_t h2b_abi_version(void);   /* 2: h2b_eval_h.flags, h2b_init_devices */
 
 /* ---- MSM ------------------------------------------------------------------------- */
 /* best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1
@@ -199,8 +199,15 @@ typedef struct h2b_eval_h {
     const void *const *sigma_cosets;      /* DEVICE pointers: pk.permutation.cosets */
     const void *const *z_cosets;          /* DEVICE pointers: permutation_product_coset of every chunk */
     const void *l0, *l_last, *l_active_row; /* DEVICE pointers */
+    uint32_t flags;                         /* H2B_EVALH_* */
 } h2b_eval_h;
-/* d_values: 2^extended_k x 32 B in HBM, overwritten (upstream starts from domain.empty_extended()). */
+/* flags: start from the values already in d_values (PreviousValue of the graph = the running value upstream threads
+ * through the circuits of one create_proof) instead of from zero. */
+#define H2B_EVALH_ACCUMULATE 1u
+/* d_values: 2^extended_k x 32 B in HBM, overwritten (upstream starts from domain.empty_extended()) unless
+ * H2B_EVALH_ACCUMULATE is set.  Gates and permutation argument run as ONE pass over the rows; a graph's intermediates
+ * are renumbered by liveness on the host and live in a per-thread array (an HBM scratch of live-slots x 2^extended_k
+ * elements is used only when more than 40 are live at once). */
 int h2b_dev_evaluate_h(const h2b_domain *d, const h2b_eval_h *a, void *d_values, void *stream);
 /* One lookup argument folded into d_values after h2b_dev_evaluate_h (evaluation.rs, "Lookup constraints"; call once
  * per lookup, in cs.lookups order).  `a` carries the column tables, the scalars, l0 / l_last / l_active_row and, as

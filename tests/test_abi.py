@@ -24,7 +24,7 @@ def test_library_exports_every_symbol():
     L = _ffi.lib()
     for name in _header_functions():
         assert hasattr(L, name), name
-    assert L.h2b_abi_version() == 1
+    assert L.h2b_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
