@@ -801,21 +801,22 @@ uint32_t ntt_warp_sync_mask(uint32_t S, uint32_t C, uint32_t EL) {
     return mask;
 }
 
-template <int S, int C, int EL, int NT, int MINB = 1>
+template <int S, int C, int EL, int NT, int MINB = 1, int VAR = 0>
 int launch_pass(const Fe *in, Fe *out, const Fe *W, const Fe *TW, uint32_t log_n, uint32_t log_ns, bool last,
                 const NttIo &io, cudaStream_t s, uint32_t batch) {
     static_assert(S >= EL && S <= 10, "a round needs EL levels; tiles hold at most 2^10 rows");
     constexpr int R = 1 << S;
-    const size_t smem = ((size_t)2 * R * C + 2 * (R >> EL)) * sizeof(uint4);  // tile + the later rounds' twiddles
-    if (smem > 48 * 1024 && !g->attr_done.count((const void *)ntt_pass_kernel<S, C, EL, NT, MINB>)) {
-        CU(cudaFuncSetAttribute(ntt_pass_kernel<S, C, EL, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    size_t smem = ((size_t)2 * R * C + 2 * (R >> EL)) * sizeof(uint4);  // tile + the later rounds' twiddles
+    if (VAR == 1) smem += (size_t)2 * R * C * sizeof(uint4) + 16;           // + the TMA staging area and its mbarrier
+    if (smem > 48 * 1024 && !g->attr_done.count((const void *)ntt_pass_kernel<S, C, EL, NT, MINB, VAR>)) {
+        CU(cudaFuncSetAttribute(ntt_pass_kernel<S, C, EL, NT, MINB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-        g->attr_done.insert((const void *)ntt_pass_kernel<S, C, EL, NT, MINB>);
+        g->attr_done.insert((const void *)ntt_pass_kernel<S, C, EL, NT, MINB, VAR>);
     }
     const uint32_t M = 1u << (log_n - S);
     const uint32_t blocks = M / C;
     if (blocks == 0) return fail(H2B_ERR_ARG, "ntt: tile wider than the pass");
-    ntt_pass_kernel<S, C, EL, NT, MINB><<<dim3(blocks, batch), NT, smem, s>>>(in, out, W, TW, log_n, log_ns, last ? 1u : 0u,
+    ntt_pass_kernel<S, C, EL, NT, MINB, VAR><<<dim3(blocks, batch), NT, smem, s>>>(in, out, W, TW, log_n, log_ns, last ? 1u : 0u,
                                                                       ntt_warp_sync_mask(S, C, EL), io);
     LAUNCHED();
     return H2B_OK;
@@ -825,7 +826,7 @@ int launch_pass(const Fe *in, Fe *out, const Fe *W, const Fe *TW, uint32_t log_n
 // 2^TL elements with 2^EL elements per thread: TL = 10 is the throughput shape (EL = 3 / 2 / 1 on 128 / 256 / 512
 // threads), TL = 9 and 8 on 128 threads give more and smaller blocks to transforms that would otherwise leave most
 // SMs idle (those are latency-bound, not throughput-bound).
-extern int g_ntt_dense;
+extern int g_ntt_dense, g_ntt_variant;
 int dispatch_pass(uint32_t S, uint32_t EL, uint32_t TL, bool single, const Fe *in, Fe *out, const Fe *W, const Fe *TW,
                   uint32_t log_n, uint32_t log_ns, bool last, const NttIo &io, cudaStream_t s, uint32_t batch) {
 #define H2B_PASS(S_, C_, EL_, NT_) return launch_pass<S_, C_, EL_, NT_>(in, out, W, TW, log_n, log_ns, last, io, s, batch)
@@ -855,6 +856,11 @@ int dispatch_pass(uint32_t S, uint32_t EL, uint32_t TL, bool single, const Fe *i
     } else if (TL == 10 && EL == 3) {
         if (g_ntt_dense) { H2B_TILE10(3, 128, 5) } else { H2B_TILE10(3, 128, 4) }
     } else if (TL == 10 && EL == 2) {
+        // measured alternatives (H2B_NTT_VARIANT): 1 = TMA bulk staging of the first round (plain transforms), 2 = shuffle exchanges
+        const bool plain = !io.pro && io.n_in == (1u << log_n);
+        if (g_ntt_variant == 1 && plain && S == 10) return launch_pass<10, 1, 2, 256, 3, 1>(in, out, W, TW, log_n, log_ns, last, io, s, batch);
+        if (g_ntt_variant == 1 && plain && S == 8) return launch_pass<8, 4, 2, 256, 3, 1>(in, out, W, TW, log_n, log_ns, last, io, s, batch);
+        if (g_ntt_variant == 2 && S == 10) return launch_pass<10, 1, 2, 256, 3, 2>(in, out, W, TW, log_n, log_ns, last, io, s, batch);
         if (g_ntt_dense) { H2B_TILE10(2, 256, 3) } else { H2B_TILE10(2, 256, 2) }
     } else if (TL == 10 && EL == 1) {
         H2B_TILE10(1, 512, 2)
@@ -887,6 +893,7 @@ int g_ntt_el_big = 2;           // elements per thread (log2) of the 2^10-elemen
                                 // 3.53 ms; 8 per thread on 128 threads, 4 blocks (16 warps) 0.220 / 0.919 / 3.62; 2 per thread on 512
                                 // threads (32 warps, but ten exchanges) 0.225 / 0.955 / 4.05
 int g_ntt_tile = 0;             // forced tile size as log2, 8..10 (H2B_NTT_TILE); 0 = by size
+int g_ntt_variant = 0;          // 0 product path, 1 TMA-staged first round, 2 shuffle exchanges (H2B_NTT_VARIANT; A/B only)
 int g_ntt_dense = 1;            // 1: registers held to 5 (EL = 3) / 3 (EL = 2) blocks per SM instead of 4 / 2 (H2B_NTT_DENSE)
 
 // Transform `src` (n_in valid elements of a 2^log_n domain) into `dst`; `dst` may equal `src`.
@@ -1341,6 +1348,8 @@ static int init_locked(const int *devices, int count) {
     if (sm && atoi(sm) >= 8 && atoi(sm) <= 30) g_shard_min_n = (size_t)1 << atoi(sm);
     const char *el = getenv("H2B_NTT_EL_BIG");
     if (el && atoi(el) >= 1 && atoi(el) <= 3) g_ntt_el_big = atoi(el);
+    const char *nv = getenv("H2B_NTT_VARIANT");
+    if (nv) g_ntt_variant = atoi(nv);
     const char *dn = getenv("H2B_NTT_DENSE");
     if (dn) g_ntt_dense = atoi(dn) != 0;
     const char *tl = getenv("H2B_NTT_TILE");

@@ -113,6 +113,62 @@ H2B_DI void cp_async_fe(uint4 *s_lo, uint4 *s_hi, uint32_t slot, const Fe *src) 
 }
 H2B_DI void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
+// ---- the two mechanisms BASELINE.json's north_star names, as measured alternatives (VAR below)
+// TMA (cp.async.bulk, SASS UBLKCP) staging of the first round's tile: one bulk copy per tile row into a linear
+// staging area, completion counted by an mbarrier.
+H2B_DI void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+H2B_DI void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+H2B_DI void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+H2B_DI void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+// Warp-shuffle exchange between two rounds of 4 elements per thread: the 2-bit register index is transposed with the
+// 2-bit lane field at bit b (element t of the lane with field m goes to register m of the lane with field t).
+H2B_DI void shfl_exchange4(Fe (&a)[4], uint32_t b) {
+    const uint32_t m = (threadIdx.x >> b) & 3u;
+    Fe o[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) o[t] = a[t];
+#pragma unroll
+    for (int d = 1; d < 4; d++) {
+        const uint32_t pick = m ^ (uint32_t)d;  // the register this lane sends, and the one it receives into
+        Fe send;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            send.l[i] = pick == 0 ? a[0].l[i] : (pick == 1 ? a[1].l[i] : (pick == 2 ? a[2].l[i] : a[3].l[i]));
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t r = __shfl_xor_sync(0xffffffffu, send.l[i], d << b);
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (pick == (uint32_t)t) o[t].l[i] = r;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) a[t] = o[t];
+}
+
 // One pass.  S = log2 radix, C = columns per tile, EL = log2 elements per thread, NT = threads per block
 // (NT * 2^EL >= 2^S * C; surplus threads only take part in the barriers), MINB = blocks per SM the register
 // allocation is held to.
@@ -136,7 +192,9 @@ H2B_DI void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.asy
 // the later rounds (2^(S - EL) - 1 values shared by the whole block) into a small table behind the tile; the
 // inter-pass twiddles of the last round again into the thread's own slots, as soon as it has read them for the last
 // time.  All of them are then read with shared-memory latency.
-template <int S, int C, int EL, int NT, int MINB>
+// VAR: 0 = the product path; 1 = first-round tile staged by TMA bulk copies (plain transforms only); 2 = warp-local
+// exchanges by shuffles instead of shared memory (4 elements per thread, single-column tiles only).
+template <int S, int C, int EL, int NT, int MINB, int VAR = 0>
 __global__ void __launch_bounds__(NT, MINB)
 ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__restrict__ TW, uint32_t log_n,
                 uint32_t log_ns, uint32_t last, uint32_t warp_sync, NttIo io) {
@@ -147,6 +205,8 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__res
     uint4 *s_lo = smem_u4;                   // low 16 bytes of the tile elements
     uint4 *s_hi = smem_u4 + TILE;            // high 16 bytes
     uint4 *tw_late = smem_u4 + 2 * TILE;     // TW[R - (R >> EL) ..): low halves, then (R >> EL entries on) high halves
+    uint4 *stage = tw_late + 2 * (R >> EL);  // VAR 1: the tile as TMA delivers it, [row][col] x 32 bytes, then the mbarrier
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + 2 * TILE);
 
     const Fe *src = in + (size_t)blockIdx.y * io.bin;
     Fe *dst = out + (size_t)blockIdx.y * io.bout;
@@ -161,8 +221,15 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__res
         for (uint32_t i = g; i < 2 * LATE; i += NT)
             cp_async16(&tw_late[(i >> 1) + (i & 1u) * (R >> EL)], reinterpret_cast<const uint4 *>(TW + (R - (R >> EL))) + i);
 
+    if constexpr (VAR == 1) {
+        if (g == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (g == 0) mbar_expect_tx(mbar, (uint32_t)(TILE * sizeof(Fe)));
+    }
+
     Fe a[E];
     uint32_t lvl = 0;
+    bool in_regs = false;  // VAR 2: the next round's elements are already in the registers (shuffle exchange)
 #pragma unroll 1
     for (uint32_t r = 0; lvl < S; r++) {
         const uint32_t er = min((uint32_t)EL, S - lvl);          // levels of this round
@@ -185,10 +252,26 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__res
                         cp_async_fe(s_lo, s_hi, e, &T[j]);
                     }
                 }
+                if constexpr (VAR == 1) {
+                    // one bulk copy per tile row (C x 32 bytes), issued by the thread that holds the row's first column
+                    if (col == 0) {
+#pragma unroll
+                        for (int t = 0; t < E; t++) {
+                            const uint32_t row = row_base + ((uint32_t)t << s);
+                            bulk_g2s(stage + 2 * row * C, &src[q0 + (size_t)row * M], (uint32_t)(C * sizeof(Fe)), mbar);
+                        }
+                    }
+                    mbar_wait(mbar, 0);
+#pragma unroll
+                    for (int t = 0; t < E; t++) {
+                        const uint32_t e = (row_base + ((uint32_t)t << s)) * C + col;
+                        a[t] = fe_from_u4(stage[2 * e], stage[2 * e + 1]);
+                    }
+                }
                 // first round: straight from global memory (128-bit loads of C adjacent elements per row), with the
                 // fused input scaling (coset powers) and zero padding
 #pragma unroll
-                for (int t = 0; t < E; t++) {
+                for (int t = 0; t < E && VAR != 1; t++) {
                     const uint32_t idx = q0 + col + (row_base + ((uint32_t)t << s)) * M;
                     Fe v;
                     if (idx < io.n_in) {
@@ -204,10 +287,12 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__res
                 }
                 cp_async_wait_all();
             } else {
+                if (!in_regs) {
 #pragma unroll
-                for (int t = 0; t < E; t++) {
-                    const uint32_t e = tile_slot((row_base + ((uint32_t)t << s)) * C + col);
-                    a[t] = fe_from_u4(s_lo[e], s_hi[e]);
+                    for (int t = 0; t < E; t++) {
+                        const uint32_t e = tile_slot((row_base + ((uint32_t)t << s)) * C + col);
+                        a[t] = fe_from_u4(s_lo[e], s_hi[e]);
+                    }
                 }
                 if (final_round && !last) {
                     // inter-pass twiddles omega^(jp * K << log_ns) of this thread's outputs -> its own slots, which it
@@ -256,6 +341,18 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__res
         }
         if (!active && r == 0) cp_async_wait_all();  // its share of the shared twiddle table
         lvl += er;
+        if constexpr (VAR == 2 && EL == 2 && C == 1) {
+            // exchange by shuffles when both rounds are full and the lane field lies inside the warp
+            in_regs = false;
+            if (lvl < S && er == EL && S - lvl >= (uint32_t)EL && ((warp_sync >> r) & 1u) && r != 0) {
+                const uint32_t s_next = S - lvl - EL;  // the thread bits [s_next, s_next + EL) swap with the register index
+                if (s_next + EL <= 5) {
+                    shfl_exchange4(a, s_next);
+                    in_regs = true;
+                    continue;
+                }
+            }
+        }
         if (lvl < S) {
             if (active) {
 #pragma unroll
