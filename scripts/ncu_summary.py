@@ -34,6 +34,12 @@ def main():
         for k in KEYS:
             if k in rec and rec[k] != "":
                 print(f"| `{k}` | {rec[k]} | {units[hdr.index(k)]} |")
+        stalls = []
+        for k in hdr:
+            if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and rec.get(k, "") not in ("", "n/a"):
+                stalls.append((float(rec[k].replace(",", "")), k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+        if stalls:
+            print("\nwarp stall cycles per issued instruction: " + ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:9]))
         print()
 
 
