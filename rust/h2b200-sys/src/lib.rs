@@ -36,6 +36,9 @@ pub struct H2bDomain {
 
 extern "C" {
     pub fn h2b_init(device: c_int) -> c_int;
+    pub fn h2b_init_devices(devices: *const c_int, count: c_int) -> c_int;
+    pub fn h2b_device_count() -> c_int;
+    pub fn h2b_srs_layout(srs: u64, parts: *mut u32, replicated: *mut u32, part_n: *mut usize) -> c_int;
     pub fn h2b_shutdown();
     pub fn h2b_last_error() -> *const c_char;
     pub fn h2b_abi_version() -> u32;
@@ -71,11 +74,20 @@ fn check(rc: c_int, what: &str) {
     }
 }
 
+/// `H2B200_DEVICES=0,1,2,3` makes one process use several GPUs (h2b_init_devices: SRS arrays of 2^21 points and more
+/// are sharded by point range, smaller ones replicated and whole columns dealt to the devices); `H2B200_DEVICE=n`
+/// (default 0) selects a single one.
 fn ensure_init() {
     static ONCE: std::sync::Once = std::sync::Once::new();
     ONCE.call_once(|| {
-        let dev = std::env::var("H2B200_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
-        check(unsafe { h2b_init(dev) }, "h2b_init");
+        if let Ok(list) = std::env::var("H2B200_DEVICES") {
+            let devs: Vec<c_int> = list.split(',').filter_map(|s| s.trim().parse().ok()).collect();
+            assert!(!devs.is_empty(), "H2B200_DEVICES is set but names no device");
+            check(unsafe { h2b_init_devices(devs.as_ptr(), devs.len() as c_int) }, "h2b_init_devices");
+        } else {
+            let dev = std::env::var("H2B200_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
+            check(unsafe { h2b_init(dev) }, "h2b_init");
+        }
     });
 }
 
@@ -101,15 +113,20 @@ pub fn best_fft(a: &mut [Fr], omega: Fr, log_n: u32) {
 }
 
 /// Device-resident SRS for `ParamsKZG::{commit, commit_lagrange}` (kzg/commitment.rs:319, :363).
-pub struct Srs(u64);
+/// (`ParamsKZG` derives `Debug` and `Clone`: the patch keeps it behind an `Arc`.)
+#[derive(Debug)]
+pub struct Srs(u64, usize);
 impl Srs {
     pub fn register(bases: &[G1Affine]) -> Self {
         ensure_init();
         let mut h = 0u64;
         check(unsafe { h2b_srs_register(bases.as_ptr() as *const u64, bases.len(), &mut h) }, "srs_register");
-        Srs(h)
+        Srs(h, bases.len())
     }
+    pub fn len(&self) -> usize { self.1 }
+    pub fn is_empty(&self) -> bool { self.1 == 0 }
     pub fn commit(&self, scalars: &[Fr]) -> G1 {
+        assert!(self.1 >= scalars.len());  // commitment.rs:319 / :363: assert!(bases.len() >= size)
         let mut out = core::mem::MaybeUninit::<G1>::uninit();
         check(unsafe { h2b_commit(self.0, scalars.as_ptr() as *const u64, scalars.len(), out.as_mut_ptr() as *mut u64) }, "commit");
         unsafe { out.assume_init() }
@@ -132,7 +149,7 @@ impl Srs {
         ensure_init();
         let (mut k, mut g, mut gl) = (0u32, 0u64, 0u64);
         check(unsafe { h2b_params_read(bytes.as_ptr(), bytes.len(), &mut k, &mut g, &mut gl) }, "params_read");
-        (k, Srs(g), Srs(gl))
+        (k, Srs(g, 1 << k), Srs(gl, 1 << k))
     }
 }
 impl Drop for Srs {
@@ -141,8 +158,14 @@ impl Drop for Srs {
     }
 }
 
-/// Fused EvaluationDomain transforms (domain.rs:227, :244, :311).
+/// Fused EvaluationDomain transforms (domain.rs:227, :244, :311).  `EvaluationDomain` derives `Clone` and `Debug`.
+#[derive(Clone, Copy)]
 pub struct Domain(H2bDomain);
+impl core::fmt::Debug for Domain {
+    fn fmt(&self, f: &mut core::fmt::Formatter<'_>) -> core::fmt::Result {
+        write!(f, "h2b200::Domain {{ k: {}, extended_k: {}, j: {} }}", self.0.k, self.0.extended_k, self.0.j)
+    }
+}
 impl Domain {
     pub fn new(j: u32, k: u32) -> Self {
         ensure_init();

@@ -64,3 +64,65 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "h2ref" not in txt and "import bn254" not in txt and "oracle/" not in txt, f
+
+
+def _build_c_test():
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "native", "abi_c_test")
+    src = exe + ".c"
+    libdir = os.path.join(ROOT, "halo2-prover_b200", "csrc")
+    if not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe):
+        subprocess.check_call(["gcc", "-std=c11", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, src,
+                               "-L" + libdir, "-lh2b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_c_program_links_against_the_header_and_gets_error_codes_without_a_gpu():
+    """A plain C program with Rust-layout structs compiles against include/h2b200.h, links libh2b200.so, and --
+    where there is no GPU -- gets status codes, never a crash or a CPU result."""
+    import subprocess
+    exe = _build_c_test()
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present: covered by test_c_program_computes_through_the_abi")
+    r = subprocess.run([exe, "nogpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "nogpu ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_computes_through_the_abi(tmp_path, href, spec):
+    """The same C program on a GPU: Rust-layout buffers in, results compared with the oracle."""
+    import struct
+    import subprocess
+    import numpy as np
+    exe = _build_c_test()
+    n, log_n = 3000, 11
+    sc, bases = href.random_fr(n, 81), href.random_g1(n, 82)
+    a = href.random_fr(1 << log_n, 83)
+    omega = spec.fr_array([pow(spec.ROOT_OF_UNITY, 1 << (spec.FR_S - log_n), spec.R_MOD)])[0]
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<QQ", n, log_n))
+        f.write(sc.tobytes()); f.write(bases.tobytes()); f.write(omega.tobytes()); f.write(a.tobytes())
+    r = subprocess.run([exe, "run", str(inp), str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "abi_c_test ok" in r.stdout, r.stdout + r.stderr
+    res = np.fromfile(out, dtype=np.uint64)
+    m = 1 << log_n
+    msm, commit, half = res[:12], res[12:24], res[24:36]
+    off = 36
+    fft = res[off:off + 4 * m].reshape(m, 4); off += 4 * m
+    lag = res[off:off + 4 * m].reshape(m, 4); off += 4 * m
+    ext = res[off:off + 16 * m].reshape(4 * m, 4)
+    want = href.g1_to_affine(href.best_multiexp(sc, bases))
+    assert (href.g1_to_affine(msm) == want).all() and (href.g1_to_affine(commit) == want).all()
+    h = n // 2
+    assert (href.g1_to_affine(half) == href.g1_to_affine(href.best_multiexp(sc[:h].copy(), bases[:h].copy()))).all()
+    assert (fft == href.best_fft(a, omega, log_n)).all()
+    dc = href.domain_new(4, log_n)
+    assert (lag == href.lagrange_to_coeff(dc, a)).all()
+    assert (ext == href.coeff_to_extended(dc, a)).all()
