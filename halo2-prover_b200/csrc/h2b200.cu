@@ -169,6 +169,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     uint32_t e2e_chunks = 4;
+    bool e2e_auto = true;      // pieces by size (two below 2^23 points) until h2b_set_e2e_chunking / H2B_E2E_CHUNKS names a count
     size_t e2e_min_n = (size_t)1 << 21;
     cudaStream_t last_stream = nullptr;
     std::vector<cudaEvent_t> tev0, tev1;  // timing event pairs
@@ -610,7 +611,7 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
     if (n == 0) return msm_identity_out(d_out, s);
     // pieces: every piece pays the fixed latency of a sort + fix-up pass (~0.3 ms), so below 2^23 points -- a device's
     // share of a 2^24-point commit on 4 or 8 GPUs -- two pieces hide the copy better than four
-    uint32_t chunks = n >= g->e2e_min_n ? (n < ((size_t)1 << 23) ? std::min(2u, g->e2e_chunks) : g->e2e_chunks) : 1;
+    uint32_t chunks = n >= g->e2e_min_n ? ((g->e2e_auto && n < ((size_t)1 << 23)) ? 2u : g->e2e_chunks) : 1;
     Fe *ds;
     Affine *db = nullptr;
     TRY(get_buf(BUF_SCALARS, n * sizeof(Fe), (void **)&ds));
@@ -1297,7 +1298,7 @@ static int ctx_create(int device, Ctx **out) {
     const char *ec = getenv("H2B_E2E_CHUNKS");
     if (ec) {
         int v = atoi(ec);
-        if (v >= 1 && v <= 64) c->e2e_chunks = (uint32_t)v;
+        if (v >= 1 && v <= 64) { c->e2e_chunks = (uint32_t)v; c->e2e_auto = false; }
     }
     c->worker.start();
     *out = c;
@@ -1438,6 +1439,7 @@ int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n) {
     if (chunks < 1 || chunks > 64) return fail(H2B_ERR_ARG, "e2e chunks must be in [1, 64]");
     for (Ctx *x : g_all) {
         x->e2e_chunks = chunks;
+        x->e2e_auto = false;
         x->e2e_min_n = min_n;
     }
     return H2B_OK;

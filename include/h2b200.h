@@ -154,7 +154,8 @@ int h2b_dev_msm(const void *d_coeffs, const void *d_bases, size_t n, void *d_out
 int h2b_dev_commit(uint64_t srs, const void *d_coeffs, size_t n, void *d_out /* 96 B */, void *stream);
 /* h2b_commit_many with the m columns already in HBM, one after the other (m x n x 32 B); d_out: m x 96 B. */
 int h2b_dev_commit_many(uint64_t srs, const void *d_coeffs, size_t n, size_t m, void *d_out, void *stream);
-/* Device address of a registered SRS (n x 64 bytes). */
+/* Device address of a registered SRS (n x 64 bytes) on the primary device; for an SRS sharded over several devices
+ * (h2b_init_devices) the primary device's share and its length. */
 int h2b_srs_device_ptr(uint64_t srs, void **d_bases, size_t *n);
 int h2b_dev_best_fft(void *d_a, const uint64_t omega[4], uint32_t log_n, void *stream);
 int h2b_dev_lagrange_to_coeff(const h2b_domain *d, void *d_a, void *stream);
@@ -239,7 +240,7 @@ int h2b_srs_layout(uint64_t srs, uint32_t *parts, uint32_t *replicated, size_t *
 int h2b_set_srs_precompute(int enabled, uint32_t c);
 /* Host-buffer MSM entry points (h2b_best_multiexp, h2b_commit) split inputs of at least `min_n`
  * points into `chunks` contiguous pieces so the H2D copy of a piece overlaps the bucket accumulation
- * of the previous one (default 4 pieces from 2^21 points). */
+ * of the previous one (default from 2^21 points: 2 pieces below 2^23 points, 4 from there; a call fixes the count). */
 int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n);
 /* Number of kernel launches issued by the library since h2b_init (for bench accounting). */
 uint64_t h2b_kernel_launches(void);
