@@ -70,8 +70,9 @@ struct Srs {
     size_t off = 0;           // first point of the share inside the registered array
     Affine *d = nullptr;      // the bases of the share (n x 64 B)
     size_t n = 0;
-    Affine *table = nullptr;  // precomputed windows: table[w * n + i] = 2^(c*w) * d[i], or null
+    Affine *table = nullptr;  // precomputed windows: table[v * n + i] = 2^(c*tstride*v) * d[i], or null
     uint32_t c = 0, windows = 0;
+    uint32_t tstride = 1;     // every tstride-th window power is tabulated (msm.cuh: t bucket sets)
     // small SRS: every multiple d * 2^(comb_c * w) * d[i], d <= 2^(comb_c - 1) (msm_comb.cuh), or null
     Affine *comb = nullptr;
     uint32_t comb_c = 0, comb_w = 0;
@@ -163,6 +164,7 @@ struct Ctx {
     uint32_t comb_c = 8;
     double e2e_ratio = 0;      // growth of the host-path chunk sizes (0 = automatic)
     uint32_t srs_window = 0;   // 0 = automatic
+    uint32_t srs_table_stride = 0;  // 0 = automatic (1 unless HBM is short), else every t-th window power is tabulated
     int srs_precompute = 1;
     int timing = 0;
     cudaEvent_t last_done = nullptr, copy_fence = nullptr;
@@ -319,7 +321,7 @@ MsmCfg msm_plan(size_t n, const Srs *srs = nullptr, uint32_t cols = 1) {
     uint32_t c;
     if (srs && srs->table) {
         c = srs->c;
-        cfg.shared = 1;
+        cfg.shared = srs->tstride;
         cfg.stride = (uint32_t)srs->n;
     } else {
         uint32_t lg = ceil_log2(n);
@@ -337,7 +339,7 @@ MsmCfg msm_plan(size_t n, const Srs *srs = nullptr, uint32_t cols = 1) {
     uint32_t W = msm_windows_for(c);
     cfg.windows = W;
     cfg.bpw = 1u << (c - 1);
-    cfg.nb = cfg.shared ? cols * cfg.bpw : W * cfg.bpw;
+    cfg.nb = cfg.shared ? cols * cfg.shared * cfg.bpw : W * cfg.bpw;
     for (uint32_t w = 0; w + 1 < W; w++) {
         uint32_t bit = c * w + c - 1;
         cfg.half[bit >> 5] |= 1u << (bit & 31);
@@ -568,7 +570,7 @@ int msm_reduce_tree(const XYZZ *buckets, uint32_t bpw, uint32_t nwin, XYZZ *wind
 
 int msm_finish(const MsmRun &run, Projective *d_out, cudaStream_t s) {
     MsmCfg cfg = run.cfg;
-    if (cfg.shared) cfg.windows = cfg.cols;  // one bucket set per column: sum_k k * B_k is the result, no Horner
+    if (cfg.shared) cfg.windows = cfg.cols * cfg.shared;  // t bucket sets per column (t = 1: sum_k k * B_k is the result)
     XYZZ *windows, *wpart;
     TRY(get_buf(BUF_WINDOWS, (size_t)cfg.windows * sizeof(XYZZ), (void **)&windows));
     if (g->reduce_tree) {
@@ -586,10 +588,11 @@ int msm_finish(const MsmRun &run, Projective *d_out, cudaStream_t s) {
         LAUNCHED();
     }
     if (cfg.shared && cfg.cols > 1) {
-        msm_batch_out_kernel<<<(cfg.cols + 31) / 32, 32, 0, s>>>(windows, cfg.cols, d_out);
+        msm_batch_out_kernel<<<(cfg.cols + 31) / 32, 32, 0, s>>>(windows, cfg.cols, cfg.shared, cfg.c, d_out);
         LAUNCHED();
         return H2B_OK;
     }
+    if (cfg.shared) cfg.windows = cfg.shared;  // Horner over the t bucket-set sums, c doublings each
     msm_final_kernel<<<1, 32, 0, s>>>(windows, cfg, d_out);
     LAUNCHED();
     return H2B_OK;
@@ -1279,6 +1282,8 @@ static int ctx_create(int device, Ctx **out) {
         int v = atoi(sw);
         if (v >= 2 && v <= 24) c->srs_window = (uint32_t)v;
     }
+    const char *ts = getenv("H2B_SRS_TABLE_STRIDE");
+    if (ts && atoi(ts) >= 0 && atoi(ts) <= 8) c->srs_table_stride = (uint32_t)atoi(ts);
     const char *rl = getenv("H2B_REDUCE_LGRP");
     if (rl) c->reduce_lgrp = (uint32_t)atoi(rl);
     const char *rt = getenv("H2B_REDUCE_TREE");
@@ -1433,13 +1438,20 @@ int h2b_set_srs_precompute(int enabled, uint32_t c) {
     }
     return H2B_OK;
 }
+int h2b_set_srs_table_stride(uint32_t t) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (t > 8) return fail(H2B_ERR_ARG, "srs table stride must be 0 (automatic) or in [1, 8]");
+    for (Ctx *x : g_all) x->srs_table_stride = t;
+    return H2B_OK;
+}
 int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());
-    if (chunks < 1 || chunks > 64) return fail(H2B_ERR_ARG, "e2e chunks must be in [1, 64]");
+    if (chunks > 64) return fail(H2B_ERR_ARG, "e2e chunks must be 0 (by size) or in [1, 64]");
     for (Ctx *x : g_all) {
-        x->e2e_chunks = chunks;
-        x->e2e_auto = false;
+        x->e2e_chunks = chunks ? chunks : 4;
+        x->e2e_auto = chunks == 0;
         x->e2e_min_n = min_n;
     }
     return H2B_OK;
@@ -1545,7 +1557,7 @@ int comb_commit(const Srs &sr, const Fe *d_scalars, size_t n, size_t cols, Proje
         count = blocks;
         std::swap(src, dst);
     }
-    msm_batch_out_kernel<<<(uint32_t)((cols + 31) / 32), 32, 0, s>>>(src, (uint32_t)cols, d_out);
+    msm_batch_out_kernel<<<(uint32_t)((cols + 31) / 32), 32, 0, s>>>(src, (uint32_t)cols, 1, 0, d_out);
     LAUNCHED();
     return H2B_OK;
 }
@@ -1572,7 +1584,7 @@ int commit_many_device(const Srs &sr, const Fe *d_scalars, size_t n, size_t m, P
         return H2B_OK;
     }
     // bound one pass: sorted entries < 2^28 and at most 1 GiB of buckets
-    const uint64_t per_col_entries = (uint64_t)n * sr.windows, per_col_buckets = (uint64_t)1 << (sr.c - 1);
+    const uint64_t per_col_entries = (uint64_t)n * sr.windows, per_col_buckets = (uint64_t)sr.tstride << (sr.c - 1);
     size_t step = m;
     while (step > 1 && (step * per_col_entries > (1ull << 28) || step * per_col_buckets * sizeof(XYZZ) > (1ull << 30)))
         step = (step + 1) / 2;
@@ -1893,12 +1905,24 @@ static int srs_part_create(const void *src, bool src_on_device, int src_device, 
     }
     if (!s.comb && g->srs_precompute && n >= 2) {
         uint32_t c = srs_window_for(n), W = msm_windows_for(c);
-        size_t bytes = (size_t)W * n * sizeof(Affine), free_b = 0, total_b = 0;
+        size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        if (bytes <= free_b / 3 && (size_t)W * n < (1u << 31)) {
+        // every t-th window power: the whole table (t = 1) when it fits a third of the free HBM, else the thinnest
+        // stride up to 4 that does (2^26 points: 51.5 GB at t = 1, 27.5 GB at t = 2 -- two such arrays stay resident)
+        // Measured on B200 (commit, ms, t = 1 / 2 / 3): 2^20 2.91 / 3.34 / 3.81, 2^22 9.59 / 10.25 / 10.72, 2^24 36.85 / 36.90 /
+        // 37.27 -- from 2^23 points the second bucket set costs 0.1 %, so the default there is half the table.
+        uint32_t t = g->srs_table_stride ? g->srs_table_stride : (n >= ((size_t)1 << 23) ? 2 : 1);
+        auto table_windows = [&](uint32_t tt) { return (W + tt - 1) / tt; };
+        if (!g->srs_table_stride)
+            while (t < 4 && (size_t)table_windows(t) * n * sizeof(Affine) > free_b / 3) t++;
+        if (t > W) t = W;
+        const uint32_t Wt = table_windows(t);
+        const size_t bytes = (size_t)Wt * n * sizeof(Affine);
+        if (bytes <= free_b / 3 && (size_t)Wt * n < (1u << 31)) {
             e = cudaMalloc(&s.table, bytes);
             if (e == cudaSuccess) {
-                msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, n, s.table);
+                s.tstride = t;
+                msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c * t, Wt, n, s.table);
                 g->launches++;
                 e = cudaGetLastError();
                 if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
@@ -2042,7 +2066,7 @@ int h2b_srs_info(uint64_t srs, size_t *n, uint32_t *window_bits, uint32_t *windo
     if (windows) *windows = sr.comb ? sr.comb_w : (sr.table ? sr.windows : 0);
     if (table_bytes)
         *table_bytes = sr.comb ? ((size_t)sr.comb_w * (1u << (sr.comb_c - 1)) * sr.n + 1) * sizeof(Affine)
-                               : (sr.table ? (size_t)sr.windows * sr.n * sizeof(Affine) : 0);
+                               : (sr.table ? (size_t)((sr.windows + sr.tstride - 1) / sr.tstride) * sr.n * sizeof(Affine) : 0);
     return H2B_OK;
 }
 int h2b_srs_layout(uint64_t srs, uint32_t *parts, uint32_t *replicated, size_t *part_n /* parts entries, may be null */) {

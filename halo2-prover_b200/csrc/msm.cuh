@@ -37,13 +37,16 @@ struct MsmCfg {
     uint32_t slice;    // L: sorted entries per accumulation thread
     uint32_t lgrp;     // log2 of buckets per reduction group
     uint32_t half[8];  // sum over windows w < W-1 of 2^(c*w + c-1): turns unsigned windows into signed digits
-    // Precomputed-window mode (registered SRS): table[w * stride + i] = 2^(c*w) * P_i, so every
-    // window feeds ONE shared bucket set (bucket = |digit| - 1) and no Horner pass is needed.
-    uint32_t shared;   // 1: shared buckets over a precomputed table
+    // Precomputed-window mode (registered SRS): table[v * stride + i] = 2^(c*t*v) * P_i holds every t-th window power, so
+    // window w = t*v + r feeds bucket set r (bucket = |digit| - 1) through table block v: t bucket sets, and a Horner
+    // over t sums (c doublings each) at the end.  t = 1 (the default): ONE shared bucket set and no Horner pass; t > 1
+    // trades 1/t of the table's HBM for t - 1 extra reductions.
+    uint32_t shared;   // t: 0 = no table (one bucket set per window), >= 1 = bucket sets over a precomputed table
     uint32_t stride;   // points per window block of the table (the registered SRS length)
     uint32_t ioff;     // index of this chunk's first point inside the SRS
     // Batched commit (shared mode only): `cols` polynomials of n scalars each, laid out one after the
     // other, against the same bases; column q owns buckets [q * bpw, (q + 1) * bpw).
+    // (with t bucket sets per column: [q * t * bpw, (q + 1) * t * bpw))
     uint32_t cols;     // >= 1
 };
 
@@ -69,7 +72,7 @@ msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg, uint32_t *__restri
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // column-major: i = column * n + point
     const uint32_t total = cfg.n * cfg.cols;
     if (i >= total) return;
-    const uint32_t colbase = cfg.cols > 1 ? (i / cfg.n) * cfg.bpw : 0u;
+    const uint32_t colbase = cfg.cols > 1 ? (i / cfg.n) * cfg.shared * cfg.bpw : 0u;
     Fe s = Fr::from_mont(load_fe_ro(&scalars[i]));
     uint32_t l[9];
     asm("add.cc.u32 %0, %8, %16;\n\t"
@@ -92,7 +95,7 @@ msm_digits_kernel(const Fe *__restrict__ scalars, MsmCfg cfg, uint32_t *__restri
             const uint32_t neg = d < 0;
             const uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
             enc = mag | (neg << 31);
-            atomicAdd(&counts[(cfg.shared ? colbase : w * cfg.bpw) + mag - 1], 1u);
+            atomicAdd(&counts[(cfg.shared ? colbase + (w % cfg.shared) * cfg.bpw : w * cfg.bpw) + mag - 1], 1u);
         }
         digits[(size_t)w * total + i] = enc;
     }
@@ -111,8 +114,9 @@ msm_scatter_kernel(const uint32_t *__restrict__ digits, MsmCfg cfg, uint32_t *__
     if (enc == 0) return;
     const uint32_t mag = enc & 0x7fffffffu;
     const uint32_t col = cfg.cols > 1 ? i / cfg.n : 0u;
-    const uint32_t pos = atomicAdd(&cursor[(cfg.shared ? col * cfg.bpw : w * cfg.bpw) + mag - 1], 1u);
-    const uint32_t idx = cfg.shared ? w * cfg.stride + cfg.ioff + (i - col * cfg.n) : i;
+    const uint32_t pos =
+        atomicAdd(&cursor[(cfg.shared ? (col * cfg.shared + w % cfg.shared) * cfg.bpw : w * cfg.bpw) + mag - 1], 1u);
+    const uint32_t idx = cfg.shared ? (w / cfg.shared) * cfg.stride + cfg.ioff + (i - col * cfg.n) : i;
     sorted[pos] = idx | (enc & 0x80000000u);
 }
 
@@ -510,12 +514,20 @@ msm_final_kernel(const XYZZ *__restrict__ window_sums, MsmCfg cfg, Projective *o
     }
 }
 
-// Batched commit: column q's result is its single window sum (shared buckets, no Horner).
+// Batched commit: column q's result is the Horner of its t bucket-set sums (t = 1: the single sum, no doubling).
 __global__ void __launch_bounds__(32)
-msm_batch_out_kernel(const XYZZ *__restrict__ window_sums, uint32_t cols, Projective *__restrict__ out) {
+msm_batch_out_kernel(const XYZZ *__restrict__ window_sums, uint32_t cols, uint32_t t, uint32_t c, Projective *__restrict__ out) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= cols) return;
-    const Projective j = xyzz_to_projective(load_xyzz(&window_sums[q]));
+    XYZZ acc = load_xyzz(&window_sums[(size_t)q * t + (t - 1)]);
+#pragma unroll 1
+    for (int r = (int)t - 2; r >= 0; r--) {
+#pragma unroll 1
+        for (uint32_t d = 0; d < c; d++) acc = xyzz_dbl_ni(acc);
+        XYZZ s = load_xyzz(&window_sums[(size_t)q * t + r]);
+        xyzz_add(acc, s);
+    }
+    const Projective j = xyzz_to_projective(acc);
     store_fe(&out[q].x, j.x);
     store_fe(&out[q].y, j.y);
     store_fe(&out[q].z, j.z);

@@ -238,9 +238,17 @@ int h2b_srs_layout(uint64_t srs, uint32_t *parts, uint32_t *replicated, size_t *
  * 0: nothing.  `c` overrides the window table's width (0 = automatic) and implies the window table.
  * Applies to SRS registered after the call. */
 int h2b_set_srs_precompute(int enabled, uint32_t c);
+/* How much of the window table h2b_srs_register keeps: every t-th window power 2^(c*t*v) * P_i (t bucket sets per
+ * commit and a Horner over their t sums at the end).  t = 1 is the whole table (one bucket set, no doubling at all);
+ * t = 2 halves its HBM for one extra bucket reduction and c doublings per commit.  0 (default): 1 below 2^23 points,
+ * 2 from there (measured: +0.1 % at 2^24 for 7.5 instead of 14 GB; 2^26: 27.5 instead of 51.5 GB), and more (up to 4)
+ * when even that would exceed a third of the free HBM.  Applies to SRS registered after the call; results are
+ * identical for every t. */
+int h2b_set_srs_table_stride(uint32_t t);
 /* Host-buffer MSM entry points (h2b_best_multiexp, h2b_commit) split inputs of at least `min_n`
  * points into `chunks` contiguous pieces so the H2D copy of a piece overlaps the bucket accumulation
- * of the previous one (default from 2^21 points: 2 pieces below 2^23 points, 4 from there; a call fixes the count). */
+ * of the previous one (default from 2^21 points: 2 pieces below 2^23 points, 4 from there; a call fixes the count,
+ * chunks = 0 returns to that rule). */
 int h2b_set_e2e_chunking(uint32_t chunks, size_t min_n);
 /* Number of kernel launches issued by the library since h2b_init (for bench accounting). */
 uint64_t h2b_kernel_launches(void);

@@ -309,7 +309,7 @@ def test_chunked_host_path_matches_oracle(h2b, spec, href, chunks):
         assert (_affine(href, params.commit(sc)) == want).all()
         params.release()
     finally:
-        _ffi.check(_ffi.lib().h2b_set_e2e_chunking(4, C.c_size_t(1 << 21)))
+        _ffi.check(_ffi.lib().h2b_set_e2e_chunking(0, C.c_size_t(1 << 21)))
 
 
 def test_max_size_msm_2p26_linearity(h2b, spec, href):
@@ -386,3 +386,40 @@ def test_g_to_lagrange_vs_oracle_msm(h2b, spec, href, k):
     for i in sorted({0, 1 % n, (n // 2 + 1) % n, n - 1}):
         sc = spec.fr_array([pow(w_inv, i * j, spec.R_MOD) * n_inv % spec.R_MOD for j in range(n)])
         assert (_affine(href, href.best_multiexp(sc, g)) == got[i]).all(), i
+
+
+@pytest.mark.parametrize("t", [2, 3, 4])
+def test_thinned_window_table_vs_oracle(h2b, href, t):
+    """h2b_set_srs_table_stride: only every t-th window power is tabulated (1/t of the table's HBM), commits use t bucket
+    sets and a Horner over their sums.  Single commits, a shorter polynomial, a batch, and the chunked host path must
+    equal the oracle (and so the t = 1 results)."""
+    import ctypes as C
+    from halo2_prover_b200 import _ffi
+    L = _ffi.lib()
+    n = 1 << 13
+    g = href.random_g1(n, 300 + t)
+    g[5] = 0
+    cols = [href.random_fr(n, 310 + 10 * t + q) for q in range(3)]
+    cols[1][::2] = cols[1][0]
+    _ffi.check(L.h2b_set_srs_precompute(2, 0))   # window table at this size too
+    _ffi.check(L.h2b_set_srs_table_stride(t))
+    try:
+        params = h2b.ParamsKZG(13, g)
+        c, w, tb = C.c_uint32(), C.c_uint32(), C.c_size_t()
+        _ffi.check(L.h2b_srs_info(C.c_uint64(params._handles["g"]), None, C.byref(c), C.byref(w), C.byref(tb)))
+        assert tb.value == ((w.value + t - 1) // t) * n * 64
+        want = [_affine(href, href.best_multiexp(p, g)) for p in cols]
+        for q in range(3):
+            assert (_affine(href, params.commit(cols[q])) == want[q]).all(), q
+        many = params.commit_many(cols)
+        for q in range(3):
+            assert (_affine(href, many[q]) == want[q]).all(), ("many", q)
+        short = cols[0][:3001].copy()
+        assert (_affine(href, params.commit(short)) == _affine(href, href.best_multiexp(short, g[:3001].copy()))).all()
+        _ffi.check(L.h2b_set_e2e_chunking(3, C.c_size_t(1000)))
+        assert (_affine(href, params.commit(cols[2])) == want[2]).all(), "chunked"
+        params.release()
+    finally:
+        _ffi.check(L.h2b_set_e2e_chunking(0, C.c_size_t(1 << 21)))
+        _ffi.check(L.h2b_set_srs_table_stride(0))
+        _ffi.check(L.h2b_set_srs_precompute(1, 0))
