@@ -865,7 +865,7 @@ int dispatch_pass(uint32_t S, uint32_t EL, uint32_t TL, bool single, const Fe *i
         if (g_ntt_variant == 1 && plain && S == 10) return launch_pass<10, 1, 2, 256, 3, 1>(in, out, W, TW, log_n, log_ns, last, io, s, batch);
         if (g_ntt_variant == 1 && plain && S == 8) return launch_pass<8, 4, 2, 256, 3, 1>(in, out, W, TW, log_n, log_ns, last, io, s, batch);
         if (g_ntt_variant == 2 && S == 10) return launch_pass<10, 1, 2, 256, 3, 2>(in, out, W, TW, log_n, log_ns, last, io, s, batch);
-        if (g_ntt_dense) { H2B_TILE10(2, 256, 3) } else { H2B_TILE10(2, 256, 2) }
+        if (g_ntt_dense == 2) { H2B_TILE10(2, 256, 4) } else if (g_ntt_dense) { H2B_TILE10(2, 256, 3) } else { H2B_TILE10(2, 256, 2) }
     } else if (TL == 10 && EL == 1) {
         H2B_TILE10(1, 512, 2)
     } else if (TL == 9 && EL == 2) {
@@ -898,7 +898,8 @@ int g_ntt_el_big = 2;           // elements per thread (log2) of the 2^10-elemen
                                 // threads (32 warps, but ten exchanges) 0.225 / 0.955 / 4.05
 int g_ntt_tile = 0;             // forced tile size as log2, 8..10 (H2B_NTT_TILE); 0 = by size
 int g_ntt_variant = 0;          // 0 product path, 1 TMA-staged first round, 2 shuffle exchanges (H2B_NTT_VARIANT; A/B only)
-int g_ntt_dense = 1;            // 1: registers held to 5 (EL = 3) / 3 (EL = 2) blocks per SM instead of 4 / 2 (H2B_NTT_DENSE)
+int g_ntt_dense = 2;            // registers held to more blocks per SM (H2B_NTT_DENSE): 0 = 4 (EL = 3) / 2 (EL = 2) blocks, 1 = 5 / 3,
+                                // 2 = 5 / 4 (EL = 2: 64 registers, 32 warps per SM, 36 bytes of spills -- the default)
 
 // Transform `src` (n_in valid elements of a 2^log_n domain) into `dst`; `dst` may equal `src`.
 // dst_full: `dst` holds 2^log_n elements and may carry intermediate passes; otherwise (truncated
@@ -1357,7 +1358,7 @@ static int init_locked(const int *devices, int count) {
     const char *nv = getenv("H2B_NTT_VARIANT");
     if (nv) g_ntt_variant = atoi(nv);
     const char *dn = getenv("H2B_NTT_DENSE");
-    if (dn) g_ntt_dense = atoi(dn) != 0;
+    if (dn) g_ntt_dense = atoi(dn);
     const char *tl = getenv("H2B_NTT_TILE");
     if (tl && atoi(tl) >= 8 && atoi(tl) <= 10) g_ntt_tile = atoi(tl);
     const char *mr = getenv("H2B_NTT_MAX_RADIX");
