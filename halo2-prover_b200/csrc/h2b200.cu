@@ -898,8 +898,8 @@ int g_ntt_el_big = 2;           // elements per thread (log2) of the 2^10-elemen
                                 // threads (32 warps, but ten exchanges) 0.225 / 0.955 / 4.05
 int g_ntt_tile = 0;             // forced tile size as log2, 8..10 (H2B_NTT_TILE); 0 = by size
 int g_ntt_variant = 0;          // 0 product path, 1 TMA-staged first round, 2 shuffle exchanges (H2B_NTT_VARIANT; A/B only)
-int g_ntt_dense = 2;            // registers held to more blocks per SM (H2B_NTT_DENSE): 0 = 4 (EL = 3) / 2 (EL = 2) blocks, 1 = 5 / 3,
-                                // 2 = 5 / 4 (EL = 2: 64 registers, 32 warps per SM, 36 bytes of spills -- the default)
+int g_ntt_dense = 1;            // registers held to more blocks per SM (H2B_NTT_DENSE): 0 = 4 (EL = 3) / 2 (EL = 2) blocks, 1 = 5 / 3
+                                // (EL = 2: 80 registers, 24 warps per SM -- the default), 2 = 5 / 4 (64 registers, 32 warps, small spills)
 
 // Transform `src` (n_in valid elements of a 2^log_n domain) into `dst`; `dst` may equal `src`.
 // dst_full: `dst` holds 2^log_n elements and may carry intermediate passes; otherwise (truncated

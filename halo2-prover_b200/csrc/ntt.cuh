@@ -230,7 +230,11 @@ ntt_pass_kernel(const Fe *in, Fe *out, const Fe *__restrict__ W, const Fe *__res
     Fe a[E];
     uint32_t lvl = 0;
     bool in_regs = false;  // VAR 2: the next round's elements are already in the registers (shuffle exchange)
-#pragma unroll 1
+    constexpr int kRoundUnroll = EL <= 2 ? 16 : 1;
+    // 8 elements per thread: ONE copy of the round body (12 inlined products per round; unrolled, the kernel outgrows
+    // the instruction cache).  Fewer elements per thread: rounds unrolled (4 resp. 1 products per round), which makes
+    // every stride, slot offset and trivial-twiddle test of a round a compile-time constant.
+#pragma unroll kRoundUnroll
     for (uint32_t r = 0; lvl < S; r++) {
         const uint32_t er = min((uint32_t)EL, S - lvl);          // levels of this round
         const uint32_t s = er < EL ? 0u : S - lvl - EL;           // register field = row bits [s, s + EL)
