@@ -773,6 +773,8 @@ int get_pass_twiddles(TwEntry *ent, uint32_t log_n, uint32_t S, cudaStream_t s, 
 // Enumerated once per tile shape: the row sets of the rounds are those of ntt_pass_kernel.
 uint32_t ntt_warp_sync_mask(uint32_t S, uint32_t C, uint32_t EL) {
     static std::map<uint32_t, uint32_t> cache;
+    static std::mutex cache_mu;  // the per-device workers of a dealt batch plan their passes concurrently
+    std::lock_guard<std::mutex> lk(cache_mu);
     const uint32_t key = S | (C << 8) | (EL << 24);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;

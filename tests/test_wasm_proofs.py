@@ -63,3 +63,15 @@ def test_reference_prover_proves_through_the_gpu(name):
     """BASELINE.json configs 1-3: arithmetic (k = 4, GWC), Poseidon (k = 7, GWC), Collatz (k = 10, SHPLONK)."""
     stats = _check(name, "gpu")
     assert stats["msm_calls_prove"] > 0 and stats["hot_msm_ms_total"] > 0
+
+
+@needs_harness
+@pytest.mark.gpu
+def test_arithmetic_k8_through_the_gpu_equals_the_unmodified_prover():
+    """The size of the reference's own end-to-end test (arithmetic_circuit.rs:333-351, k = 8): no recorded fixture, so the
+    all-interpreted run is made here and the run through the GPU must write the same bytes under the same seed."""
+    plain, _ = harness.run("arithmetic", 8, 2024, hot=None)
+    gpu, stats = harness.run("arithmetic", 8, 2024, hot="gpu")
+    assert plain["verify_ok"] == 1 and gpu["verify_ok"] == 1
+    assert gpu["params"] == plain["params"] and gpu["proof"] == plain["proof"]
+    assert stats["hot"] == "gpu" and stats["msm_calls_prove"] == plain["msm_calls_prove"]
