@@ -428,6 +428,14 @@ def run_b200(args) -> None:
         else:
             _wait_flag(dist, "h2b_single_done", rank, False)
 
+    # `python bench.py --gpus N` without torchrun: the one-process path is the only multi-GPU path there is
+    if world == 1 and args.gpus > 1 and not args.no_single_process and torch.cuda.device_count() >= args.gpus:
+        _ffi.shutdown()
+        try:
+            single = bench_single_process(args, torch, _ffi, args.gpus, gen)
+        except Exception as exc:
+            single = {"error": repr(exc)}
+
     if rank == 0:
         peaks = measured_peaks()
         acc_ms = m["acc_ms_total"] / max(m["acc_calls"], 1)
