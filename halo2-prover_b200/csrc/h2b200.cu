@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <condition_variable>
 #include <functional>
@@ -163,6 +164,8 @@ struct Ctx {
     size_t comb_max_n = (size_t)1 << 14;  // registered SRS up to this length get the bucket-free table
     uint32_t comb_c = 8;
     double e2e_ratio = 0;      // growth of the host-path chunk sizes (0 = automatic)
+    double h2d_gbs = 55.0;     // pinned host -> this device, GB/s, with every device of the library copying at once (measured by
+                               // h2b_init_devices; one device alone: the PCIe Gen5 x16 figure of this host)
     uint32_t srs_window = 0;   // 0 = automatic
     uint32_t srs_table_stride = 0;  // 0 = automatic (1 unless HBM is short), else every t-th window power is tabulated
     int srs_precompute = 1;
@@ -614,7 +617,11 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
     if (n == 0) return msm_identity_out(d_out, s);
     // pieces: every piece pays the fixed latency of a sort + fix-up pass (~0.3 ms), so below 2^23 points -- a device's
     // share of a 2^24-point commit on 4 or 8 GPUs -- two pieces hide the copy better than four
-    uint32_t chunks = n >= g->e2e_min_n ? ((g->e2e_auto && n < ((size_t)1 << 23)) ? 2u : g->e2e_chunks) : 1;
+    // Growth of the piece sizes = accumulation time per point over copy time per point (each piece copies while its
+    // predecessor accumulates): ~4 when this device has the host's PCIe bandwidth to itself, less when the devices of
+    // one process share it (8 x B200: 24 GB/s each instead of 55).  A slower copy wants more, more even pieces.
+    const double copy_ns = 32.0 / g->h2d_gbs, auto_ratio = std::min(4.0, std::max(1.3, 2.3 / copy_ns));
+    uint32_t chunks = n >= g->e2e_min_n ? ((g->e2e_auto && n < ((size_t)1 << 23)) ? (auto_ratio < 3.0 ? 3u : 2u) : g->e2e_chunks) : 1;
     Fe *ds;
     Affine *db = nullptr;
     TRY(get_buf(BUF_SCALARS, n * sizeof(Fe), (void **)&ds));
@@ -667,7 +674,7 @@ int msm_run_pipelined(const uint64_t *h_scalars, const uint64_t *h_bases, const 
     // Chunk sizes grow geometrically: the first copy is the only one nothing overlaps, so it is small, and
     // every later chunk is as large as the accumulation of its predecessor can hide (the ratio is compute
     // time per point over copy time per point: ~4 with resident bases, ~1.5 when the bases travel too).
-    const double ratio = g->e2e_ratio > 0 ? g->e2e_ratio : (h_bases ? 1.5 : 4.0);
+    const double ratio = g->e2e_ratio > 0 ? g->e2e_ratio : (h_bases ? 1.5 : auto_ratio);
     double denom = 0, pw = 1;
     for (uint32_t k = 0; k < chunks; k++) { denom += pw; pw *= ratio; }
     std::vector<size_t> lo, hi;
@@ -1390,6 +1397,46 @@ static int init_locked(const int *devices, int count) {
                 if (pe != cudaSuccess) (void)cudaGetLastError();  // already enabled (e.g. by the host framework)
             }
         }
+    }
+    // what the host delivers to every device when all of them copy at once sizes the copy pieces of a sharded commit
+    if (count > 1) {
+        const size_t probe = (size_t)32 << 20;
+        void *hbuf = nullptr;
+        std::vector<void *> dbuf(count, nullptr);
+        bool ok = cudaHostAlloc(&hbuf, probe, cudaHostAllocDefault) == cudaSuccess;
+        for (int i = 0; ok && i < count; i++) {
+            cudaSetDevice(devices[i]);
+            ok = cudaMalloc(&dbuf[i], probe) == cudaSuccess;
+        }
+        if (ok) {
+            double best = 0;
+            for (int rep = 0; rep < 3; rep++) {
+                for (int i = 0; i < count; i++) {
+                    cudaSetDevice(devices[i]);
+                    cudaStreamSynchronize(made[i]->copy_stream);
+                }
+                const auto t0 = std::chrono::steady_clock::now();
+                for (int i = 0; i < count; i++) {
+                    cudaSetDevice(devices[i]);
+                    cudaMemcpyAsync(dbuf[i], hbuf, probe, cudaMemcpyHostToDevice, made[i]->copy_stream);
+                }
+                for (int i = 0; i < count; i++) {
+                    cudaSetDevice(devices[i]);
+                    cudaStreamSynchronize(made[i]->copy_stream);
+                }
+                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (rep) best = std::max(best, (double)probe / sec / 1e9);  // per device, all copying at once
+            }
+            if (best > 1.0)
+                for (Ctx *c : made) c->h2d_gbs = std::min(55.0, best);
+        }
+        (void)cudaGetLastError();
+        for (int i = 0; i < count; i++)
+            if (dbuf[i]) {
+                cudaSetDevice(devices[i]);
+                cudaFree(dbuf[i]);
+            }
+        if (hbuf) cudaFreeHost(hbuf);
     }
     cudaSetDevice(devices[0]);
     g_all = made;
