@@ -201,6 +201,28 @@ def run_b200(args) -> None:
     sp = C.c_void_p(stream.cuda_stream)
     gen = bn254.affine_to_array([bn254.G1_GENERATOR])[0]
 
+    if world > 1:
+        # every rank shares the host's memory bandwidth with the others: measure what this rank gets while all of
+        # them copy at once and tell the library (it sizes the copy pieces of h2b_commit from it)
+        probe_h = torch.empty(32 << 20, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
+        best = 0.0
+        for rep in range(3):
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            probe_d.copy_(probe_h, non_blocking=True)
+            torch.cuda.synchronize()
+            if rep:
+                best = max(best, (32 << 20) / (time.perf_counter() - t0) / 1e9)
+        L.h2b_set_h2d_bandwidth.argtypes = [C.c_double]
+        _ffi.check(L.h2b_set_h2d_bandwidth(C.c_double(best)))
+        h2d_gbs_rank = best
+        del probe_h, probe_d
+    else:
+        h2d_gbs_rank = None
+
     def make_inputs(n, seed):
         """pinned host scalars, device scalars, device bases [s_i] G (distinct random points) for one rank"""
         hs = torch.from_numpy(rand_fr_np(n, 1000 + seed).view(np.int64)).pin_memory()
@@ -460,7 +482,7 @@ def run_b200(args) -> None:
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
                     "api": "ParamsKZG.commit -> h2b_commit per rank, pinned host scalars, SRS resident"
                            + ("; all-gather + fold of the partials" if world > 1 else ""),
-                    "pageable_host_value": e2e_pageable},
+                    "pageable_host_value": e2e_pageable, "h2d_gbs_with_all_ranks_copying": h2d_gbs_rank},
             "gpu_launches": m["launches"],
             "parity": parity,
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel",

@@ -1488,6 +1488,13 @@ int h2b_set_srs_precompute(int enabled, uint32_t c) {
     }
     return H2B_OK;
 }
+int h2b_set_h2d_bandwidth(double gbs) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (gbs < 0 || gbs > 1000) return fail(H2B_ERR_ARG, "h2d bandwidth must be 0 (default) or a positive GB/s figure");
+    for (Ctx *x : g_all) x->h2d_gbs = gbs > 0 ? std::min(55.0, gbs) : 55.0;
+    return H2B_OK;
+}
 int h2b_set_srs_table_stride(uint32_t t) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());

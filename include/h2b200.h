@@ -238,6 +238,12 @@ int h2b_srs_layout(uint64_t srs, uint32_t *parts, uint32_t *replicated, size_t *
  * 0: nothing.  `c` overrides the window table's width (0 = automatic) and implies the window table.
  * Applies to SRS registered after the call. */
 int h2b_set_srs_precompute(int enabled, uint32_t c);
+/* The pinned-host-to-device bandwidth (GB/s) this process can count on for its scalar copies.  The copy pieces grow by
+ * (accumulation time per point) / (copy time per point): ~4 with a PCIe Gen5 x16 link to itself (the default, 55), less
+ * when several devices or processes share the host's bandwidth (8 x B200 copying at once: 24 GB/s each).
+ * h2b_init_devices measures it with all its devices copying at once; a process that shares the host with other
+ * processes (one rank per GPU) can pass what it measured.  0 restores the default. */
+int h2b_set_h2d_bandwidth(double gbs);
 /* How much of the window table h2b_srs_register keeps: every t-th window power 2^(c*t*v) * P_i (t bucket sets per
  * commit and a Horner over their t sums at the end).  t = 1 is the whole table (one bucket set, no doubling at all);
  * t = 2 halves its HBM for one extra bucket reduction and c doublings per commit.  0 (default): 1 below 2^23 points,
