@@ -12,6 +12,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -29,11 +30,14 @@ class HostCopier {
         void *host;
         size_t bytes;
     };
-    // below this the wake-up of the workers costs more than the driver's own staging loses (measured: 0.5-4 MiB
-    // column copies of a k = 14 proof got slower, the 28 MiB read-back of its extended columns 25 % faster)
-    static constexpr size_t kMinStaged = (size_t)8 << 20;
+    // below this total the driver's own staging is used.  Measured on B200 / PCIe Gen5 (scripts/hostpath_probe.py, best_fft on a
+    // pageable buffer, ms per call at 8 MiB / 2 MiB / 512 KiB thresholds): 2^14 0.161 / 0.157 / 0.103, 2^16 0.414 / 0.265 /
+    // 0.275, 2^17 0.719 / 0.419 / 0.376, 2^18 1.375 / 1.120 / 1.219
+    size_t kMinStaged = (size_t)512 << 10;  // (H2B_MIN_STAGED_KB overrides)
 
-    explicit HostCopier(int threads) : nthreads_(threads) {}
+    explicit HostCopier(int threads) : nthreads_(threads) {
+        if (const char *e = getenv("H2B_MIN_STAGED_KB")) kMinStaged = (size_t)atol(e) << 10;
+    }
     ~HostCopier() { shutdown(); }
     int threads() const { return nthreads_; }
     // true when copies from/to `host` go through the pinned ring (pageable memory, staging enabled)
