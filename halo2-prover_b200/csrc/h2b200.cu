@@ -224,8 +224,9 @@ int ensure_ctx() {
 }
 
 // host <-> device copies of caller buffers (pinned buffers go straight to the DMA engine)
-int copy_in(void *dev, const void *host, size_t bytes, cudaStream_t s) {
-    cudaError_t e = g->copier->h2d(dev, host, bytes, s);
+// round_trip: the call will read a result of similar size back (NTT entry points): stage the input through the ring too
+int copy_in(void *dev, const void *host, size_t bytes, cudaStream_t s, bool round_trip = false) {
+    cudaError_t e = g->copier->h2d(dev, host, bytes, s, round_trip);
     if (e != cudaSuccess) return fail(H2B_ERR_CUDA, "host-to-device copy", e);
     return H2B_OK;
 }
@@ -1252,9 +1253,9 @@ __global__ void imad_wide_bench_kernel(uint64_t *sink, uint32_t iters, uint32_t 
 }
 
 // host staging helpers
-int stage_in(BufId id, const void *host, size_t bytes, void **dev) {
+int stage_in(BufId id, const void *host, size_t bytes, void **dev, bool round_trip = false) {
     TRY(get_buf(id, bytes, dev));
-    return copy_in(*dev, host, bytes, g->stream);
+    return copy_in(*dev, host, bytes, g->stream, round_trip);
 }
 
 }  // namespace
@@ -2473,7 +2474,7 @@ int h2b_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
     TRY(sc.begin(g->stream));
     size_t bytes = ((size_t)1 << log_n) * 32;
     void *da;
-    TRY(stage_in(BUF_NTT_A, a, bytes, &da));
+    TRY(stage_in(BUF_NTT_A, a, bytes, &da, /*round_trip=*/true));
     TRY(ntt_run((const Fe *)da, (Fe *)da, log_n, omega, io_plain(log_n), g->stream));
     TRY(copy_out(a, da, bytes, g->stream));
     return H2B_OK;
@@ -2510,7 +2511,7 @@ int h2b_lagrange_to_coeff(const h2b_domain *d, uint64_t *a) {
     TRY(sc.begin(g->stream));
     size_t bytes = ((size_t)1 << d->k) * 32;
     void *da;
-    TRY(stage_in(BUF_NTT_A, a, bytes, &da));
+    TRY(stage_in(BUF_NTT_A, a, bytes, &da, /*round_trip=*/true));
     TRY(dev_lagrange_to_coeff(d, (Fe *)da, g->stream));
     TRY(copy_out(a, da, bytes, g->stream));
     return H2B_OK;
@@ -2536,7 +2537,7 @@ int h2b_coeff_to_extended(const h2b_domain *d, const uint64_t *in, uint64_t *out
     TRY(sc.begin(g->stream));
     size_t in_bytes = ((size_t)1 << d->k) * 32, out_bytes = ((size_t)1 << d->extended_k) * 32;
     void *din, *dout;
-    TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din));
+    TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din, /*round_trip=*/true));
     TRY(get_buf(BUF_NTT_A, out_bytes, &dout));
     TRY(dev_coeff_to_extended(d, (const Fe *)din, (Fe *)dout, g->stream));
     TRY(copy_out(out, dout, out_bytes, g->stream));
@@ -2676,7 +2677,7 @@ int h2b_extended_to_coeff(const h2b_domain *d, const uint64_t *in, uint64_t *out
     size_t in_bytes = ((size_t)1 << d->extended_k) * 32;
     size_t out_bytes = ((size_t)(d->j - 1) << d->k) * 32;
     void *din, *dout;
-    TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din));
+    TRY(stage_in(BUF_NTT_IN, in, in_bytes, &din, /*round_trip=*/true));
     TRY(get_buf(BUF_NTT_OUT, out_bytes, &dout));
     TRY(dev_extended_to_coeff(d, (const Fe *)din, (Fe *)dout, g->stream));
     TRY(copy_out(out, dout, out_bytes, g->stream));
@@ -2692,7 +2693,7 @@ int h2b_divide_by_vanishing_poly(const h2b_domain *d, uint64_t *a) {
     TRY(sc.begin(g->stream));
     size_t n = (size_t)1 << d->extended_k;
     void *da, *dt;
-    TRY(stage_in(BUF_NTT_A, a, n * 32, &da));
+    TRY(stage_in(BUF_NTT_A, a, n * 32, &da, /*round_trip=*/true));
     TRY(stage_in(BUF_MISC, d->t_evaluations, (size_t)d->n_t * 32, &dt));
     fr_scale_cyclic_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, g->stream>>>((Fe *)da, (uint32_t)n,
                                                                                (const Fe *)dt, d->n_t);

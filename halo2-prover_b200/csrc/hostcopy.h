@@ -30,13 +30,17 @@ class HostCopier {
         void *host;
         size_t bytes;
     };
-    // below this total the driver's own staging is used.  Measured on B200 / PCIe Gen5 (scripts/hostpath_probe.py, best_fft on a
-    // pageable buffer, ms per call at 8 MiB / 2 MiB / 512 KiB thresholds): 2^14 0.161 / 0.157 / 0.103, 2^16 0.414 / 0.265 /
-    // 0.275, 2^17 0.719 / 0.419 / 0.376, 2^18 1.375 / 1.120 / 1.219
-    size_t kMinStaged = (size_t)512 << 10;  // (H2B_MIN_STAGED_KB overrides)
+    // Below these totals the driver's own staging is used.  Measured on B200 / PCIe Gen5 (scripts/hostpath_probe.py):
+    //  * device-to-host: the ring pays from 512 KiB when the call's input went through it too;
+    //  * host-to-device alone (a commit: scalars in, 96 bytes out): the ring LOSES below 8 MiB (8 commits of 2 MiB each
+    //    5.1 -> 7.1 ms, commit_many of 8 x 512 KiB 1.09 -> 1.6 ms), so only round trips (the NTT entry points, `round_trip`)
+    //    stage their input from 512 KiB: best_fft on a pageable buffer at 2^14 / 2^16 / 2^17 0.169 / 0.412 / 0.710 ->
+    //    0.104 / 0.258 / 0.518 ms.
+    size_t kMinStagedH2D = (size_t)8 << 20, kMinStagedD2H = (size_t)512 << 10, kMinStagedRoundTrip = (size_t)512 << 10;
 
     explicit HostCopier(int threads) : nthreads_(threads) {
-        if (const char *e = getenv("H2B_MIN_STAGED_KB")) kMinStaged = (size_t)atol(e) << 10;
+        if (const char *e = getenv("H2B_MIN_STAGED_H2D_KB")) kMinStagedH2D = (size_t)atol(e) << 10;
+        if (const char *e = getenv("H2B_MIN_STAGED_D2H_KB")) kMinStagedD2H = (size_t)atol(e) << 10;
     }
     ~HostCopier() { shutdown(); }
     int threads() const { return nthreads_; }
@@ -44,9 +48,9 @@ class HostCopier {
     bool stages(const void *host) const { return staged(host, 0); }
 
     // dev <- host for every segment.  On return every DMA has been enqueued and `s` waits for them.
-    cudaError_t h2d(const std::vector<Seg> &segs, cudaStream_t s) {
+    cudaError_t h2d(const std::vector<Seg> &segs, cudaStream_t s, bool round_trip = false) {
         std::vector<Piece> pieces;
-        cudaError_t e = plan(segs, cudaMemcpyHostToDevice, s, pieces);
+        cudaError_t e = plan(segs, cudaMemcpyHostToDevice, s, pieces, round_trip ? kMinStagedRoundTrip : kMinStagedH2D);
         if (e != cudaSuccess || pieces.empty()) return e;
         if ((e = ensure()) != cudaSuccess) return e;
         for (size_t base = 0; base < pieces.size(); base += kSlots) {
@@ -64,15 +68,15 @@ class HostCopier {
         busy_ = true;
         return cudaStreamWaitEvent(s, done_, 0);
     }
-    cudaError_t h2d(void *dev, const void *host, size_t bytes, cudaStream_t s) {
-        return h2d(std::vector<Seg>{{dev, const_cast<void *>(host), bytes}}, s);
+    cudaError_t h2d(void *dev, const void *host, size_t bytes, cudaStream_t s, bool round_trip = false) {
+        return h2d(std::vector<Seg>{{dev, const_cast<void *>(host), bytes}}, s, round_trip);
     }
 
     // host <- dev for every segment, ordered after the work already enqueued on `s`.  Blocks until the host
     // buffers are complete (and `s` is idle).
     cudaError_t d2h(const std::vector<Seg> &segs, cudaStream_t s) {
         std::vector<Piece> pieces;
-        cudaError_t e = plan(segs, cudaMemcpyDeviceToHost, s, pieces);
+        cudaError_t e = plan(segs, cudaMemcpyDeviceToHost, s, pieces, kMinStagedD2H);
         if (e != cudaSuccess) return e;
         if (pieces.empty()) return cudaStreamSynchronize(s);
         if ((e = ensure()) != cudaSuccess) return e;
@@ -133,12 +137,12 @@ class HostCopier {
         size_t len;
     };
     // Segments that are small or pinned are copied directly on `s`; the rest is cut into ring-sized pieces.
-    cudaError_t plan(const std::vector<Seg> &segs, cudaMemcpyKind kind, cudaStream_t s, std::vector<Piece> &pieces) {
+    cudaError_t plan(const std::vector<Seg> &segs, cudaMemcpyKind kind, cudaStream_t s, std::vector<Piece> &pieces, size_t min_total) {
         size_t total = 0;
         for (const Seg &g : segs) total += g.bytes;
         for (const Seg &g : segs) {
             if (g.bytes == 0) continue;
-            if (total < kMinStaged || !staged(g.host, g.bytes)) {
+            if (total < min_total || !staged(g.host, g.bytes)) {
                 cudaError_t e = kind == cudaMemcpyHostToDevice ? cudaMemcpyAsync(g.dev, g.host, g.bytes, kind, s)
                                                                : cudaMemcpyAsync(g.host, g.dev, g.bytes, kind, s);
                 if (e != cudaSuccess) return e;

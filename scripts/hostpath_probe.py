@@ -47,3 +47,23 @@ for _ in range(10):
     for q in range(7):
         d.coeff_to_extended(cols[q], outs[q])
 print(f"coeff_to_extended x 7 14->17: {(time.perf_counter() - t0) / 10 * 1e3:.3f} ms", flush=True)
+
+import h2ref  # noqa: E402
+for k in (13, 14, 16):
+    n = 1 << k
+    g = h2ref.random_g1(1 << 10, 5)
+    g = np.ascontiguousarray(np.tile(g, (n >> 10, 1)))
+    params = h2b.ParamsKZG(k, g)
+    cs = [rnd(n) for _ in range(8)]
+    for _ in range(3):
+        params.commit(cs[0]); params.commit_many(cs)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        for c in cs:
+            params.commit(c)
+    t1 = time.perf_counter()
+    for _ in range(20):
+        params.commit_many(cs)
+    t2 = time.perf_counter()
+    print(f"k={k}: 8 commits {(t1 - t0) / 20 * 1e3:.3f} ms, commit_many(8) {(t2 - t1) / 20 * 1e3:.3f} ms", flush=True)
+    params.release()
