@@ -499,8 +499,8 @@ def run_b200(args) -> None:
                          "model": "43,520 IMAD-class/point (160 modmul x 272) x %d points per launch" % n,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 / 13 windows from the
                          # committed capture (ncu cannot run inside the timed bench); only quoted for that geometry
-                         "traffic": 29.42e9 if (n == 1 << 24 and srs_w.value == 13) else None,
-                         "traffic_source": "profiles/r01_ncu_full_commit_accumulate_v12.md (ncu --set full, per launch)",
+                         "traffic": 29.47e9 if (n == 1 << 24 and srs_w.value == 13) else None,
+                         "traffic_source": "profiles/r02_ncu_full_commit_accumulate.md (ncu --set full, per launch)",
                          "launch_ms": acc_ms,
                          "peak_source": "measured live: mad.lo.u32 microbenchmark (h2b_imad_peak); "
                                         "IMAD.WIDE rate %.1f G/s" % imad_w.value,

@@ -24,7 +24,7 @@ namespace h2b {
 class HostCopier {
   public:
     static constexpr size_t kChunk = (size_t)512 << 10;  // bytes per staged chunk
-    static constexpr size_t kSlots = 128;                // pinned ring: 64 MiB
+    static constexpr size_t kMinSlots = 8, kSlots = 128;  // pinned ring: 4 MiB at first, grown on demand up to 64 MiB
     struct Seg {
         void *dev;
         void *host;
@@ -52,9 +52,9 @@ class HostCopier {
         std::vector<Piece> pieces;
         cudaError_t e = plan(segs, cudaMemcpyHostToDevice, s, pieces, round_trip ? kMinStagedRoundTrip : kMinStagedH2D);
         if (e != cudaSuccess || pieces.empty()) return e;
-        if ((e = ensure()) != cudaSuccess) return e;
-        for (size_t base = 0; base < pieces.size(); base += kSlots) {
-            const size_t cnt = std::min(kSlots, pieces.size() - base);
+        if ((e = ensure(pieces.size())) != cudaSuccess) return e;
+        for (size_t base = 0; base < pieces.size(); base += slots_) {
+            const size_t cnt = std::min(slots_, pieces.size() - base);
             if (base && (e = cudaStreamSynchronize(copy_)) != cudaSuccess) return e;  // ring reused: drain its DMAs
             std::atomic<int> err{0};
             run(cnt, [&](size_t i) {
@@ -79,11 +79,11 @@ class HostCopier {
         cudaError_t e = plan(segs, cudaMemcpyDeviceToHost, s, pieces, kMinStagedD2H);
         if (e != cudaSuccess) return e;
         if (pieces.empty()) return cudaStreamSynchronize(s);
-        if ((e = ensure()) != cudaSuccess) return e;
+        if ((e = ensure(pieces.size())) != cudaSuccess) return e;
         if ((e = cudaEventRecord(fence_, s)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(copy_, fence_, 0)) != cudaSuccess) return e;
-        for (size_t base = 0; base < pieces.size(); base += kSlots) {
-            const size_t cnt = std::min(kSlots, pieces.size() - base);
+        for (size_t base = 0; base < pieces.size(); base += slots_) {
+            const size_t cnt = std::min(slots_, pieces.size() - base);
             for (size_t i = 0; i < cnt; i++) {
                 const Piece &p = pieces[base + i];
                 if ((e = cudaMemcpyAsync(ring_ + i * kChunk, p.dev, p.len, cudaMemcpyDeviceToHost, copy_)) != cudaSuccess) return e;
@@ -121,6 +121,7 @@ class HostCopier {
         stop_ = false;
         if (ring_) cudaFreeHost(ring_);
         ring_ = nullptr;
+        slots_ = 0;
         for (auto e : slot_ev_) cudaEventDestroy(e);
         slot_ev_.clear();
         if (done_) cudaEventDestroy(done_);
@@ -163,20 +164,35 @@ class HostCopier {
         }
         return a.type == cudaMemoryTypeUnregistered;  // pinned / managed memory goes to the DMA engine directly
     }
-    cudaError_t ensure() {
-        if (ring_) return busy_ ? drain_keep() : cudaSuccess;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        device_ = dev;
-        cudaError_t e = cudaHostAlloc((void **)&ring_, kChunk * kSlots, cudaHostAllocDefault);
-        if (e != cudaSuccess) return e;
-        if ((e = cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&done_, cudaEventDisableTiming)) != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&fence_, cudaEventDisableTiming)) != cudaSuccess) return e;
-        slot_ev_.resize(kSlots);
-        for (auto &ev : slot_ev_)
+    // Pinning host memory costs ~0.4 ms per MiB, so a process that only ever moves a few MiB (one proof at k <= 14)
+    // should not pay for the full ring: it starts at what the first transfer needs and doubles up to kSlots.
+    cudaError_t ensure(size_t want) {
+        cudaError_t e;
+        if (ring_ && busy_ && (e = drain_keep()) != cudaSuccess) return e;
+        size_t need = kMinSlots;
+        while (need < want && need < kSlots) need *= 2;
+        if (ring_ && need <= slots_) return cudaSuccess;
+        if (!ring_) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            device_ = dev;
+            if ((e = cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&done_, cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&fence_, cudaEventDisableTiming)) != cudaSuccess) return e;
+            for (int t = 0; t < nthreads_; t++) workers_.emplace_back([this] { loop(); });
+        } else {
+            if ((e = cudaStreamSynchronize(copy_)) != cudaSuccess) return e;
+            cudaFreeHost(ring_);
+            ring_ = nullptr;
+            slots_ = 0;
+        }
+        if ((e = cudaHostAlloc((void **)&ring_, kChunk * need, cudaHostAllocDefault)) != cudaSuccess) return e;
+        while (slot_ev_.size() < need) {
+            cudaEvent_t ev;
             if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-        for (int t = 0; t < nthreads_; t++) workers_.emplace_back([this] { loop(); });
+            slot_ev_.push_back(ev);
+        }
+        slots_ = need;
         return cudaSuccess;
     }
     // the ring still holds chunks of an earlier h2d whose DMAs may be in flight
@@ -232,6 +248,7 @@ class HostCopier {
     int nthreads_;
     int device_ = 0;
     char *ring_ = nullptr;
+    size_t slots_ = 0;
     cudaStream_t copy_ = nullptr;
     cudaEvent_t done_ = nullptr, fence_ = nullptr;
     std::vector<cudaEvent_t> slot_ev_;

@@ -421,3 +421,216 @@ def test_cuda_evaluate_h_rejects_malformed_graphs(h2b, spec):
             run(bad)
     with pytest.raises(_ffi.H2BError):
         run([(ev.STORE, 0, (ev.ADVICE, 0, 0))], rotations=tuple(range(33)))   # more than 32 rotations
+
+
+# ---------------------------------------------------------------------------------------------- Poseidon (k = 7)
+# Third pin: the Pow5 chip (halo2_gadgets, the gates restated from circuits/src/poseidon/pow5.rs:57-201): ten gate
+# polynomials of degree up to 6 behind three selector columns, Rotation::prev / next with rot_scale = 8, MDS constants
+# inside the expressions, and a permutation argument over SEVEN columns of all three kinds (instance, fixed, advice) in
+# two chunks of length cs.degree() - 2 = 4, so the products are genuinely multi-column.
+# Fixture: tests/golden/wasm_poseidon_k7.npz, the complete record of that proof.  Order of its best_fft calls in
+# keygen_pk + create_proof: 0-8 fixed lagrange_to_coeff (rc_a x3, rc_b x3, s_full, s_partial, s_pad_and_add), 9-17 their
+# coeff_to_extended, 18-24 / 25-31 the seven permutation polynomials, 32-37 l0, l_blind, l_last, 38 instance, 39-42 the two
+# permutation products, 43-46 advice (state x3, partial_sbox), 47-51 coeff_to_extended of advice + instance inside
+# evaluate_h, 52 extended_to_coeff of the quotient.
+PK, PEXT = 7, 10
+PN, PEN = 1 << PK, 1 << PEXT
+
+
+def _poseidon_fixture(spec):
+    z = np.load(f"{GOLDEN}/{MANIFEST['poseidon']['file']}")
+    R = spec.R_MOD
+    out = lambda i: spec.fr_ints(z[f"fft{i}_out"])
+    assert [z[f"fft{i}_in"].shape[0] for i in range(53)] == [PN] * 9 + [PEN] * 9 + [PN] * 7 + [PEN] * 7 + [PN, PEN] * 3 + \
+        [PN, PN, PEN, PN, PEN] + [PN] * 4 + [PEN] * 6
+    d = {"fixed": [out(i) for i in range(9, 18)], "fixed_lagrange": [spec.fr_ints(z[f"fft{i}_in"]) for i in range(9)],
+         "sigma": [out(i) for i in range(25, 32)], "l0": out(33), "l_blind": out(35), "l_last": out(37),
+         "z": [out(40), out(42)], "advice": [out(i) for i in range(47, 51)], "instance": [out(51)]}
+    d["ext_omega"] = pow(spec.ROOT_OF_UNITY, 1 << (28 - PEXT), R)
+    # coset generator read off the record: coefficient 1 of the first state column is multiplied by it
+    d["zeta"] = spec.fr_ints(z["fft47_in"][1:2])[0] * pow(spec.fr_ints(z["fft43_out"][1:2])[0] * pow(PN, -1, R), -1, R) % R
+    d["l_active"] = [(1 - a - b) % R for a, b in zip(d["l_last"], d["l_blind"])]
+    tev = [pow((pow(d["zeta"] * pow(d["ext_omega"], i, R) % R, PN, R) - 1) % R, -1, R) for i in range(PEN // PN)]
+    d["values"] = [v * pow(tev[i % len(tev)], -1, R) % R for i, v in enumerate(spec.fr_ints(z["fft52_in"]))]
+    d["quotient_in"] = z["fft52_in"]
+    return d
+
+
+def _poseidon_columns(ev):
+    """cs.permutation in enable_equality order: the instance column (poseidon_circuit.rs:70), rc_b[0] through
+    enable_constant (:77), then state[0..3] and rc_b[0..3] (pow5.rs:79-84; rc_b[0] is already there)."""
+    return [(ev.INSTANCE, 0), (ev.FIXED, 3), (ev.ADVICE, 0), (ev.ADVICE, 1), (ev.ADVICE, 2), (ev.FIXED, 4), (ev.FIXED, 5)]
+
+
+def _poseidon_gate_polys(spec, fixed, advice, idx, rot_scale, size):
+    """The ten gate polynomials at one row, straight from their definition (independent of the graph encoding)."""
+    import poseidon_spec as ps
+    R = spec.R_MOD
+    _, m, minv = _poseidon_constants()
+    cur, nxt, prv = idx, (idx + rot_scale) % size, (idx - rot_scale) % size
+    st = lambda j, r: advice[j][r]
+    sbox = advice[3][cur]
+    rc_a = [fixed[j][cur] for j in range(3)]
+    rc_b = [fixed[3 + j][cur] for j in range(3)]
+    s_full, s_partial, s_pad = fixed[6][cur], fixed[7][cur], fixed[8][cur]
+    p5 = lambda v: pow(v, 5, R)
+    polys = [s_full * (sum(p5(st(j, cur) + rc_a[j]) * m[i][j] for j in range(3)) - st(i, nxt)) for i in range(3)]
+    mid = lambda i: sbox * m[i][0] + sum((st(j, cur) + rc_a[j]) * m[i][j] for j in (1, 2))
+    nx = lambda i: sum(st(j, nxt) * minv[i][j] for j in range(3))
+    polys.append(s_partial * (p5(st(0, cur) + rc_a[0]) - sbox))
+    polys.append(s_partial * (p5(mid(0) + rc_b[0]) - nx(0)))
+    polys += [s_partial * (mid(i) + rc_b[i] - nx(i)) for i in (1, 2)]
+    polys += [s_pad * (st(i, prv) + st(i, cur) - st(i, nxt)) for i in (0, 1)]
+    polys.append(s_pad * (st(2, prv) - st(2, nxt)))
+    assert ps.R == R
+    return [p % R for p in polys]
+
+
+_P_CONST = []
+
+
+def _poseidon_constants():
+    import poseidon_spec as ps
+    if not _P_CONST:
+        _P_CONST.append(ps.generate_constants(3))
+    return _P_CONST[0]
+
+
+def _poseidon_graph(ev, spec):
+    """The same ten polynomials as a GraphEvaluator program: one Horner over them with y."""
+    _, m, minv = _poseidon_constants()
+    g = ev.Graph()
+    cur, nxt, prv = g.add_rotation(0), g.add_rotation(1), g.add_rotation(-1)
+    c = g.add_calc
+    st = lambda j, r: (ev.ADVICE, j, r)
+    sbox = (ev.ADVICE, 3, cur)
+    rc_a = [(ev.FIXED, j, cur) for j in range(3)]
+    rc_b = [(ev.FIXED, 3 + j, cur) for j in range(3)]
+    s_full, s_partial, s_pad = [(ev.FIXED, 6 + j, cur) for j in range(3)]
+    M = [[g.add_constant(v) for v in row] for row in m]
+    MI = [[g.add_constant(v) for v in row] for row in minv]
+
+    def p5(v):
+        v2 = c(ev.SQUARE, v)
+        return c(ev.MUL, c(ev.SQUARE, v2), v)
+
+    def total(terms):
+        acc = terms[0]
+        for t in terms[1:]:
+            acc = c(ev.ADD, acc, t)
+        return acc
+
+    pows = [p5(c(ev.ADD, st(j, cur), rc_a[j])) for j in range(3)]
+    polys = [c(ev.MUL, s_full, c(ev.SUB, total([c(ev.MUL, pows[j], M[i][j]) for j in range(3)]), st(i, nxt))) for i in range(3)]
+    lin = [c(ev.ADD, st(j, cur), rc_a[j]) for j in range(3)]
+    mid = lambda i: total([c(ev.MUL, sbox, M[i][0])] + [c(ev.MUL, lin[j], M[i][j]) for j in (1, 2)])
+    nx = lambda i: total([c(ev.MUL, st(j, nxt), MI[i][j]) for j in range(3)])
+    polys.append(c(ev.MUL, s_partial, c(ev.SUB, pows[0], sbox)))
+    polys.append(c(ev.MUL, s_partial, c(ev.SUB, p5(c(ev.ADD, mid(0), rc_b[0])), nx(0))))
+    polys += [c(ev.MUL, s_partial, c(ev.SUB, c(ev.ADD, mid(i), rc_b[i]), nx(i))) for i in (1, 2)]
+    polys += [c(ev.MUL, s_pad, c(ev.SUB, c(ev.ADD, st(i, prv), st(i, cur)), st(i, nxt))) for i in (0, 1)]
+    polys.append(c(ev.MUL, s_pad, c(ev.SUB, st(2, prv), st(2, nxt))))
+    c(ev.HORNER, (ev.PREVIOUS, 0, 0), polys, (ev.Y, 0, 0))
+    return g
+
+
+def _bivariate_product(factors, R):
+    """prod (c + beta s + gamma) as {(a, b): coefficient of beta^a gamma^b}"""
+    poly = {(0, 0): 1}
+    for cst, s in factors:
+        nxt = {}
+        for (a, b), v in poly.items():
+            for key, w in (((a, b), cst), ((a + 1, b), s), ((a, b + 1), 1)):
+                nxt[key] = (nxt.get(key, 0) + v * w) % R
+        poly = nxt
+    return poly
+
+
+def _poseidon_challenges(d, spec, ev):
+    """values[idx] = sum_{i<13} y^(14-i) T_i + y C_0(beta, gamma) + C_1(beta, gamma) with the 13 simple Horner terms T (10
+    gates, l0 (1 - z0), l_last (z1^2 - z1), l0 (z1 - z0(last))) and the two chunk terms, polynomials of degree 4 and 3 in
+    (beta, gamma): linear in 13 + 15 + 9 = 37 monomials (the constant of C_1 is known).  Solved on 200 sampled rows."""
+    import random
+    R = spec.R_MOD
+    cols = _poseidon_columns(ev)
+    col_of = {ev.ADVICE: d["advice"], ev.FIXED: d["fixed"], ev.INSTANCE: d["instance"]}
+    mono4 = sorted((a, b) for a in range(5) for b in range(5) if a + b <= 4)
+    mono3 = sorted((a, b) for a in range(4) for b in range(4) if 0 < a + b <= 3)
+    rows, rhs = [], []
+    for idx in random.Random(11).sample(range(PEN), 200):
+        nx, last = (idx + 8) % PEN, (idx - 6 * 8) % PEN
+        z0, z1 = d["z"]
+        terms = _poseidon_gate_polys(spec, d["fixed"], d["advice"], idx, 8, PEN)
+        terms += [(1 - z0[idx]) * d["l0"][idx], (z1[idx] ** 2 - z1[idx]) * d["l_last"][idx], (z1[idx] - z0[last]) * d["l0"][idx]]
+        X = d["zeta"] * pow(d["ext_omega"], idx, R) % R
+        chunk = []
+        for ci, zc in enumerate(d["z"]):
+            part = list(enumerate(cols))[ci * 4:(ci + 1) * 4]
+            left = _bivariate_product([(col_of[kd][ix][idx], d["sigma"][j][idx]) for j, (kd, ix) in part], R)
+            right = _bivariate_product([(col_of[kd][ix][idx], pow(ev.DELTA, j, R) * X % R) for j, (kd, ix) in part], R)
+            chunk.append({key: (zc[nx] * left.get(key, 0) - zc[idx] * right.get(key, 0)) * d["l_active"][idx] % R
+                          for key in set(left) | set(right)})
+        rows.append([t % R for t in terms] + [chunk[0].get(mn, 0) for mn in mono4] + [chunk[1].get(mn, 0) for mn in mono3])
+        rhs.append((d["values"][idx] - chunk[1].get((0, 0), 0)) % R)
+    sol, rank, residual = _solve(rows, rhs, R)
+    y = sol[13 + mono4.index((0, 0))]
+    beta, gamma = sol[28 + mono3.index((1, 0))], sol[28 + mono3.index((0, 1))]
+    consistent = all(sol[i] == pow(y, 14 - i, R) for i in range(13)) and \
+        all(sol[13 + i] == y * pow(beta, a, R) * pow(gamma, b, R) % R for i, (a, b) in enumerate(mono4)) and \
+        all(sol[28 + i] == pow(beta, a, R) * pow(gamma, b, R) % R for i, (a, b) in enumerate(mono3))
+    return (y, beta, gamma), rank, residual, consistent
+
+
+def _poseidon_perm(ev, d):
+    return ev.Permutation(columns=_poseidon_columns(ev), sigma_cosets=d["sigma"], z_cosets=d["z"], chunk_len=4, last_rotation=-6,
+                          l0=d["l0"], l_last=d["l_last"], l_active_row=d["l_active"])
+
+
+def test_poseidon_fixed_columns_hold_the_generated_round_constants(spec):
+    """oracle/poseidon_spec.py against the record: the public output for the recorded input, and the proving key's rc_a /
+    rc_b columns (full rounds: one round per row; partial rounds: rc_a = round 2i, rc_b = round 2i + 1)."""
+    import poseidon_spec as ps
+    ent = MANIFEST["poseidon"]
+    inp = json.loads(ent["input"])
+    assert ps.hash_constant_length(inp["x"]) == int(inp["output"], 16)
+    rc, m, minv = _poseidon_constants()
+    assert all(sum(m[i][k] * minv[k][j] for k in range(3)) % spec.R_MOD == int(i == j) for i in range(3) for j in range(3))
+    fx = _poseidon_fixture(spec)["fixed_lagrange"]
+    full = [r for r in range(PN) if fx[6][r]]
+    partial = [r for r in range(PN) if fx[7][r]]
+    assert len(full) == 8 and len(partial) == 30 and sum(fx[8]) == 1
+    rounds = iter(range(68))
+    for row in full[:4]:
+        assert [fx[j][row] for j in range(3)] == rc[next(rounds)]
+    for row in partial:
+        assert [fx[j][row] for j in range(3)] == rc[next(rounds)]
+        assert [fx[3 + j][row] for j in range(3)] == rc[next(rounds)]
+    for row in full[4:]:
+        assert [fx[j][row] for j in range(3)] == rc[next(rounds)]
+
+
+def test_oracle_evaluate_h_poseidon_pin(spec):
+    import evaluate_h as ev
+    d = _poseidon_fixture(spec)
+    assert d["zeta"] == spec.ZETA
+    (y, beta, gamma), rank, residual, consistent = _poseidon_challenges(d, spec, ev)
+    assert rank == 37 and residual == 0 and consistent
+    sc = ev.Scalars(challenges=[], beta=beta, gamma=gamma, theta=0, y=y)
+    got = ev.evaluate_h(_poseidon_graph(ev, spec), d["fixed"], d["advice"], d["instance"], sc, _poseidon_perm(ev, d), PK, PEXT,
+                        d["ext_omega"], d["zeta"])
+    assert got == d["values"]   # all 1024 rows, 37 of them used up by the unknowns
+
+
+@pytest.mark.gpu
+def test_cuda_evaluate_h_poseidon_reproduces_the_reference_quotient(h2b, spec):
+    import evaluate_h as ev
+    from halo2_prover_b200 import evaluation
+    d = _poseidon_fixture(spec)
+    (y, beta, gamma), rank, residual, consistent = _poseidon_challenges(d, spec, ev)
+    assert residual == 0 and consistent
+    sc = ev.Scalars(challenges=[], beta=beta, gamma=gamma, theta=0, y=y)
+    got, dom = _run_gpu(h2b, spec, evaluation, _poseidon_graph(ev, spec), d["fixed"], d["advice"], d["instance"], sc,
+                        _poseidon_perm(ev, d), PK, 6)
+    assert dom.extended_k == PEXT
+    assert got == d["values"]
+    assert (dom.divide_by_vanishing_poly(spec.fr_array(got)) == d["quotient_in"]).all()

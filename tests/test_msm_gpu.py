@@ -423,3 +423,45 @@ def test_thinned_window_table_vs_oracle(h2b, href, t):
         _ffi.check(L.h2b_set_e2e_chunking(0, C.c_size_t(1 << 21)))
         _ffi.check(L.h2b_set_srs_table_stride(0))
         _ffi.check(L.h2b_set_srs_precompute(1, 0))
+
+
+def test_concurrent_host_threads(h2b, spec, href):
+    """The library serialises its entry points on one lock (one workspace per device): calls from several host threads
+    at once -- rayon workers in the reference's create_proof, plonk/prover.rs -- must all return the right answer."""
+    import threading
+
+    jobs = [(href.random_fr(n, 7100 + n), href.random_g1(n, 7200 + n)) for n in (300, 4096, 5000, 1 << 14)]
+    want = [_affine(href, href.best_multiexp(s, p)) for s, p in jobs]
+    polys = [href.random_fr(1 << k, 7300 + k) for k in (10, 12, 13)]
+    omega = lambda k: spec.fr_array([pow(spec.ROOT_OF_UNITY, 1 << (spec.FR_S - k), spec.R_MOD)])[0]  # noqa: E731
+    want_fft = [href.best_fft(a, omega(a.shape[0].bit_length() - 1), a.shape[0].bit_length() - 1) for a in polys]
+    got, got_fft, errs = [None] * len(jobs), [None] * len(polys), []
+
+    def msm(i):
+        try:
+            for _ in range(3):
+                got[i] = _affine(href, h2b.best_multiexp(jobs[i][0], jobs[i][1]))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    def fft(i):
+        try:
+            for _ in range(3):
+                a = polys[i].copy()
+                k = a.shape[0].bit_length() - 1
+                h2b.best_fft(a, omega(k), k)
+                got_fft[i] = a
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=msm, args=(i,)) for i in range(len(jobs))]
+    ts += [threading.Thread(target=fft, args=(i,)) for i in range(len(polys))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for g, w in zip(got, want):
+        assert (g == w).all()
+    for g, w in zip(got_fft, want_fft):
+        assert (g == w).all()
