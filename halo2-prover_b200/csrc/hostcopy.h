@@ -37,10 +37,17 @@ class HostCopier {
     //    stage their input from 512 KiB: best_fft on a pageable buffer at 2^14 / 2^16 / 2^17 0.169 / 0.412 / 0.710 ->
     //    0.104 / 0.258 / 0.518 ms.
     size_t kMinStagedH2D = (size_t)8 << 20, kMinStagedD2H = (size_t)512 << 10, kMinStagedRoundTrip = (size_t)512 << 10;
+    // Below this many staged bytes the calling thread fills / drains the ring alone: waking the worker threads costs more
+    // than their help is worth when they have been asleep (a prover doing host work between calls), and a process that
+    // never moves this much never creates them (each costs ~10 ms to start: 58 / 111 ms on the first staged call of a
+    // Poseidon proof at k = 12 / 14 with six of them, scripts/proof_hostpath_ab.py).
+    size_t kMinWorkers = (size_t)8 << 20;
 
     explicit HostCopier(int threads) : nthreads_(threads) {
         if (const char *e = getenv("H2B_MIN_STAGED_H2D_KB")) kMinStagedH2D = (size_t)atol(e) << 10;
         if (const char *e = getenv("H2B_MIN_STAGED_D2H_KB")) kMinStagedD2H = (size_t)atol(e) << 10;
+        if (const char *e = getenv("H2B_MIN_STAGED_RT_KB")) kMinStagedRoundTrip = (size_t)atol(e) << 10;
+        if (const char *e = getenv("H2B_COPY_WORKERS_MIN_KB")) kMinWorkers = (size_t)atol(e) << 10;
     }
     ~HostCopier() { shutdown(); }
     int threads() const { return nthreads_; }
@@ -53,11 +60,12 @@ class HostCopier {
         cudaError_t e = plan(segs, cudaMemcpyHostToDevice, s, pieces, round_trip ? kMinStagedRoundTrip : kMinStagedH2D);
         if (e != cudaSuccess || pieces.empty()) return e;
         if ((e = ensure(pieces.size())) != cudaSuccess) return e;
+        const bool helpers = pieces.size() * kChunk >= kMinWorkers;
         for (size_t base = 0; base < pieces.size(); base += slots_) {
             const size_t cnt = std::min(slots_, pieces.size() - base);
             if (base && (e = cudaStreamSynchronize(copy_)) != cudaSuccess) return e;  // ring reused: drain its DMAs
             std::atomic<int> err{0};
-            run(cnt, [&](size_t i) {
+            run(cnt, helpers, [&](size_t i) {
                 const Piece &p = pieces[base + i];
                 std::memcpy(ring_ + i * kChunk, p.host, p.len);
                 if (cudaMemcpyAsync(p.dev, ring_ + i * kChunk, p.len, cudaMemcpyHostToDevice, copy_) != cudaSuccess) err = 1;
@@ -82,6 +90,7 @@ class HostCopier {
         if ((e = ensure(pieces.size())) != cudaSuccess) return e;
         if ((e = cudaEventRecord(fence_, s)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(copy_, fence_, 0)) != cudaSuccess) return e;
+        const bool helpers = pieces.size() * kChunk >= kMinWorkers;
         for (size_t base = 0; base < pieces.size(); base += slots_) {
             const size_t cnt = std::min(slots_, pieces.size() - base);
             for (size_t i = 0; i < cnt; i++) {
@@ -90,7 +99,7 @@ class HostCopier {
                 if ((e = cudaEventRecord(slot_ev_[i], copy_)) != cudaSuccess) return e;
             }
             std::atomic<int> err{0};
-            run(cnt, [&](size_t i) {
+            run(cnt, helpers, [&](size_t i) {
                 const Piece &p = pieces[base + i];
                 if (cudaEventSynchronize(slot_ev_[i]) != cudaSuccess) err = 1;
                 std::memcpy(p.host, ring_ + i * kChunk, p.len);
@@ -179,7 +188,6 @@ class HostCopier {
             if ((e = cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking)) != cudaSuccess) return e;
             if ((e = cudaEventCreateWithFlags(&done_, cudaEventDisableTiming)) != cudaSuccess) return e;
             if ((e = cudaEventCreateWithFlags(&fence_, cudaEventDisableTiming)) != cudaSuccess) return e;
-            for (int t = 0; t < nthreads_; t++) workers_.emplace_back([this] { loop(); });
         } else {
             if ((e = cudaStreamSynchronize(copy_)) != cudaSuccess) return e;
             cudaFreeHost(ring_);
@@ -200,8 +208,14 @@ class HostCopier {
         busy_ = false;
         return cudaStreamSynchronize(copy_);
     }
-    // run fn(0..count-1) on the workers (and the calling thread) and wait
-    void run(size_t count, const std::function<void(size_t)> &fn) {
+    // run fn(0..count-1) on the calling thread, helped by the workers when `helpers`, and wait
+    void run(size_t count, bool helpers, const std::function<void(size_t)> &fn) {
+        if (!helpers) {
+            for (size_t i = 0; i < count; i++) fn(i);
+            return;
+        }
+        if (workers_.empty())
+            for (int t = 0; t < nthreads_; t++) workers_.emplace_back([this] { loop(); });
         {
             std::lock_guard<std::mutex> lk(mu_);
             job_ = &fn;

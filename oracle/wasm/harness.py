@@ -60,10 +60,13 @@ def parse_meta(path: str) -> dict:
 
 
 def run(circuit: str, k: int, seed: int, hot: str | None = None, threads: int | None = None, record: bool = False,
-        timeout: int = 1800, keep: str | None = None) -> tuple[dict, dict]:
-    """-> (meta, stats): meta as parse_meta, stats the harness's JSON line (times inside the dispatched calls)."""
+        timeout: int = 1800, keep: str | None = None, repeat: int = 0) -> tuple[dict, dict]:
+    """-> (meta, stats): meta as parse_meta, stats the harness's JSON line (times inside the dispatched calls).
+    repeat > 0 proves that many more times in the same process (same random stream; the harness insists on identical
+    bytes) and reports the last repeat's hot-path time as steady_*."""
     idx, inp = CIRCUITS[circuit]
     env = dict(os.environ)
+    env["WASMRUN_REPEAT"] = str(repeat)
     env["WASMRUN_RECORD"] = "1" if record else "0"
     if hot == "gpu":
         env["WASMRUN_HOT"] = "gpu:" + LIB_GPU

@@ -135,6 +135,7 @@ struct VM {
     double hot_msm_s = 0, hot_fft_s = 0, srs_register_s = 0;
     u64 hot_msm_calls = 0, hot_fft_calls = 0, hot_msm_points = 0, srs_registered = 0;
     bool record_io = true;
+    bool trace_hot = getenv("WASMRUN_TRACE") != nullptr;  // one stderr line per dispatched call
 
     // ---- JS heap (mirrors halo2_prover.js:3-46)
     void heap_init() {
@@ -410,6 +411,7 @@ struct VM {
                         const double t0 = now_s();
                         rc = gpu_commit(it->second, c.data(), n, res);
                         hot_msm_s += now_s() - t0;
+                        if (trace_hot) fprintf(stderr, "hot commit n=%zu %.3f ms\n", (size_t)n, (now_s() - t0) * 1e3);
                     } else {
                         const double t0 = now_s();
                         rc = gpu_msm(c.data(), b.data(), n, res);
@@ -457,6 +459,7 @@ struct VM {
                 }
                 hot_fft_s += now_s() - t0;
                 hot_fft_calls++;
+                if (trace_hot) fprintf(stderr, "hot fft log_n=%u %.3f ms\n", logn, (now_s() - t0) * 1e3);
                 memcpy(&m.mem[a], buf.data(), (size_t)len * 32);
                 sp -= 4;
             }
@@ -1020,6 +1023,7 @@ int main(int argc, char **argv) {
 
         // wasm_generate_proof(params, s, circuit) -> proof bytes
         std::vector<u8> sbytes(input.begin(), input.end());
+        const u64 rng_before_prove = vm.rng;
         u32 p0 = pass_bytes(vm, params), p1 = pass_bytes(vm, sbytes);
         h = (u32)call_export(vm, "wasm_generate_proof", {p0, (u64)params.size(), p1, (u64)sbytes.size(), circuit});
         std::vector<u8> proof = take_u8arr(vm, h);
@@ -1028,6 +1032,36 @@ int main(int argc, char **argv) {
         vm.rec.put32(11); vm.rec.put32((u32)proof.size()); vm.rec.bytes(proof.data(), proof.size());
         u64 msm_prove = vm.n_msm, fft_prove = vm.n_fft;
         const double hot_msm_prove = vm.hot_msm_s, hot_fft_prove = vm.hot_fft_s, t_after_prove = VM::now_s();
+
+        // WASMRUN_REPEAT=n: prove again n times in the same process from the same random stream.  Every repeat must write
+        // the same bytes; the last one's time inside the dispatched calls is the steady state of a prover that stays up
+        // (device kernels loaded, workspace and twiddle tables allocated, SRS registered).
+        const int repeat = getenv("WASMRUN_REPEAT") ? atoi(getenv("WASMRUN_REPEAT")) : 0;
+        double steady_msm = 0, steady_fft = 0, steady_prove_s = 0;
+        if (repeat > 0) {
+            const bool rec_io = vm.record_io;
+            const u64 rng_after = vm.rng, n_msm0 = vm.n_msm, n_fft0 = vm.n_fft;
+            vm.record_io = false;
+            for (int r = 0; r < repeat; r++) {
+                vm.rng = rng_before_prove;
+                const double m0 = vm.hot_msm_s, f0 = vm.hot_fft_s, t0 = VM::now_s();
+                p0 = pass_bytes(vm, params);
+                p1 = pass_bytes(vm, sbytes);
+                h = (u32)call_export(vm, "wasm_generate_proof", {p0, (u64)params.size(), p1, (u64)sbytes.size(), circuit});
+                if (take_u8arr(vm, h) != proof) throw Trap("repeat proof differs from the first proof");
+                steady_msm = vm.hot_msm_s - m0;
+                steady_fft = vm.hot_fft_s - f0;
+                steady_prove_s = VM::now_s() - t0;
+            }
+            // leave the state the verifier and the totals see as after the first proof
+            vm.hot_msm_s = hot_msm_prove;
+            vm.hot_fft_s = hot_fft_prove;
+            vm.rng = rng_after;
+            vm.n_msm = n_msm0;
+            vm.n_fft = n_fft0;
+            vm.record_io = rec_io;
+        }
+        const double t_before_verify = VM::now_s();
 
         // wasm_verify_proof(params, proof, s, circuit) -> bool  (the reference verifier)
         p0 = pass_bytes(vm, params);
@@ -1045,11 +1079,13 @@ int main(int argc, char **argv) {
         printf("{\"hot\": \"%s\", \"k\": %u, \"circuit\": %u, \"verify_ok\": %u, \"setup_s\": %.3f, \"prove_s\": %.3f, "
                "\"verify_s\": %.3f, \"msm_calls_prove\": %llu, \"fft_calls_prove\": %llu, \"hot_msm_ms_prove\": %.3f, "
                "\"hot_fft_ms_prove\": %.3f, \"hot_msm_ms_total\": %.3f, \"hot_fft_ms_total\": %.3f, \"msm_points_total\": %llu, "
-               "\"srs_registered\": %llu, \"srs_register_ms\": %.3f, \"cpu_threads\": %d, \"fast\": %d, \"native_checked\": %llu}\n",
+               "\"srs_registered\": %llu, \"srs_register_ms\": %.3f, \"cpu_threads\": %d, \"fast\": %d, \"native_checked\": %llu, "
+               "\"repeat\": %d, \"steady_msm_ms\": %.3f, \"steady_fft_ms\": %.3f, \"steady_prove_s\": %.3f}\n",
                vm.hot == VM::HOT_GPU ? "gpu" : (vm.hot == VM::HOT_CPU ? "cpu" : "interp"), k, circuit, ok, t_after_setup - t_start,
-               t_after_prove - t_after_setup, VM::now_s() - t_after_prove, (unsigned long long)msm_prove, (unsigned long long)fft_prove,
+               t_after_prove - t_after_setup, VM::now_s() - t_before_verify, (unsigned long long)msm_prove, (unsigned long long)fft_prove,
                hot_msm_prove * 1e3, hot_fft_prove * 1e3, vm.hot_msm_s * 1e3, vm.hot_fft_s * 1e3, (unsigned long long)vm.hot_msm_points,
-               (unsigned long long)vm.srs_registered, vm.srs_register_s * 1e3, vm.cpu_threads, vm.fast, (unsigned long long)vm.n_checked);
+               (unsigned long long)vm.srs_registered, vm.srs_register_s * 1e3, vm.cpu_threads, vm.fast, (unsigned long long)vm.n_checked,
+               repeat, steady_msm * 1e3, steady_fft * 1e3, steady_prove_s);
         return ok ? 0 : 1;
     } catch (const std::exception &e) {
         fprintf(stderr, "trap: %s\n", e.what());
