@@ -1910,7 +1910,17 @@ static int srs_part_create(const void *src, bool src_on_device, int src_device, 
     s.n = n;
     Scope sc;
     TRY(sc.begin(g->stream));
+    // H2B_TRACE=1: where the time of a registration goes (allocation calls vs kernels), one stderr line per phase
+    static const bool trace = getenv("H2B_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "h2b trace: srs n=%zu %s %.3f ms\n", n, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     cudaError_t e = cudaMalloc(&s.d, n * sizeof(Affine));
+    phase("cudaMalloc(points)");
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return fail(H2B_ERR_OOM, "cudaMalloc(srs)", e);
@@ -1920,6 +1930,7 @@ static int srs_part_create(const void *src, bool src_on_device, int src_device, 
     else if (src_device == g->device) e = cudaMemcpyAsync(s.d, from, n * sizeof(Affine), cudaMemcpyDeviceToDevice, g->stream);
     else e = cudaMemcpyPeerAsync(s.d, g->device, from, src_device, n * sizeof(Affine), g->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+    phase("copy points");
     if (e != cudaSuccess) {
         cudaFree(s.d);
         return fail(H2B_ERR_CUDA, "cudaMemcpy(srs)", e);
@@ -1940,6 +1951,7 @@ static int srs_part_create(const void *src, bool src_on_device, int src_device, 
                 cudaFree(s.comb);
                 s.comb = nullptr;
             }
+            phase("cudaMalloc(multiples table + scratch)");
             if (e == cudaSuccess) {
                 e = cudaMemsetAsync(s.comb + (count - 1), 0, sizeof(Affine), g->stream);  // the identity entry
                 msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c, W, (size_t)M * n, s.comb);
@@ -1947,7 +1959,9 @@ static int srs_part_create(const void *src, bool src_on_device, int src_device, 
                 g->launches += 2;
                 if (e == cudaSuccess) e = cudaGetLastError();
                 if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+                phase("multiples table kernels");
                 cudaFree(scratch);
+                phase("cudaFree(scratch)");
                 if (e != cudaSuccess) {
                     cudaFree(s.comb);
                     cudaFree(s.d);
@@ -1978,12 +1992,14 @@ static int srs_part_create(const void *src, bool src_on_device, int src_device, 
         const size_t bytes = (size_t)Wt * n * sizeof(Affine);
         if (bytes <= free_b / 3 && (size_t)Wt * n < (1u << 31)) {
             e = cudaMalloc(&s.table, bytes);
+            phase("cudaMalloc(window table)");
             if (e == cudaSuccess) {
                 s.tstride = t;
                 msm_precompute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, g->stream>>>(s.d, (uint32_t)n, c * t, Wt, n, s.table);
                 g->launches++;
                 e = cudaGetLastError();
                 if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+                phase("window table kernel");
                 if (e != cudaSuccess) {
                     cudaFree(s.table);
                     cudaFree(s.d);
