@@ -26,7 +26,7 @@ SYMBOLS = [
     "h2b_dev_lagrange_to_coeff_many", "h2b_dev_coeff_to_extended_many", "h2b_dev_divide_by_vanishing_poly",
     "h2b_dev_srs_register", "h2b_dev_msm", "h2b_dev_commit", "h2b_dev_commit_many", "h2b_commit_many", "h2b_srs_device_ptr", "h2b_dev_best_fft", "h2b_dev_lagrange_to_coeff",
     "h2b_dev_coeff_to_extended", "h2b_dev_extended_to_coeff", "h2b_dev_g1_fold", "h2b_dev_fixed_base_mul",
-    "h2b_set_msm_window", "h2b_srs_info", "h2b_srs_layout", "h2b_test_set_max_entries", "h2b_params_read", "h2b_set_srs_precompute", "h2b_set_srs_table_stride", "h2b_set_h2d_bandwidth", "h2b_set_e2e_chunking", "h2b_kernel_launches", "h2b_set_kernel_timing", "h2b_kernel_time_collect",
+    "h2b_set_msm_window", "h2b_srs_info", "h2b_srs_layout", "h2b_test_set_max_entries", "h2b_params_read", "h2b_params_write", "h2b_set_srs_precompute", "h2b_set_srs_table_stride", "h2b_set_h2d_bandwidth", "h2b_set_e2e_chunking", "h2b_kernel_launches", "h2b_set_kernel_timing", "h2b_kernel_time_collect",
     "h2b_test_field_op", "h2b_test_g1_add_affine", "h2b_imad_peak",
 ]
 

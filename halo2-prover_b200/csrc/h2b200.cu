@@ -2110,6 +2110,34 @@ int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k_out, uint64_t 
     *g_lagrange_handle = hl;
     return H2B_OK;
 }
+// One registered array back to host memory, whatever its layout over the devices (unified addressing: a device-to-host copy
+// needs no current-device switch).
+static int srs_read_back(const SrsSet &set, uint8_t *out) {
+    if (set.replicated || set.parts.size() == 1) {
+        CU(cudaMemcpy(out, set.parts[0].d, set.n * sizeof(Affine), cudaMemcpyDeviceToHost));
+        return H2B_OK;
+    }
+    for (const Srs &pt : set.parts)
+        CU(cudaMemcpy(out + pt.off * sizeof(Affine), pt.d, pt.n * sizeof(Affine), cudaMemcpyDeviceToHost));
+    return H2B_OK;
+}
+int h2b_params_write(uint32_t k, uint64_t g_handle, uint64_t g_lagrange_handle, const uint8_t *g2_and_s_g2, uint8_t *out, size_t len) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(ensure_ctx());
+    if (!g2_and_s_g2 || !out) return fail(H2B_ERR_ARG, "params_write: null pointer");
+    if (k > 28) return fail(H2B_ERR_ARG, "params_write: k > 28");
+    const size_t n = (size_t)1 << k;
+    if (len != 4 + 128 * n + 256) return fail(H2B_ERR_ARG, "params_write: length is not 4 + 128 * 2^k + 256");
+    auto ig = g_srs.find(g_handle), il = g_srs.find(g_lagrange_handle);
+    if (ig == g_srs.end() || il == g_srs.end()) return fail(H2B_ERR_STATE, "params_write: unknown handle");
+    if (ig->second.n != n || il->second.n != n) return fail(H2B_ERR_ARG, "params_write: a base array is not 2^k points long");
+    CU(cudaStreamSynchronize(g->stream));
+    for (int i = 0; i < 4; i++) out[i] = (uint8_t)(k >> (8 * i));
+    TRY(srs_read_back(ig->second, out + 4));
+    TRY(srs_read_back(il->second, out + 4 + 64 * n));
+    memcpy(out + 4 + 128 * n, g2_and_s_g2, 256);
+    return H2B_OK;
+}
 int h2b_srs_release(uint64_t handle) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(ensure_ctx());

@@ -61,7 +61,21 @@ class ParamsKZG:
         self.k = k.value
         self.n = 1 << k.value
         self._handles = {"g": hg.value, "g_lagrange": hl.value}
+        self.g2_and_s_g2 = bytes(data)[-256:]
         return self
+
+    def write(self, g2_and_s_g2: bytes | None = None) -> bytes:
+        """ParamsKZG::write (SerdeFormat::RawBytes): k | g | g_lagrange read back from HBM | g2 | s_g2.  The 256 bytes
+        of G2 points are the caller's (kept from read(); G2 arithmetic is not on this path)."""
+        tail = g2_and_s_g2 if g2_and_s_g2 is not None else getattr(self, "g2_and_s_g2", None)
+        assert tail is not None and len(tail) == 256, "write: 256 bytes of g2 | s_g2 are needed"
+        assert "g" in self._handles and "g_lagrange" in self._handles
+        out = np.zeros(4 + 128 * self.n + 256, dtype=np.uint8)
+        t = np.frombuffer(tail, dtype=np.uint8)
+        _ffi.check(_ffi.lib().h2b_params_write(C.c_uint32(self.k), C.c_uint64(self._handles["g"]),
+                                               C.c_uint64(self._handles["g_lagrange"]), t.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                               out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(out.size)))
+        return out.tobytes()
 
     def _commit(self, which: str, poly: np.ndarray) -> np.ndarray:
         poly = _ffi.as_u64(poly, 4)

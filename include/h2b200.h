@@ -225,6 +225,11 @@ int h2b_set_msm_window(uint32_t c);
  * k:u32 LE | g[2^k] x 64 B | g_lagrange[2^k] x 64 B | g2 128 B | s_g2 128 B.  Registers both base arrays
  * straight from the buffer and returns their handles (release each with h2b_srs_release). */
 int h2b_params_read(const uint8_t *bytes, size_t len, uint32_t *k, uint64_t *g_handle, uint64_t *g_lagrange_handle);
+/* ParamsKZG::write (same format, wasm.rs:52): the two registered base arrays (each 2^k points, e.g. built on the device
+ * by h2b_dev_fixed_base_mul + h2b_g_to_lagrange and registered with h2b_dev_srs_register) are read back from HBM into
+ * `out` (len = 4 + 128 * 2^k + 256) between the k header and the caller's 256 bytes of g2 | s_g2 (G2 arithmetic is not
+ * on this path).  h2b_params_write(h2b_params_read(bytes)) reproduces the reference's own setup() bytes. */
+int h2b_params_write(uint32_t k, uint64_t g_handle, uint64_t g_lagrange_handle, const uint8_t *g2_and_s_g2, uint8_t *out, size_t len);
 /* Geometry of a registered SRS: its length and, when it has a precomputed window table, the window
  * width, the number of windows (= bucket additions per point of a commit) and the table's size in HBM
  * (zeros when there is no table). */

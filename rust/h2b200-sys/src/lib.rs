@@ -55,6 +55,7 @@ extern "C" {
     pub fn h2b_divide_by_vanishing_poly(d: *const H2bDomain, a: *mut u64) -> c_int;
     pub fn h2b_commit_many(srs: u64, polys: *const *const u64, n: usize, m: usize, out: *mut u64) -> c_int;
     pub fn h2b_params_read(bytes: *const u8, len: usize, k: *mut u32, g: *mut u64, g_lagrange: *mut u64) -> c_int;
+    pub fn h2b_params_write(k: u32, g: u64, g_lagrange: u64, g2_and_s_g2: *const u8, out: *mut u8, len: usize) -> c_int;
     pub fn h2b_lagrange_to_coeff_many(d: *const H2bDomain, cols: *const *mut u64, m: usize) -> c_int;
     pub fn h2b_coeff_to_extended_many(d: *const H2bDomain, input: *const *const u64, out: *const *mut u64, m: usize) -> c_int;
     pub fn h2b_dev_evaluate_h(d: *const H2bDomain, a: *const c_void /* h2b_eval_h, include/h2b200.h */, values: *mut c_void, stream: *mut c_void) -> c_int;
@@ -150,6 +151,12 @@ impl Srs {
         let (mut k, mut g, mut gl) = (0u32, 0u64, 0u64);
         check(unsafe { h2b_params_read(bytes.as_ptr(), bytes.len(), &mut k, &mut g, &mut gl) }, "params_read");
         (k, Srs(g, 1 << k), Srs(gl, 1 << k))
+    }
+    /// `ParamsKZG::write` (SerdeFormat::RawBytes): k | g | g_lagrange read back from HBM | the caller's g2 | s_g2.
+    pub fn write_params(k: u32, g: &Srs, g_lagrange: &Srs, g2_and_s_g2: &[u8; 256]) -> Vec<u8> {
+        let mut out = vec![0u8; 4 + (128usize << k) + 256];
+        check(unsafe { h2b_params_write(k, g.0, g_lagrange.0, g2_and_s_g2.as_ptr(), out.as_mut_ptr(), out.len()) }, "params_write");
+        out
     }
 }
 impl Drop for Srs {

@@ -140,6 +140,8 @@ def test_params_read_from_reference_setup_bytes(name, h2b, href):
         outs = params.commit_many([sc for sc, _ in items]) if which == "g" else params.commit_lagrange_many([sc for sc, _ in items])
         for out, (_, want) in zip(outs, items):
             assert (href.g1_to_affine(out) == want).all(), (name, which)
+    # ParamsKZG::write: both arrays read back from HBM reproduce the reference's bytes
+    assert params.write() == z["params"].tobytes()
     params.release()
     for bad in (b"", b"\x04\x00\x00", z["params"].tobytes()[:-1]):
         with pytest.raises(Exception):

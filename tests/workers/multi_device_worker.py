@@ -63,6 +63,13 @@ for q in range(5):
     assert (aff(o[q]) == aff(many[q])).all(), ("dev_commit_many", q)
 assert (aff(one.cpu().numpy().view(np.uint64)) == aff(many[3])).all(), "dev_commit"
 params.release()
+# ParamsKZG::write gathers the shares of both arrays back into the reference's byte layout
+lag_bases = h2ref.random_g1(n, 4)
+params = h2b.ParamsKZG(k, bases, lag_bases)
+tail = bytes(range(256))
+blob = params.write(tail)
+assert blob == k.to_bytes(4, "little") + bases.tobytes() + lag_bases.tobytes() + tail, "sharded params write"
+params.release()
 
 # ---- replicated SRS (small): whole columns are dealt to the devices
 k = 10
