@@ -796,11 +796,11 @@ def bench_poseidon_proof(args) -> dict | None:
     out["timing"] = ("gpu_hot_ms / cpu_hot_ms: the SECOND proof of the same process (a prover that stays up: kernels loaded, "
                      "workspace, twiddle tables and SRS in place; the harness checks it writes the same bytes); "
                      "*_first_proof: the first proof of a fresh process, one-time costs inside the calls included")
-    for k in args.poseidon_k:
-        mg, sg = harness.run("poseidon", k, 4242, hot="gpu", repeat=1)
-        mc, sc = harness.run("poseidon", k, 4242, hot="cpu", repeat=1)
-        out["runs"].append({
-            "k": k, "proof_bytes": len(mg["proof"]), "proofs_identical": mg["proof"] == mc["proof"],
+    def one(circuit, k, seed):
+        mg, sg = harness.run(circuit, k, seed, hot="gpu", repeat=1)
+        mc, sc = harness.run(circuit, k, seed, hot="cpu", repeat=1)
+        return {
+            "circuit": circuit, "k": k, "proof_bytes": len(mg["proof"]), "proofs_identical": mg["proof"] == mc["proof"],
             "verified_by_reference_verifier": bool(mg["verify_ok"] == 1 and mc["verify_ok"] == 1),
             "msm_calls": sg["msm_calls_prove"], "fft_calls": sg["fft_calls_prove"],
             "gpu_hot_ms": sg["steady_msm_ms"] + sg["steady_fft_ms"], "gpu_msm_ms": sg["steady_msm_ms"],
@@ -810,7 +810,18 @@ def bench_poseidon_proof(args) -> dict | None:
             "cpu_hot_ms": sc["steady_msm_ms"] + sc["steady_fft_ms"], "cpu_msm_ms": sc["steady_msm_ms"],
             "cpu_fft_ms": sc["steady_fft_ms"],
             "cpu_hot_ms_first_proof": sc["hot_msm_ms_prove"] + sc["hot_fft_ms_prove"], "cpu_threads": sc["cpu_threads"],
-            "interpreted_rest_s": sg["steady_prove_s"] - (sg["steady_msm_ms"] + sg["steady_fft_ms"]) * 1e-3})
+            "interpreted_rest_s": sg["steady_prove_s"] - (sg["steady_msm_ms"] + sg["steady_fft_ms"]) * 1e-3}
+
+    for k in args.poseidon_k:
+        out["runs"].append(one("poseidon", k, 4242))
+    # BASELINE.json configs 1 and 2: the reference's arithmetic circuit at the size of its own end-to-end test
+    # (arithmetic_circuit.rs:333-351, k = 8, GWC) and its Collatz circuit (collatz.rs, k = 10, SHPLONK), same procedure
+    out["other_circuits"] = []
+    for circuit, k, seed in (("arithmetic", 8, 2024), ("collatz", 10, 777)):
+        try:
+            out["other_circuits"].append(one(circuit, k, seed))
+        except Exception as exc:  # noqa: BLE001 - the Poseidon runs above are the metric; keep them
+            out["other_circuits"].append({"circuit": circuit, "k": k, "error": repr(exc)})
     return out
 
 
