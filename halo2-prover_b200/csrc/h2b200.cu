@@ -1979,14 +1979,16 @@ static int srs_part_create(const void *src, bool src_on_device, int src_device, 
         uint32_t c = srs_window_for(n), W = msm_windows_for(c);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        // every t-th window power: the whole table (t = 1) when it fits a third of the free HBM, else the thinnest
-        // stride up to 4 that does (2^26 points: 51.5 GB at t = 1, 27.5 GB at t = 2 -- two such arrays stay resident)
-        // Measured on B200 (commit, ms, t = 1 / 2 / 3): 2^20 2.91 / 3.34 / 3.81, 2^22 9.59 / 10.25 / 10.72, 2^24 36.85 / 36.90 /
-        // 37.27 -- from 2^23 points the second bucket set costs 0.1 %, so the default there is half the table.
-        uint32_t t = g->srs_table_stride ? g->srs_table_stride : (n >= ((size_t)1 << 23) ? 2 : 1);
+        // every t-th window power: the whole table (t = 1) while it fits a sixth of the free HBM (2^24 points: 14 GB), else
+        // the thinnest stride up to 4 that does (2^26 points: 51.5 GB at t = 1, 27.5 GB at t = 2 -- two such arrays stay
+        // resident).  Measured on B200 (commit, ms, t = 1 / 2 / 3): 2^20 2.91 / 3.34 / 3.81, 2^22 9.59 / 10.25 / 10.72,
+        // 2^24 36.81 / 36.90 / 37.27 device-resident -- but 37.9-38.2 / 38.8 ms end to end from host memory: every copy
+        // piece of the pipelined path sorts into t times the buckets (profiles/r02_e2e_chunk_probe.txt), so the thinner
+        // table is for when HBM is short, not the default.
+        uint32_t t = g->srs_table_stride ? g->srs_table_stride : 1;
         auto table_windows = [&](uint32_t tt) { return (W + tt - 1) / tt; };
         if (!g->srs_table_stride)
-            while (t < 4 && (size_t)table_windows(t) * n * sizeof(Affine) > free_b / 3) t++;
+            while (t < 4 && (size_t)table_windows(t) * n * sizeof(Affine) > free_b / 6) t++;
         if (t > W) t = W;
         const uint32_t Wt = table_windows(t);
         const size_t bytes = (size_t)Wt * n * sizeof(Affine);

@@ -251,10 +251,11 @@ int h2b_set_srs_precompute(int enabled, uint32_t c);
 int h2b_set_h2d_bandwidth(double gbs);
 /* How much of the window table h2b_srs_register keeps: every t-th window power 2^(c*t*v) * P_i (t bucket sets per
  * commit and a Horner over their t sums at the end).  t = 1 is the whole table (one bucket set, no doubling at all);
- * t = 2 halves its HBM for one extra bucket reduction and c doublings per commit.  0 (default): 1 below 2^23 points,
- * 2 from there (measured: +0.1 % at 2^24 for 7.5 instead of 14 GB; 2^26: 27.5 instead of 51.5 GB), and more (up to 4)
- * when even that would exceed a third of the free HBM.  Applies to SRS registered after the call; results are
- * identical for every t. */
+ * t = 2 halves its HBM for one extra bucket reduction and c doublings per commit (measured at 2^24: 7.5 instead of
+ * 14 GB for +0.25 % device-resident, +2.4 % end to end from host memory, where every copy piece sorts into t times the
+ * buckets).  0 (default): the whole table while it fits a sixth of the free HBM, else the thinnest stride up to 4 that
+ * does (2^26 points: t = 2, 27.5 instead of 51.5 GB).  Applies to SRS registered after the call; results are identical
+ * for every t. */
 int h2b_set_srs_table_stride(uint32_t t);
 /* Host-buffer MSM entry points (h2b_best_multiexp, h2b_commit) split inputs of at least `min_n`
  * points into `chunks` contiguous pieces so the H2D copy of a piece overlaps the bucket accumulation
