@@ -99,3 +99,27 @@ def test_golden_vectors_c_oracle(spec, href):
     for v in g["msm"]:
         jac = href.best_multiexp(unhx(v["scalars"], 4), unhx(v["bases"], 8), 4)
         assert (href.g1_to_affine(jac) == unhx(v["affine"], 8)[0]).all()
+
+
+def test_poseidon_constants_against_the_reference_known_answers():
+    """oracle/poseidon_spec.py (the constants behind the third evaluate_h pin) against the known answers the reference
+    holds for the same generator over the Pallas base field: all 192 round constants, MDS, MDS^-1
+    (circuits/src/poseidon/primitives/fp.rs; the reference's own test p128pow5t3.rs:116-148 makes this comparison), and
+    its zcash permutation / hash vectors (primitives/test_vectors.rs:16, :420).  Fixture cut by oracle/make_poseidon_kat.py."""
+    import hashlib
+    import json
+    import os
+
+    import poseidon_spec as ps
+    from util import GOLDEN
+    kat = json.load(open(os.path.join(GOLDEN, "poseidon_pallas_kat.json")))
+    p = int(kat["modulus"], 16)
+    rc, mds, inv = ps.generate_constants(3, r_p=56, modulus=p, num_bits=kat["num_bits"])
+    hx = lambda rows: [[hex(v) for v in row] for row in rows]
+    assert len(rc) == 64 and hx(rc[:2]) == kat["round_constants_first"] and hx([rc[-1]])[0] == kat["round_constants_last"]
+    assert hashlib.sha256(",".join(hex(v) for row in rc for v in row).encode()).hexdigest() == kat["round_constants_sha256"]
+    assert hx(mds) == kat["mds"] and hx(inv) == kat["mds_inv"]
+    for v in kat["permute_vectors"]:
+        assert [hex(x) for x in ps.permute([int(x, 16) for x in v["initial"]], rc, mds, p)] == v["final"]
+    for v in kat["hash_vectors"]:
+        assert hex(ps.hash_constant_length([int(x, 16) for x in v["input"]], 3, (rc, mds, inv), p)) == v["output"]
