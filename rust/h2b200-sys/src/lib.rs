@@ -65,6 +65,27 @@ extern "C" {
     pub fn h2b_g_to_lagrange(g: *const u64, k: u32, out: *mut u64) -> c_int;
     pub fn h2b_g1_to_bytes(points: *const u64, m: usize, out: *mut u8) -> c_int;
     pub fn h2b_dev_msm(c: *const c_void, b: *const c_void, n: usize, out: *mut c_void, stream: *mut c_void) -> c_int;
+    // device-resident entry points (polynomials stay in HBM between the phases of create_proof; `stream` = a CUDA stream or null)
+    pub fn h2b_dev_srs_register(d_bases: *const c_void, n: usize, handle: *mut u64) -> c_int;
+    pub fn h2b_srs_device_ptr(srs: u64, d_bases: *mut *mut c_void, n: *mut usize) -> c_int;
+    pub fn h2b_srs_info(srs: u64, n: *mut usize, window_bits: *mut u32, windows: *mut u32, table_bytes: *mut usize) -> c_int;
+    pub fn h2b_dev_commit(srs: u64, d_coeffs: *const c_void, n: usize, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_commit_many(srs: u64, d_coeffs: *const c_void, n: usize, m: usize, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_best_fft(d_a: *mut c_void, omega: *const u64, log_n: u32, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_lagrange_to_coeff(d: *const H2bDomain, d_a: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_coeff_to_extended(d: *const H2bDomain, d_in: *const c_void, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_extended_to_coeff(d: *const H2bDomain, d_in: *const c_void, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_lagrange_to_coeff_many(d: *const H2bDomain, d_a: *mut c_void, m: usize, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_coeff_to_extended_many(d: *const H2bDomain, d_in: *const c_void, d_out: *mut c_void, m: usize, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_g1_fold(d_points: *const c_void, count: usize, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_dev_fixed_base_mul(d_scalars: *const c_void, n: usize, base: *const u64, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    // tuning (defaults are the measured optima)
+    pub fn h2b_set_msm_window(c: u32) -> c_int;
+    pub fn h2b_set_srs_precompute(enabled: c_int, c: u32) -> c_int;
+    pub fn h2b_set_srs_table_stride(t: u32) -> c_int;
+    pub fn h2b_set_h2d_bandwidth(gbs: f64) -> c_int;
+    pub fn h2b_set_e2e_chunking(chunks: u32, min_n: usize) -> c_int;
+    pub fn h2b_kernel_launches() -> u64;
 }
 
 fn check(rc: c_int, what: &str) {
