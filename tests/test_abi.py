@@ -19,6 +19,33 @@ def test_header_and_binding_agree():
     assert _header_functions() == sorted(_ffi.SYMBOLS)
 
 
+def _param_counts_header():
+    txt = open(os.path.join(ROOT, "include", "h2b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(h2b_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_rust_binding_declares_header_functions_with_the_same_arity():
+    """rust/h2b200-sys cannot be compiled in this image (no rustc): at least every `pub fn h2b_*` of its extern block
+    must name a function of the header and take as many parameters."""
+    src = open(os.path.join(ROOT, "rust", "h2b200-sys", "src", "lib.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    block = re.sub(r"/\*.*?\*/", "", block, flags=re.S)
+    block = re.sub(r"//[^\n]*", "", block)
+    decls = re.findall(r"pub fn (h2b_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->\s*[^;]+)?;", block, flags=re.S)
+    want = _param_counts_header()
+    assert len(decls) >= 40
+    for name, params in decls:
+        assert name in want, name
+        n = 0 if not params.strip() else params.count(":")
+        assert n == want[name], (name, n, want[name])
+
+
 def test_library_exports_every_symbol():
     from halo2_prover_b200 import _ffi
     L = _ffi.lib()
