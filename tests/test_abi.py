@@ -46,6 +46,28 @@ def test_rust_binding_declares_header_functions_with_the_same_arity():
         assert n == want[name], (name, n, want[name])
 
 
+def test_halo2_proofs_patch_uses_only_defined_items():
+    """The round-1 patch called helpers nothing defined.  Every `h2b200_sys::item` the patch uses must exist in the
+    crate, and every `b200_*` helper it calls must be defined by one of its own hunks."""
+    patch = open(os.path.join(ROOT, "rust", "patches", "halo2_proofs-6b43b6b.patch")).read()
+    crate = open(os.path.join(ROOT, "rust", "h2b200-sys", "src", "lib.rs")).read()
+    added = "\n".join(line[1:] for line in patch.splitlines() if line.startswith("+") and not line.startswith("+++"))
+    free_fns = set(re.findall(r"^pub fn ([a-z0-9_]+)", crate, flags=re.M))
+    types = set(re.findall(r"^pub struct ([A-Za-z0-9_]+)", crate, flags=re.M))
+    methods = set(re.findall(r"^\s+pub fn ([a-z0-9_]+)", crate, flags=re.M))
+    for path in set(re.findall(r"h2b200_sys::([A-Za-z0-9_]+(?:::[a-z0-9_]+)?)", added)):
+        head, _, tail = path.partition("::")
+        assert head in free_fns | types, path
+        if tail:
+            assert tail in methods, path
+    called = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", added))
+    defined = set(re.findall(r"fn (b200_[a-z0-9_]+)", added))
+    assert called and called <= defined, called - defined
+    for m in set(re.findall(r"\bsrs\.([a-z0-9_]+)\(|\bd\.([a-z0-9_]+)\(", added)):
+        name = m[0] or m[1]
+        assert name in methods, name
+
+
 def test_library_exports_every_symbol():
     from halo2_prover_b200 import _ffi
     L = _ffi.lib()
