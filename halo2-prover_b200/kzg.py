@@ -49,6 +49,33 @@ class ParamsKZG:
         return self
 
     @classmethod
+    def setup(cls, k: int, s: int) -> "ParamsKZG":
+        """ParamsKZG::setup(k, rng) (kzg/commitment.rs:68-114; the reference's generate_params, utils.rs:59-61) with the
+        secret scalar given instead of drawn: g[i] = [s^i] G by the per-element fixed-base multiplication on the device
+        (h2b_dev_fixed_base_mul), g_lagrange = g_to_lagrange(g) (h2b_g_to_lagrange), both registered.  The G2 half of the
+        parameters (g2, s_g2) is not on this path; write() takes those 256 bytes from the caller."""
+        import torch
+        n = 1 << k
+        r = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001   # Fr modulus
+        q = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47   # Fq modulus
+        limbs = lambda v: [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+        powers, acc = np.zeros((n, 4), dtype=np.uint64), 1
+        for i in range(n):                      # Montgomery form: s^i * 2^256 mod r
+            powers[i] = limbs(acc * (1 << 256) % r)
+            acc = acc * s % r
+        gen = np.array(limbs((1 << 256) % q) + limbs(2 * (1 << 256) % q), dtype=np.uint64)   # G = (1, 2)
+        _ffi.init()
+        d_s = torch.from_numpy(powers.view(np.int64)).cuda()
+        d_g = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        st = torch.cuda.current_stream()
+        _ffi.check(_ffi.lib().h2b_dev_fixed_base_mul(C.c_void_p(d_s.data_ptr()), C.c_size_t(n), _ffi.u64p(gen),
+                                                     C.c_void_p(d_g.data_ptr()), C.c_void_p(st.cuda_stream or 1)))
+        st.synchronize()
+        g = np.ascontiguousarray(d_g.cpu().numpy().view(np.uint64))
+        from .arithmetic import g_to_lagrange
+        return cls(k, g, g_to_lagrange(g, k))
+
+    @classmethod
     def read(cls, data) -> "ParamsKZG":
         """ParamsKZG::read (SerdeFormat::RawBytes): ``data`` is the byte string ParamsKZG::write produced
         (k | g | g_lagrange | g2 | s_g2); both base arrays are registered straight from it."""

@@ -465,3 +465,24 @@ def test_concurrent_host_threads(h2b, spec, href):
         assert (g == w).all()
     for g, w in zip(got_fft, want_fft):
         assert (g == w).all()
+
+
+def test_params_setup_vs_oracle(h2b, spec, href):
+    """ParamsKZG.setup(k, s) (the reference's generate_params with the secret given): g[i] = [s^i] G against the oracle's
+    scalar multiplication, and g_lagrange through its defining property -- the commitment of a polynomial from its
+    coefficients equals the commitment from its evaluations."""
+    k, s = 6, 0x1234567_89ABCDEF_0FEDCBA9
+    n = 1 << k
+    params = h2b.ParamsKZG.setup(k, s)
+    blob = params.write(bytes(256))
+    g = np.frombuffer(blob, dtype=np.uint64, count=8 * n, offset=4).reshape(n, 8)
+    gen = spec.affine_to_array([spec.G1_GENERATOR])[0]
+    for i in (0, 1, 2, n - 1):
+        want = href.g1_to_affine(href.g1_scalar_mul(gen, spec.fr_array([pow(s, i, spec.R_MOD)])[0]))
+        assert (g[i] == want).all(), i
+    coeffs = href.random_fr(n, 4242)
+    omega = spec.fr_array([pow(spec.ROOT_OF_UNITY, 1 << (spec.FR_S - k), spec.R_MOD)])[0]
+    evals = href.best_fft(coeffs, omega, k)
+    assert (_affine(href, params.commit(coeffs)) == _affine(href, params.commit_lagrange(evals))).all()
+    assert (_affine(href, params.commit(coeffs)) == _affine(href, href.best_multiexp(coeffs, np.ascontiguousarray(g)))).all()
+    params.release()
